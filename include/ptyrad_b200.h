@@ -1,0 +1,135 @@
+/* ptyrad_b200 -- C ABI of the B200-native multislice ptychography hot path.
+ *
+ * The reference (wdwzyyg/ptyrad, pure Python/PyTorch) has no FFI of its own: its hot path is the Python
+ * surface PtychoAD.forward -> multislice_forward_model_vec_all -> CombinedLoss.forward -> autograd.
+ * Each entry point below names the reference function(s) it replaces (file:line relative to the reference
+ * tree).  All pointers are DEVICE pointers owned by the caller (torch tensors in practice); nothing is
+ * allocated inside the library; work is enqueued on the caller's stream and the calls do not block.
+ * Return value: 0 = OK, non-zero = error, text via ptyb200_last_error().
+ *
+ * Complex arrays are interleaved (re,im) float32 pairs ("float2").
+ */
+#ifndef PTYRAD_B200_H
+#define PTYRAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTYB200_ABI_VERSION 1
+
+/* cudaStream_t without pulling in the CUDA headers */
+typedef void* ptyb200_stream;
+
+/* bits of `need_mask` (which gradients the caller wants; mirrors requires_grad, reconstruction.py:783-790) */
+#define PTYB200_NEED_OBJ     1u   /* obja + objp */
+#define PTYB200_NEED_PROBE   2u
+#define PTYB200_NEED_SHIFTS  4u
+#define PTYB200_NEED_TILTS   8u
+#define PTYB200_NEED_DZ     16u
+
+/* code paths (ptyb200_cfg.path) */
+#define PTYB200_PATH_AUTO    0    /* fused on-chip kernels where available (N == 128), else general */
+#define PTYB200_PATH_GENERAL 1    /* row/column-pass kernels, any supported N */
+#define PTYB200_PATH_FUSED   2    /* fail if the fused kernels do not cover this configuration */
+
+typedef struct ptyb200_cfg {
+    int32_t N;             /* pattern = probe = ROI size in px (square, even; supported: 16,32,48,64,96,128,192,256) */
+    int32_t P;             /* probe modes   */
+    int32_t M;             /* object modes  */
+    int32_t Z;             /* slices        */
+    int32_t Noy, Nox;      /* object canvas */
+    int32_t Ntot;          /* scan positions (rows of crop_pos / shifts / measurements) */
+    int32_t shift_probes;  /* 1: sub-pixel Fourier shift of the probe per position (models.py:120,294-295) */
+    int32_t tilt_mode;     /* 0: propagator shared by all positions; 1: one global tilt (1,2); 2: per-position (Ntot,2) */
+    int32_t stash_fourier; /* 1: keep the Fourier-domain waves so tilt / thickness gradients can be formed */
+    int32_t path;          /* PTYB200_PATH_* */
+    int32_t reserved[5];
+    float   dx;            /* real-space pixel size (propagator k-grid, models.py:164-171) */
+    float   lambd;         /* wavelength (Kz, models.py:222-223) */
+    float   eps;           /* added to the intensities after the mode sum (forward.py:79); reference: 1e-10 */
+    float   reserved_f;
+} ptyb200_cfg;
+
+typedef struct ptyb200_loss_cfg {
+    /* CombinedLoss terms computed natively (losses.py:36-104); state 0 => term is 0 */
+    int32_t single_state;  float single_weight;  float single_pow;                   /* losses.py:36-50  */
+    int32_t poissn_state;  float poissn_weight;  float poissn_pow;  float poissn_eps; /* losses.py:52-75  */
+    int32_t pacbed_state;  float pacbed_weight;  float pacbed_pow;                   /* losses.py:77-89  */
+    int32_t sparse_state;  float sparse_weight;  float sparse_order;                 /* losses.py:91-104 */
+} ptyb200_loss_cfg;
+
+int         ptyb200_abi_version(void);
+const char* ptyb200_last_error(void);
+
+/* Bytes of caller-owned scratch one forward/backward pair of batch size B needs (wave stash for the
+ * adjoint, transposed wave buffers, complex object, gradient scratch).  One workspace per in-flight
+ * forward: the LBFGS closure (reconstruction.py:705-718) keeps several alive. */
+size_t ptyb200_workspace_bytes(const ptyb200_cfg* cfg, int32_t B);
+
+/* H = exp(i*dz*Kz) on the half-bin-shifted grid, evaluated in float64 and rounded once
+ * (replaces the float32 torch.exp(1j*dz*Kz) of models.py:341,355; Kz from models.py:222-223). */
+int ptyb200_propagator(const ptyb200_cfg* cfg, const float* dz, float* H_out /* (N,N) float2 */, ptyb200_stream s);
+
+/* Bit-exact ROI gather (models.py:251-265): patches[b,m,z,y,x,{a,phi}] = obj{a,p}[m,z,crop[idx[b]].y+y, crop[idx[b]].x+x] */
+int ptyb200_gather_patches(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                           const int32_t* crop_pos, float* patches_out, ptyb200_stream s);
+
+/* PtychoAD.forward (models.py:422-436) = get_obj_ROI + get_probes (image_proc.py:495-537) + get_propagators
+ * (models.py:300-360) + multislice_forward_model_vec_all (forward.py:20-80).
+ *   idx      (B)            int64   scan indices of the batch
+ *   obja,objp(M,Z,Noy,Nox)  float32 amplitude / phase
+ *   crop_pos (Ntot,2)       int32   ROI top-left (y,x)
+ *   probe    (P,N,N)        float2
+ *   shifts   (Ntot,2)       float32 sub-pixel (y,x) shifts; may be NULL iff !shift_probes
+ *   Hbase    (N,N)          float2  propagator for zero tilt (model.H, or ptyb200_propagator output)
+ *   tilts    (1|Ntot,2)     float32 mrad (y,x); NULL iff tilt_mode == 0
+ *   dz       scalar         float32 slice thickness (device; used by the tilt ramp only)
+ *   occu     (M)            float32
+ *   dp_out   (B,N,N)        float32 fftshifted intensities + eps
+ */
+int ptyb200_forward(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                    const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                    const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
+                    ptyb200_stream s);
+
+/* Adjoint of ptyb200_forward (what torch autograd derives for the reference).  Must follow
+ * a forward on the same workspace with the same inputs.  G = dL/d(dp) (B,N,N).  Gradient outputs are DENSE
+ * and are OVERWRITTEN (zero-filled where no pattern contributes), as the reference's .grad tensors are:
+ *   g_obja,g_objp (M,Z,Noy,Nox); g_probe (P,N,N) float2; g_shifts (Ntot,2); g_tilts (1|Ntot,2); g_dz scalar.
+ * Outputs whose bit is absent from need_mask may be NULL and cost nothing. */
+int ptyb200_backward(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                     const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                     const float* tilts, const float* dz, const float* occu, const float* G, void* workspace,
+                     float* g_obja, float* g_objp, float* g_probe, float* g_shifts, float* g_tilts, float* g_dz,
+                     uint32_t need_mask, ptyb200_stream s);
+
+/* CombinedLoss data terms (losses.py:36-89) on the batch: losses3 = {single, poissn, pacbed} (device floats).
+ * `stats` is 8 doubles of caller-owned device memory kept for ptyb200_loss_grad.  meas_all is the full
+ * (Ntot,N,N) measurement array; rows idx[b] are read in place (no gathered copy; models.py:399). */
+int ptyb200_loss_forward(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
+                         const int64_t* idx, int32_t B, float* losses3, double* stats, float* pacbed_scratch /* 2*N*N */,
+                         ptyb200_stream s);
+
+/* G = sum_t upstream[t] * d(loss_t)/d(dp), t over {single, poissn, pacbed}; upstream = 3 device floats. */
+int ptyb200_loss_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
+                      const int64_t* idx, int32_t B, const double* stats, const float* pacbed_scratch,
+                      const float* upstream3, float* G_out, ptyb200_stream s);
+
+/* loss_sparse (losses.py:91-104) evaluated on the ROIs without materialising the patches:
+ * loss = weight * sum_m occu_m * (mean_{b,z,y,x} |phi_patch|^n)^(1/n);  Ssum (M doubles) kept for the gradient. */
+int ptyb200_sparse_forward(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
+                           const int64_t* idx, int32_t B, const float* occu, float* loss_out, double* Ssum, ptyb200_stream s);
+
+/* g_objp (dense, += ) gets upstream * d(loss_sparse)/d(objp); cover_scratch = Noy*Nox int32 of scratch. */
+int ptyb200_sparse_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
+                        const int64_t* idx, int32_t B, const float* occu, const double* Ssum, const float* upstream,
+                        int32_t* cover_scratch, float* g_objp, ptyb200_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTYRAD_B200_H */

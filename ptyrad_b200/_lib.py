@@ -1,0 +1,83 @@
+"""ctypes binding of ``libptyrad_b200.so`` (C ABI declared in ``include/ptyrad_b200.h``).
+
+The library is the product: there is no Python/torch fallback for the hot path.  ``lib()`` raises if the
+shared object is missing, and every call raises ``RuntimeError`` with ``ptyb200_last_error()`` on failure.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libptyrad_b200.so")
+ABI_VERSION = 1
+
+NEED_OBJ, NEED_PROBE, NEED_SHIFTS, NEED_TILTS, NEED_DZ = 1, 2, 4, 8, 16
+PATH_AUTO, PATH_GENERAL, PATH_FUSED = 0, 1, 2
+SUPPORTED_N = (16, 32, 48, 64, 96, 128, 192, 256)
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("P", C.c_int32), ("M", C.c_int32), ("Z", C.c_int32),
+        ("Noy", C.c_int32), ("Nox", C.c_int32), ("Ntot", C.c_int32),
+        ("shift_probes", C.c_int32), ("tilt_mode", C.c_int32), ("stash_fourier", C.c_int32),
+        ("path", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("dx", C.c_float), ("lambd", C.c_float), ("eps", C.c_float), ("reserved_f", C.c_float),
+    ]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [
+        ("single_state", C.c_int32), ("single_weight", C.c_float), ("single_pow", C.c_float),
+        ("poissn_state", C.c_int32), ("poissn_weight", C.c_float), ("poissn_pow", C.c_float), ("poissn_eps", C.c_float),
+        ("pacbed_state", C.c_int32), ("pacbed_weight", C.c_float), ("pacbed_pow", C.c_float),
+        ("sparse_state", C.c_int32), ("sparse_weight", C.c_float), ("sparse_order", C.c_float),
+    ]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "ptyb200_abi_version": (C.c_int, []),
+    "ptyb200_last_error": (C.c_char_p, []),
+    "ptyb200_workspace_bytes": (C.c_size_t, [C.POINTER(Cfg), C.c_int32]),
+    "ptyb200_propagator": (C.c_int, [C.POINTER(Cfg), _P, _P, _P]),
+    "ptyb200_gather_patches": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, _P, _P]),
+    "ptyb200_forward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 12),
+    "ptyb200_backward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 17 + [C.c_uint32, _P]),
+    "ptyb200_loss_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "ptyb200_loss_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    "ptyb200_sparse_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "ptyb200_sparse_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; raise loudly if it is not built (run ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with ptyrad_b200.build.build_library(); "
+                               "there is no CPU or torch fallback for the multislice hot path")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        v = h.ptyb200_abi_version()
+        if v != ABI_VERSION:
+            raise RuntimeError(f"libptyrad_b200 ABI {v} != expected {ABI_VERSION}; rebuild the library")
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("ptyrad_b200: " + lib().ptyb200_last_error().decode())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,357 @@
+// C ABI of libptyrad_b200.so (see include/ptyrad_b200.h).  Host-side sequencing of the kernels; no allocation,
+// no synchronisation: everything is enqueued on the caller's stream.
+#include "../../include/ptyrad_b200.h"
+#include "general_kernels.cuh"
+#include "fused128.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace ptyb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* what, cudaError_t e, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    g_err = buf;
+    return 1;
+}
+int fail_msg(const std::string& m) { g_err = m; return 2; }
+
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return fail(#call, e_, __FILE__, __LINE__); \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Workspace {
+    float2 *O, *gO, *PhatT, *tmpP, *gPhatT, *HT, *wvec, *tvec, *stash, *phis, *G1, *G2, *farT;
+    float* gprop;
+    unsigned char* fused;      // scratch owned by the fused path
+    size_t total;
+};
+
+Workspace carve(const ptyb200_cfg& c, int B, void* base) {
+    Workspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return reinterpret_cast<unsigned char*>(base) + o; };
+    const size_t NN = (size_t)c.N * c.N, obj = (size_t)c.M * c.Z * c.Noy * c.Nox, tiles = (size_t)B * c.P * c.M;
+    w.O = (float2*)take(obj * 8);
+    w.gO = (float2*)take(obj * 8);
+    w.PhatT = (float2*)take(c.P * NN * 8);
+    w.tmpP = (float2*)take(c.P * NN * 8);
+    w.gPhatT = (float2*)take(c.P * NN * 8);
+    w.HT = (float2*)take(NN * 8);
+    w.wvec = (float2*)take((size_t)B * 2 * c.N * 8);
+    w.tvec = (float2*)take((size_t)B * 2 * c.N * 8);
+    w.gprop = (float*)take((size_t)B * 3 * 4);
+    w.stash = (float2*)take(tiles * c.Z * NN * 8);
+    w.phis = (float2*)take(c.stash_fourier ? tiles * (c.Z > 1 ? c.Z - 1 : 0) * NN * 8 : 0);
+    w.G1 = (float2*)take(tiles * NN * 8);
+    w.G2 = (float2*)take(tiles * NN * 8);
+    w.farT = (float2*)take(tiles * NN * 8);
+    w.fused = take(fused128::scratch_bytes(c, B));
+    w.total = off;
+    return w;
+}
+
+bool supported_N(int N) { return N == 16 || N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192 || N == 256; }
+
+int check_cfg(const ptyb200_cfg* c, int B) {
+    if (!c) return fail_msg("cfg is NULL");
+    if (!supported_N(c->N)) return fail_msg("unsupported N=" + std::to_string(c->N) + " (supported: 16,32,48,64,96,128,192,256)");
+    if (c->P < 1 || c->M < 1 || c->Z < 1 || B < 1) return fail_msg("P, M, Z and B must be >= 1");
+    if (c->Noy < c->N || c->Nox < c->N) return fail_msg("object canvas smaller than the probe");
+    if (c->tilt_mode < 0 || c->tilt_mode > 2) return fail_msg("tilt_mode must be 0, 1 or 2");
+    return 0;
+}
+
+#define DISPATCH_N(N_, ...)                                                              \
+    switch (N_) {                                                                         \
+        case 16:  { using F = RowFFT<4, 4>;   __VA_ARGS__; } break;                       \
+        case 32:  { using F = RowFFT<8, 4>;   __VA_ARGS__; } break;                       \
+        case 48:  { using F = RowFFT<8, 6>;   __VA_ARGS__; } break;                       \
+        case 64:  { using F = RowFFT<8, 8>;   __VA_ARGS__; } break;                       \
+        case 96:  { using F = RowFFT<12, 8>;  __VA_ARGS__; } break;                       \
+        case 128: { using F = RowFFT<16, 8>;  __VA_ARGS__; } break;                       \
+        case 192: { using F = RowFFT<16, 12>; __VA_ARGS__; } break;                       \
+        case 256: { using F = RowFFT<16, 16>; __VA_ARGS__; } break;                       \
+        default: return fail_msg("unsupported N");                                        \
+    }
+
+template <class K> cudaError_t prep(K kern, size_t bytes) {
+    return bytes > 48 * 1024 ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+}
+
+#define LAUNCH(kern, grid, stream, ...)                                   \
+    do {                                                                  \
+        const size_t sm_ = Slab<F>::smem_bytes();                         \
+        CK(prep(kern, sm_));                                              \
+        kern<<<grid, NT, sm_, stream>>>(__VA_ARGS__);                     \
+        CKL();                                                            \
+    } while (0)
+
+template <class F> int fft2_tiles(const float2* in, float2* tmp, float2* out, int count, int dir, cudaStream_t st) {
+    dim3 g(F::N / ROWS, count);
+    if (dir < 0) {
+        LAUNCH((k_pass<F, -1, true>), g, st, in, tmp, 1.0f);
+        LAUNCH((k_pass<F, -1, false>), g, st, tmp, out, 1.0f);
+    } else {
+        LAUNCH((k_pass<F, +1, true>), g, st, in, tmp, 1.0f);
+        LAUNCH((k_pass<F, +1, false>), g, st, tmp, out, 1.0f);
+    }
+    return 0;
+}
+
+FwdArgs make_fwd_args(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const int32_t* crop, const float* probe,
+                      const float* occu, float* dp) {
+    FwdArgs a;
+    a.d = Dims{c.N, c.P, c.M, c.Z, c.Noy, c.Nox, B};
+    a.idx = idx; a.crop = crop; a.O = w.O; a.probe = (const float2*)probe; a.PhatT = w.PhatT; a.HT = w.HT;
+    a.wvec = c.shift_probes ? w.wvec : nullptr;
+    a.tvec = c.tilt_mode ? w.tvec : nullptr;
+    a.occu = occu; a.stash = w.stash; a.phis = c.stash_fourier && c.Z > 1 ? w.phis : nullptr;
+    a.G1 = w.G1; a.G2 = w.G2; a.farT = w.farT; a.dp = dp; a.eps = c.eps;
+    return a;
+}
+
+bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && fused128::covers(c); }
+
+// shared setup: complex object, transposed propagator, probe spectrum, per-sample ramps
+template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const float* obja,
+                                    const float* objp, const float* probe, const float* shifts, const float* Hbase,
+                                    const float* tilts, const float* dz, cudaStream_t st) {
+    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
+    CKL();
+    dim3 tb(32, 8), tg((c.N + 31) / 32, (c.N + 31) / 32);
+    k_transpose<<<tg, tb, 0, st>>>((const float2*)Hbase, w.HT, c.N);
+    CKL();
+    if (c.shift_probes) {
+        if (!shifts) return fail_msg("shift_probes set but shifts is NULL");
+        if (int r = fft2_tiles<F>((const float2*)probe, w.tmpP, w.PhatT, c.P, -1, st)) return r;
+        k_shift_vectors<<<B, 128, 0, st>>>(shifts, idx, B, c.N, w.wvec);
+        CKL();
+    }
+    if (c.tilt_mode) {
+        if (!tilts || !dz) return fail_msg("tilt_mode set but tilts/dz is NULL");
+        k_tilt_vectors<<<B, 128, 0, st>>>(tilts, c.tilt_mode, idx, B, c.N, c.dx, dz, w.tvec);
+        CKL();
+    }
+    return 0;
+}
+
+template <class F> int forward_general(const ptyb200_cfg& c, int B, const Workspace& w, FwdArgs a, cudaStream_t st) {
+    const int nb = c.N / ROWS;
+    if (c.shift_probes) LAUNCH((k_init_shift<F>), dim3(nb, B), st, a);
+    for (int z = 0; z < c.Z; ++z) {
+        const int src_mode = (z == 0 && !c.shift_probes) ? 1 : 0;
+        LAUNCH((k_fwd_da<F>), dim3(nb, c.M, B), st, a, z, src_mode, z == c.Z - 1 ? 1 : 0);
+        if (z < c.Z - 1) LAUNCH((k_fwd_bc<F>), dim3(nb, c.M, B), st, a, z);
+    }
+    LAUNCH((k_fwd_final<F>), dim3(nb, B), st, a);
+    return 0;
+}
+
+template <class F> int backward_general(const ptyb200_cfg& c, int B, const Workspace& w, BwdArgs a, float* g_probe, cudaStream_t st) {
+    const int nb = c.N / ROWS;
+    const bool want_p = a.need_probe || a.need_shift;
+    LAUNCH((k_bwd_start<F>), dim3(nb, c.M, B), st, a);
+    for (int z = c.Z - 1; z >= 0; --z) {
+        int out_mode = 0;
+        if (z == 0) out_mode = want_p ? (c.shift_probes ? 0 : 1) : 2;
+        LAUNCH((k_bwd_da<F>), dim3(nb, c.M, B), st, a, z, out_mode);
+        if (z > 0) LAUNCH((k_bwd_bc<F>), dim3(nb, c.M, B), st, a, z);
+    }
+    if (want_p) {
+        if (c.shift_probes) {
+            int per = nb * c.P;
+            int nchunk = (296 + per - 1) / per;
+            if (nchunk > B) nchunk = B;
+            if (nchunk < 1) nchunk = 1;
+            int bchunk = (B + nchunk - 1) / nchunk;
+            nchunk = (B + bchunk - 1) / bchunk;
+            LAUNCH((k_bwd_probe<F>), dim3(nb, c.P, nchunk), st, a, bchunk);
+            if (a.need_probe)
+                if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c.P, +1, st)) return r;
+        } else if (a.need_probe) {
+            k_bwd_probe_noshift<<<dim3((c.N * c.N + 255) / 256, c.P), 256, 0, st>>>(a.f.d, w.G1, (float2*)g_probe);
+            CKL();
+        }
+    }
+    return 0;
+}
+
+LossK make_lossk(const ptyb200_loss_cfg& l) {
+    LossK k;
+    k.s_on = l.single_state; k.s_w = l.single_weight; k.s_p = l.single_pow;
+    k.p_on = l.poissn_state; k.p_w = l.poissn_weight; k.p_p = l.poissn_pow; k.p_eps = l.poissn_eps;
+    k.b_on = l.pacbed_state; k.b_w = l.pacbed_weight; k.b_p = l.pacbed_pow;
+    return k;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptyb200_abi_version(void) { return PTYB200_ABI_VERSION; }
+const char* ptyb200_last_error(void) { return g_err.c_str(); }
+
+size_t ptyb200_workspace_bytes(const ptyb200_cfg* cfg, int32_t B) {
+    if (check_cfg(cfg, B)) return 0;
+    return carve(*cfg, B, nullptr).total;
+}
+
+int ptyb200_propagator(const ptyb200_cfg* c, const float* dz, float* H_out, ptyb200_stream s) {
+    if (!c || !dz || !H_out) return fail_msg("NULL argument");
+    k_propagator<<<(c->N * c->N + 255) / 256, 256, 0, (cudaStream_t)s>>>(c->N, c->dx, c->lambd, dz, (float2*)H_out);
+    CKL();
+    return 0;
+}
+
+int ptyb200_gather_patches(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                           const int32_t* crop_pos, float* patches_out, ptyb200_stream s) {
+    if (!c || !idx || !obja || !objp || !crop_pos || !patches_out) return fail_msg("NULL argument");
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
+    dim3 g((c->N * c->N + 1023) / 1024, c->M * c->Z, B);
+    k_gather_patches<<<g, 256, 0, (cudaStream_t)s>>>(d, idx, obja, objp, crop_pos, patches_out);
+    CKL();
+    return 0;
+}
+
+int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                    const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                    const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
+                    ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!idx || !obja || !objp || !crop_pos || !probe || !Hbase || !occu || !dp_out || !workspace) return fail_msg("NULL argument");
+    cudaStream_t st = (cudaStream_t)s;
+    Workspace w = carve(*c, B, workspace);
+    FwdArgs a = make_fwd_args(*c, B, w, idx, crop_pos, probe, occu, dp_out);
+    if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
+    DISPATCH_N(c->N, {
+        if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
+        if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, w.fused, st, g_err)) return r; }
+        else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
+    });
+    return 0;
+}
+
+int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                     const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                     const float* tilts, const float* dz, const float* occu, const float* G, void* workspace,
+                     float* g_obja, float* g_objp, float* g_probe, float* g_shifts, float* g_tilts, float* g_dz,
+                     uint32_t need_mask, ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!idx || !obja || !objp || !crop_pos || !probe || !Hbase || !occu || !G || !workspace) return fail_msg("NULL argument");
+    cudaStream_t st = (cudaStream_t)s;
+    Workspace w = carve(*c, B, workspace);
+    BwdArgs a;
+    a.f = make_fwd_args(*c, B, w, idx, crop_pos, probe, occu, nullptr);
+    a.G = G; a.gO = w.gO; a.gPhatT = w.gPhatT; a.gprop = w.gprop; a.gshift = g_shifts;
+    a.dx = c->dx; a.k0 = 6.283185307179586f / c->lambd;
+    a.need_obj = (need_mask & PTYB200_NEED_OBJ) ? 1 : 0;
+    a.need_probe = (need_mask & PTYB200_NEED_PROBE) ? 1 : 0;
+    a.need_shift = ((need_mask & PTYB200_NEED_SHIFTS) && c->shift_probes) ? 1 : 0;
+    const bool need_t = (need_mask & PTYB200_NEED_TILTS) != 0, need_dz = (need_mask & PTYB200_NEED_DZ) != 0;
+    a.need_prop = ((need_t || need_dz) && c->Z > 1) ? 1 : 0;
+    if (a.need_obj && (!g_obja || !g_objp)) return fail_msg("g_obja/g_objp is NULL");
+    if (a.need_probe && !g_probe) return fail_msg("g_probe is NULL");
+    if ((need_mask & PTYB200_NEED_SHIFTS) && !g_shifts) return fail_msg("g_shifts is NULL");
+    if (need_t && (!g_tilts || !c->tilt_mode)) return fail_msg("tilt gradient requested without tilts");
+    if (need_dz && !g_dz) return fail_msg("g_dz is NULL");
+    if (a.need_prop && !c->stash_fourier) return fail_msg("tilt/thickness gradients need cfg.stash_fourier = 1 in the forward");
+    const size_t obj = (size_t)c->M * c->Z * c->Noy * c->Nox;
+    if (a.need_obj) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
+    if (a.need_probe && c->shift_probes) CK(cudaMemsetAsync(w.gPhatT, 0, (size_t)c->P * c->N * c->N * 8, st));
+    if (need_mask & PTYB200_NEED_SHIFTS) CK(cudaMemsetAsync(g_shifts, 0, (size_t)c->Ntot * 2 * 4, st));
+    if (need_t || need_dz) CK(cudaMemsetAsync(w.gprop, 0, (size_t)B * 3 * 4, st));
+    if (need_t) CK(cudaMemsetAsync(g_tilts, 0, (size_t)(c->tilt_mode == 2 ? c->Ntot : 1) * 2 * 4, st));
+    if (need_dz) CK(cudaMemsetAsync(g_dz, 0, 4, st));
+    if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
+    DISPATCH_N(c->N, {
+        if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, w.fused, (float2*)g_probe, w.tmpP, st, g_err)) return r; }
+        else if (int r = backward_general<F>(*c, B, w, a, g_probe, st)) return r;
+        if (use_fused(*c) && a.need_probe && c->shift_probes)
+            if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, st)) return r;
+    });
+    if (a.need_obj) {
+        k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj);
+        CKL();
+    }
+    if (a.need_prop) {
+        k_prop_finish<<<1, 256, 0, st>>>(w.gprop, tilts, c->tilt_mode, idx, B, dz, need_t ? g_tilts : nullptr, need_dz ? g_dz : nullptr);
+        CKL();
+    }
+    return 0;
+}
+
+int ptyb200_loss_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
+                         const int64_t* idx, int32_t B, float* losses3, double* stats, float* pac, ptyb200_stream s) {
+    if (!c || !lc || !dp || !meas_all || !idx || !losses3 || !stats) return fail_msg("NULL argument");
+    if (lc->pacbed_state && !pac) return fail_msg("pacbed needs pacbed_scratch");
+    cudaStream_t st = (cudaStream_t)s;
+    LossK k = make_lossk(*lc);
+    CK(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
+    if (k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
+    size_t tot = (size_t)B * c->N * c->N;
+    unsigned blocks = (unsigned)((tot + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_loss_partial<<<blocks, 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac);
+    CKL();
+    k_loss_final<<<1, 256, 0, st>>>(k, B, c->N, stats, pac, losses3);
+    CKL();
+    return 0;
+}
+
+int ptyb200_loss_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
+                      const int64_t* idx, int32_t B, const double* stats, const float* pac, const float* upstream3,
+                      float* G_out, ptyb200_stream s) {
+    if (!c || !lc || !dp || !meas_all || !idx || !stats || !upstream3 || !G_out) return fail_msg("NULL argument");
+    cudaStream_t st = (cudaStream_t)s;
+    LossK k = make_lossk(*lc);
+    size_t tot = (size_t)B * c->N * c->N;
+    unsigned blocks = (unsigned)((tot + 256 * 4 - 1) / (256 * 4));
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_loss_grad<<<blocks, 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac, upstream3, G_out);
+    CKL();
+    return 0;
+}
+
+int ptyb200_sparse_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
+                           const int64_t* idx, int32_t B, const float* occu, float* loss_out, double* Ssum, ptyb200_stream s) {
+    if (!c || !lc || !objp || !crop_pos || !idx || !occu || !loss_out || !Ssum) return fail_msg("NULL argument");
+    cudaStream_t st = (cudaStream_t)s;
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
+    CK(cudaMemsetAsync(Ssum, 0, sizeof(double) * c->M, st));
+    dim3 g((c->N * c->N + 2047) / 2048, c->M * c->Z, B);
+    k_sparse_partial<<<g, 256, 0, st>>>(d, lc->sparse_order, objp, crop_pos, idx, Ssum);
+    CKL();
+    k_sparse_final<<<1, 32, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, occu, Ssum, loss_out);
+    CKL();
+    return 0;
+}
+
+int ptyb200_sparse_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
+                        const int64_t* idx, int32_t B, const float* occu, const double* Ssum, const float* upstream,
+                        int32_t* cover, float* g_objp, ptyb200_stream s) {
+    if (!c || !lc || !objp || !crop_pos || !idx || !occu || !Ssum || !upstream || !cover || !g_objp) return fail_msg("NULL argument");
+    cudaStream_t st = (cudaStream_t)s;
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
+    CK(cudaMemsetAsync(cover, 0, (size_t)c->Noy * c->Nox * 4, st));
+    k_cover<<<dim3((c->N * c->N + 1023) / 1024, B), 256, 0, st>>>(d, crop_pos, idx, cover);
+    CKL();
+    size_t n = (size_t)c->M * c->Z * c->Noy * c->Nox;
+    k_sparse_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, objp, occu, Ssum, upstream, cover, g_objp);
+    CKL();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// Register-resident small DFTs with compile-time twiddles (sm_100a; also compiles for the host so the
+// index algebra can be unit-tested without a GPU).
+//
+// Dft<R, DIR>::run(v) transforms v[0..R) in place, natural order in and out,
+//   X[k] = sum_n v[n] * exp(DIR * 2*pi*i * n*k / R),   DIR = -1 (forward) or +1 (inverse, unnormalised).
+// R is factored at compile time (4, then 2, then 3); twiddles are constexpr so that ptxas sees immediates
+// (FFMA with an immediate operand issues at twice the rate of the 3-register form on Blackwell).
+#pragma once
+#include <cuda_runtime.h>
+#include <utility>
+
+#ifdef __CUDACC__
+#define PTYB_HD __host__ __device__ __forceinline__
+#define PTYB_CE __host__ __device__ constexpr
+#else
+#define PTYB_HD inline
+#define PTYB_CE constexpr
+#endif
+
+namespace ptyb {
+
+// ---- complex helpers on float2 -----------------------------------------------------------------
+PTYB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+PTYB_HD float2 cmulc(float2 a, float2 b) { /* a * conj(b) */ return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+PTYB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PTYB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PTYB_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+PTYB_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+PTYB_HD float cabs2(float2 a) { return a.x * a.x + a.y * a.y; }
+
+// ---- constexpr cos/sin of 2*pi*k/r: exact quadrant reduction on integers, Taylor on |phi| <= pi/4 ----
+constexpr double kPi = 3.14159265358979323846264338327950288;
+PTYB_CE double taylor_sin(double x) {
+    double x2 = x * x, t = x, s = x;
+    for (int i = 1; i < 14; ++i) { t *= -x2 / double((2 * i) * (2 * i + 1)); s += t; }
+    return s;
+}
+PTYB_CE double taylor_cos(double x) {
+    double x2 = x * x, t = 1.0, s = 1.0;
+    for (int i = 1; i < 14; ++i) { t *= -x2 / double((2 * i - 1) * (2 * i)); s += t; }
+    return s;
+}
+struct cd { double c, s; };
+PTYB_CE cd cs2pi(long long k, long long r) {
+    k %= r;
+    if (k < 0) k += r;
+    long long k4 = 4 * k;
+    int quad = int(k4 / r);
+    long long rem = k4 - quad * r;                 // angle = quad*pi/2 + (pi/2)*rem/r
+    double c = 1.0, s = 0.0;
+    if (rem != 0) {
+        if (2 * rem <= r) { double phi = (kPi / 2) * double(rem) / double(r); c = taylor_cos(phi); s = taylor_sin(phi); }
+        else { double phi = (kPi / 2) * double(r - rem) / double(r); c = taylor_sin(phi); s = taylor_cos(phi); }
+    }
+    switch (quad) {
+        case 0: return cd{c, s};
+        case 1: return cd{-s, c};
+        case 2: return cd{-c, -s};
+        default: return cd{s, -c};
+    }
+}
+
+// multiply by exp(DIR * i*pi/2) = DIR*i
+template <int DIR> PTYB_HD float2 mul_i(float2 a) { return DIR > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+// a * exp(DIR * 2*pi*i * K/R), K and R compile-time
+template <int K, int R, int DIR> PTYB_HD float2 twmul(float2 a) {
+    constexpr int k = ((K % R) + R) % R;
+    if constexpr (k == 0) return a;
+    else if constexpr (4 * k == R) return mul_i<DIR>(a);
+    else if constexpr (2 * k == R) return make_float2(-a.x, -a.y);
+    else if constexpr (4 * k == 3 * R) return mul_i<-DIR>(a);
+    else if constexpr (8 * k == R || 8 * k == 3 * R || 8 * k == 5 * R || 8 * k == 7 * R) {
+        constexpr float h = 0.70710678118654752440f;
+        constexpr cd w = cs2pi(k, R);
+        constexpr float sc = w.c > 0 ? 1.f : -1.f, ss = (DIR * w.s) > 0 ? 1.f : -1.f;
+        // (x + i y) * h * (sc + i ss)
+        return make_float2((a.x * sc - a.y * ss) * h, (a.x * ss + a.y * sc) * h);
+    } else {
+        constexpr cd w = cs2pi(k, R);
+        constexpr float c = float(w.c), s = float(DIR * w.s);
+        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    }
+}
+
+PTYB_CE int first_factor(int R) {
+    return (R % 4 == 0 && R > 4) ? 4 : (R % 2 == 0 && R > 2) ? 2 : (R % 3 == 0 && R > 3) ? 3 : R;
+}
+
+template <int R, int DIR> struct Dft;
+
+template <int DIR> struct Dft<1, DIR> { PTYB_HD static void run(float2*) {} };
+
+template <int DIR> struct Dft<2, DIR> {
+    PTYB_HD static void run(float2* v) {
+        float2 t = v[0];
+        v[0] = cadd(t, v[1]);
+        v[1] = csub(t, v[1]);
+    }
+};
+
+template <int DIR> struct Dft<3, DIR> {
+    PTYB_HD static void run(float2* v) {
+        constexpr float h = 0.86602540378443864676f * float(DIR);
+        float2 t = cadd(v[1], v[2]), u = csub(v[1], v[2]);
+        float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
+        float2 iu = make_float2(-h * u.y, h * u.x);                 // DIR*i*(sqrt3/2)*u
+        v[0] = cadd(v[0], t);
+        v[1] = cadd(m, iu);
+        v[2] = csub(m, iu);
+    }
+};
+
+template <int DIR> struct Dft<4, DIR> {
+    PTYB_HD static void run(float2* v) {
+        float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+        float2 a2 = cadd(v[1], v[3]), a3 = mul_i<DIR>(csub(v[1], v[3]));
+        v[0] = cadd(a0, a2);
+        v[2] = csub(a0, a2);
+        v[1] = cadd(a1, a3);
+        v[3] = csub(a1, a3);
+    }
+};
+
+template <int R, int DIR, int A, int B, int... Is>
+PTYB_HD void apply_twiddles(float2 (*y)[B], std::integer_sequence<int, Is...>) {
+    ((y[Is / B][Is % B] = twmul<(Is / B) * (Is % B), R, DIR>(y[Is / B][Is % B])), ...);
+}
+
+// composite R = A*B:  X[kb + B*ka] = sum_a W_A^{a ka} W_R^{a kb} sum_b W_B^{b kb} x[a + A b]
+template <int R, int DIR> struct Dft {
+    static constexpr int A = first_factor(R), B = R / A;
+    static_assert(A != R, "prime radix not implemented");
+    PTYB_HD static void run(float2* v) {
+        float2 y[A][B];
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int b = 0; b < B; ++b) y[a][b] = v[a + A * b];
+#pragma unroll
+        for (int a = 0; a < A; ++a) Dft<B, DIR>::run(y[a]);
+        apply_twiddles<R, DIR, A, B>(y, std::make_integer_sequence<int, A * B>{});
+#pragma unroll
+        for (int kb = 0; kb < B; ++kb) {
+            float2 t[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) t[a] = y[a][kb];
+            Dft<A, DIR>::run(t);
+#pragma unroll
+            for (int ka = 0; ka < A; ++ka) v[kb + B * ka] = t[ka];
+        }
+    }
+};
+
+}  // namespace ptyb

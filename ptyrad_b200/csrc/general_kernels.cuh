@@ -1,0 +1,757 @@
+// General multislice path: every 2-D FFT is two row passes over 16-row slabs held in shared memory, each
+// pass writing its result transposed, with the pointwise physics fused into the passes:
+//
+//   forward, per slice z      DA: (inverse-x) -> psi_z -> stash, *O_z (ROI gather), forward-x  -> G1 (transposed)
+//                             BC: forward-y, *H_n, inverse-y                                    -> G2
+//   far field                 FINAL: forward-y, |.|^2 * occu summed over probe/object modes     -> dp (fftshifted)
+//   adjoint, per slice z      START: forward-y, *2 occu G, inverse-y                            -> G2
+//                             DA^H: inverse-x -> gphi_z; gO += conj(psi_z) gphi (summed over probe modes in
+//                                   registers, one red.global per pixel), gpsi = conj(O_z) gphi, forward-x -> G1
+//                             BC^H: forward-y, *conj(H_n) [+ tilt/thickness sums], inverse-y     -> G2
+//
+// A CTA owns (sample, object mode, 16-row slab) and loops over the probe modes, so the O_z ROI, the propagator
+// values, the intensity accumulators and the object-gradient accumulators live in registers across the loop.
+// Works for N = N1*N2 with N1,N2 <= 16 (see dispatch in api.cu).  The N = 128 on-chip kernels are in fused128.cuh.
+#pragma once
+#include "rowfft.cuh"
+#include <stdint.h>
+
+namespace ptyb {
+
+constexpr int ROWS = 16;   // slab height (rows per CTA)
+constexpr int NT = 256;    // threads per CTA
+
+struct Dims {
+    int N, P, M, Z, Noy, Nox, B;
+};
+
+__device__ __forceinline__ int shift_idx(int k, int N) {  // (k + N/2) mod N  (fftshift == ifftshift for even N)
+    int h = N >> 1;
+    k += h;
+    return k >= N ? k - N : k;
+}
+
+// K[n]: ifftshift'ed, half-bin shifted angular frequency grid (models.py:164-171)
+__device__ __forceinline__ float kgrid(int n, int N, float dx) {
+    int j = shift_idx(n, N);
+    return 6.283185307179586f * ((float(j - (N >> 1)) + 0.5f) / float(N)) / dx;
+}
+
+__device__ __forceinline__ void red_add_f2(float2* addr, float2 v) {
+#if __CUDA_ARCH__ >= 900
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
+#else
+    atomicAdd(&addr->x, v.x);
+    atomicAdd(&addr->y, v.y);
+#endif
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum of NV floats; result valid in thread 0. red = smem scratch of NV*32 floats.
+template <int NV> __device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 32 + w] = v[i];
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float t = lane < nw ? red[i * 32 + lane] : 0.f;
+            v[i] = warp_sum(t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small setup kernels
+// ------------------------------------------------------------------------------------------------
+
+// O = a * exp(i*phi) for the whole object (torch.polar, forward.py:53), evaluated once per step
+__global__ void k_obj_polar(const float* __restrict__ a, const float* __restrict__ ph, float2* __restrict__ O, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, c;
+    sincosf(ph[i], &s, &c);
+    float av = a[i];
+    O[i] = make_float2(av * c, av * s);
+}
+
+// per-sample shift ramps, separable: w'[ky,kx] = wy[ky]*wx[kx], w.[n] = exp(-2 pi i s kappa_n),
+// kappa_n = ((n + N/2) mod N)/N   (image_proc.py:531-532 with the non-centred grid of models.py:179)
+__global__ void k_shift_vectors(const float* __restrict__ shifts, const int64_t* __restrict__ idx, int B, int N,
+                                float2* __restrict__ wvec) {
+    int b = blockIdx.x;
+    int64_t n0 = idx[b];
+    float sy = shifts[2 * n0], sx = shifts[2 * n0 + 1];
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float kap = float(shift_idx(n, N)) / float(N);
+        float s, c;
+        sincospif(-2.0f * sy * kap, &s, &c);
+        wvec[((size_t)b * 2 + 0) * N + n] = make_float2(c, s);
+        sincospif(-2.0f * sx * kap, &s, &c);
+        wvec[((size_t)b * 2 + 1) * N + n] = make_float2(c, s);
+    }
+}
+
+// per-sample tilt ramps, separable: exp(i dz (Ky tan ty + Kx tan tx)) = ey[ky]*ex[kx]  (models.py:336-347)
+__global__ void k_tilt_vectors(const float* __restrict__ tilts, int tilt_mode, const int64_t* __restrict__ idx, int B, int N,
+                               float dx, const float* __restrict__ dz, float2* __restrict__ tvec) {
+    int b = blockIdx.x;
+    int64_t n0 = tilt_mode == 2 ? idx[b] : 0;
+    float ty = tanf(tilts[2 * n0] / 1e3f), tx = tanf(tilts[2 * n0 + 1] / 1e3f);
+    float d = dz[0];
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float K = kgrid(n, N, dx);
+        float s, c;
+        sincosf(d * K * ty, &s, &c);
+        tvec[((size_t)b * 2 + 0) * N + n] = make_float2(c, s);
+        sincosf(d * K * tx, &s, &c);
+        tvec[((size_t)b * 2 + 1) * N + n] = make_float2(c, s);
+    }
+}
+
+__global__ void k_transpose(const float2* __restrict__ in, float2* __restrict__ out, int N) {
+    __shared__ float2 t[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (x < N && y0 + j < N) t[j][threadIdx.x] = in[(size_t)(y0 + j) * N + x];
+    __syncthreads();
+    int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (ox < N && oy0 + j < N) out[(size_t)(oy0 + j) * N + ox] = t[threadIdx.x][j];
+}
+
+// exp(i*dz*Kz) in float64 (models.py:222-223,341,355)
+__global__ void k_propagator(int N, float dx, float lambd, const float* __restrict__ dz, float2* __restrict__ H) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * N) return;
+    int ky = i / N, kx = i % N;
+    const double twopi = 6.283185307179586476925286766559;
+    double Ky = twopi * ((double(shift_idx(ky, N) - (N >> 1)) + 0.5) / double(N)) / double(dx);
+    double Kx = twopi * ((double(shift_idx(kx, N) - (N >> 1)) + 0.5) / double(N)) / double(dx);
+    double k0 = twopi / double(lambd);
+    double ph = double(dz[0]) * sqrt(k0 * k0 - Kx * Kx - Ky * Ky);
+    double s, c;
+    sincos(ph, &s, &c);
+    H[i] = make_float2(float(c), float(s));
+}
+
+// ROI gather, bit-exact copy (models.py:251-265)
+__global__ void k_gather_patches(Dims d, const int64_t* __restrict__ idx, const float* __restrict__ obja,
+                                 const float* __restrict__ objp, const int32_t* __restrict__ crop, float* __restrict__ out) {
+    int b = blockIdx.z, mz = blockIdx.y;
+    int64_t n0 = idx[b];
+    int32_t cy = crop[2 * n0], cx = crop[2 * n0 + 1];
+    size_t plane = (size_t)mz * d.Noy * d.Nox;
+    float2* o = reinterpret_cast<float2*>(out) + ((size_t)b * d.M * d.Z + mz) * d.N * d.N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.N * d.N; e += gridDim.x * blockDim.x) {
+        int y = e / d.N, x = e % d.N;
+        size_t src = plane + (size_t)(cy + y) * d.Nox + (cx + x);
+        o[e] = make_float2(obja[src], objp[src]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab helpers
+// ------------------------------------------------------------------------------------------------
+template <class F> struct Slab {
+    static constexpr int N = F::N;
+    static constexpr int EPT = ROWS * N / NT;  // elements per thread in the pointwise phases
+    static_assert(ROWS * N % NT == 0, "slab size must be a multiple of the block size");
+    static constexpr int SLAB_ELEMS = ROWS * F::RS;
+    // natural ownership: lanes run along the row (coalesced for row-major global arrays)
+    template <class Fn> __device__ __forceinline__ static void nat(Fn f) {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            int e = threadIdx.x + i * NT;
+            f(i, e / N, e % N);
+        }
+    }
+    // transposed ownership: lanes run across the 16 rows (coalesced for arrays indexed [q][row])
+    template <class Fn> __device__ __forceinline__ static void tr(Fn f) {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            int e = threadIdx.x + i * NT;
+            f(i, e % ROWS, e / ROWS);
+        }
+    }
+    static constexpr size_t smem_bytes() { return sizeof(float2) * (SLAB_ELEMS + N) + sizeof(float) * (ROWS * (N + 1) + 4 * 32); }
+};
+
+#define PTYB_SMEM_CARVE(F)                                                      \
+    extern __shared__ __align__(16) unsigned char smem_raw[];                   \
+    float2* slab = reinterpret_cast<float2*>(smem_raw);                          \
+    float2* twN = slab + Slab<F>::SLAB_ELEMS;                                    \
+    float* fbuf = reinterpret_cast<float*>(twN + F::N);                          \
+    float* red = fbuf + ROWS * (F::N + 1);                                       \
+    (void)fbuf; (void)red;                                                       \
+    F::fill_twiddles(twN);                                                       \
+    __syncthreads();
+
+// ------------------------------------------------------------------------------------------------
+// plain pass: FFT along the rows of `count` tiles, output transposed or not.  grid (N/ROWS, count)
+//   DIR=-1: natural in, frequency-ordered out;  DIR=+1: frequency-ordered (natural index) in, natural out
+// ------------------------------------------------------------------------------------------------
+template <class F, int DIR, bool TOUT> __global__ void __launch_bounds__(NT) k_pass(const float2* __restrict__ in, float2* __restrict__ out, float scale) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const int r0 = blockIdx.x * ROWS;
+    const float2* src = in + (size_t)blockIdx.y * N * N;
+    float2* dst = out + (size_t)blockIdx.y * N * N;
+    Slab<F>::nat([&](int, int r, int n) {
+        float2 v = src[(size_t)(r0 + r) * N + n];
+        slab[r * F::RS + (DIR < 0 ? F::addr(n) : F::apos(n))] = v;
+    });
+    __syncthreads();
+    if (DIR < 0) F::forward(slab, ROWS, twN); else F::inverse(slab, ROWS, twN);
+    if (TOUT) {
+        Slab<F>::tr([&](int, int r, int q) {
+            float2 v = slab[r * F::RS + (DIR < 0 ? F::apos(q) : F::addr(q))];
+            dst[(size_t)q * N + r0 + r] = cscale(v, scale);
+        });
+    } else {
+        Slab<F>::nat([&](int, int r, int q) {
+            float2 v = slab[r * F::RS + (DIR < 0 ? F::apos(q) : F::addr(q))];
+            dst[(size_t)(r0 + r) * N + q] = cscale(v, scale);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    Dims d;
+    const int64_t* idx;
+    const int32_t* crop;
+    const float2* O;        // (M,Z,Noy,Nox)
+    const float2* probe;    // (P,N,N)
+    const float2* PhatT;    // (P,N,N) [kx][ky]
+    const float2* HT;       // (N,N)   [kx][ky]
+    const float2* wvec;     // (B,2,N)  shift ramps or null
+    const float2* tvec;     // (B,2,N)  tilt ramps or null
+    const float* occu;      // (M)
+    float2* stash;          // (B,P,M,Z,N,N)
+    float2* phis;           // (B,P,M,Z-1,N,N) [kx][ky] or null
+    float2* G1;             // (B,P,M,N,N) [kx][y]
+    float2* G2;             // (B,P,M,N,N) [y][kx]
+    float2* farT;           // (B,P,M,N,N) [kx][y]
+    float* dp;              // (B,N,N)
+    float eps;
+};
+
+// psi0 half-shifted: G2[b,p,0][y][kx] = (1/N) * inverse-y( PhatT[p][kx][ky] * wy[ky] * wx[kx] ).  grid (N/ROWS, B)
+template <class F> __global__ void __launch_bounds__(NT) k_init_shift(FwdArgs a) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const int kx0 = blockIdx.x * ROWS, b = blockIdx.y;
+    const float2* wy = a.wvec + ((size_t)b * 2 + 0) * N;
+    const float2* wx = a.wvec + ((size_t)b * 2 + 1) * N;
+    float2 wreg[Slab<F>::EPT];
+    Slab<F>::nat([&](int i, int r, int ky) { wreg[i] = cmul(wy[ky], wx[kx0 + r]); });
+    for (int p = 0; p < a.d.P; ++p) {
+        const float2* src = a.PhatT + (size_t)p * N * N;
+        Slab<F>::nat([&](int i, int r, int ky) { slab[r * F::RS + F::apos(ky)] = cmul(src[(size_t)(kx0 + r) * N + ky], wreg[i]); });
+        __syncthreads();
+        F::inverse(slab, ROWS, twN);
+        float2* dst = a.G2 + ((size_t)b * a.d.P + p) * a.d.M * N * N;   // m = 0 slot
+        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        __syncthreads();
+    }
+}
+
+// grid (N/ROWS, M, B).  src_mode: 0 = psi_z comes from G2 (inverse-x), 1 = psi_0 is the unshifted probe
+template <class F> __global__ void __launch_bounds__(NT) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.d;
+    const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    const int64_t n0 = a.idx[b];
+    const int cy = a.crop[2 * n0], cx = a.crop[2 * n0 + 1];
+    const float2* Oz = a.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
+    float2 Oreg[Slab<F>::EPT];
+    Slab<F>::nat([&](int i, int r, int x) { Oreg[i] = Oz[(size_t)(cy + y0 + r) * d.Nox + cx + x]; });
+    const int msrc = (z == 0) ? 0 : m;
+    for (int p = 0; p < d.P; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M;
+        float2* st = a.stash + ((tile + m) * d.Z + z) * N * N;
+        if (src_mode == 1) {
+            const float2* pr = a.probe + (size_t)p * N * N;
+            Slab<F>::nat([&](int i, int r, int x) {
+                float2 psi = pr[(size_t)(y0 + r) * N + x];
+                st[(size_t)(y0 + r) * N + x] = psi;
+                slab[r * F::RS + F::addr(x)] = cmul(psi, Oreg[i]);
+            });
+        } else {
+            const float2* src = a.G2 + (tile + msrc) * N * N;
+            Slab<F>::nat([&](int, int r, int kx) { slab[r * F::RS + F::apos(kx)] = src[(size_t)(y0 + r) * N + kx]; });
+            __syncthreads();
+            F::inverse(slab, ROWS, twN);
+            Slab<F>::nat([&](int i, int r, int x) {
+                float2 psi = cscale(slab[r * F::RS + F::addr(x)], 1.0f / N);
+                st[(size_t)(y0 + r) * N + x] = psi;
+                slab[r * F::RS + F::addr(x)] = cmul(psi, Oreg[i]);
+            });
+        }
+        __syncthreads();
+        F::forward(slab, ROWS, twN);
+        float2* dst = (last ? a.farT : a.G1) + (tile + m) * N * N;
+        Slab<F>::tr([&](int, int r, int q) { dst[(size_t)q * N + y0 + r] = slab[r * F::RS + F::apos(q)]; });
+        __syncthreads();
+    }
+}
+
+// propagator value at (ky, kx) for this sample, natural ownership registers
+template <class F> __device__ __forceinline__ void load_prop(const FwdArgs& a, int b, int kx0, float2 (&Hreg)[Slab<F>::EPT]) {
+    constexpr int N = F::N;
+    Slab<F>::nat([&](int i, int r, int ky) { Hreg[i] = a.HT[(size_t)(kx0 + r) * N + ky]; });
+    if (a.tvec) {
+        const float2* ey = a.tvec + ((size_t)b * 2 + 0) * N;
+        const float2* ex = a.tvec + ((size_t)b * 2 + 1) * N;
+        Slab<F>::nat([&](int i, int r, int ky) { Hreg[i] = cmul(Hreg[i], cmul(ey[ky], ex[kx0 + r])); });
+    }
+}
+
+// grid (N/ROWS, M, B): G1[kx][y] -> forward-y -> *H -> inverse-y -> G2[y][kx]
+template <class F> __global__ void __launch_bounds__(NT) k_fwd_bc(FwdArgs a, int z) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.d;
+    const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    float2 Hreg[Slab<F>::EPT];
+    load_prop<F>(a, b, kx0, Hreg);
+    for (int p = 0; p < d.P; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const float2* src = a.G1 + tile * N * N;
+        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+        __syncthreads();
+        F::forward(slab, ROWS, twN);
+        float2* ph = a.phis ? a.phis + (tile * (d.Z - 1) + z) * N * N : nullptr;
+        Slab<F>::nat([&](int i, int r, int ky) {
+            float2 v = slab[r * F::RS + F::apos(ky)];
+            if (ph) ph[(size_t)(kx0 + r) * N + ky] = v;
+            slab[r * F::RS + F::apos(ky)] = cmul(v, Hreg[i]);
+        });
+        __syncthreads();
+        F::inverse(slab, ROWS, twN);
+        float2* dst = a.G2 + tile * N * N;
+        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        __syncthreads();
+    }
+}
+
+// grid (N/ROWS, B): dp[b][sh(ky)][sh(kx)] = eps + sum_{m,p} occu_m |forward-y(farT)|^2 / N^2
+template <class F> __global__ void __launch_bounds__(NT) k_fwd_final(FwdArgs a) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.d;
+    const int kx0 = blockIdx.x * ROWS, b = blockIdx.y;
+    float acc[Slab<F>::EPT];
+#pragma unroll
+    for (int i = 0; i < Slab<F>::EPT; ++i) acc[i] = 0.f;
+    for (int m = 0; m < d.M; ++m) {
+        const float oc = a.occu[m];
+        for (int p = 0; p < d.P; ++p) {
+            const float2* src = a.farT + (((size_t)b * d.P + p) * d.M + m) * N * N;
+            Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+            __syncthreads();
+            F::forward(slab, ROWS, twN);
+            Slab<F>::nat([&](int i, int r, int ky) { acc[i] += oc * cabs2(slab[r * F::RS + F::apos(ky)]); });
+            __syncthreads();
+        }
+    }
+    const float inv = 1.0f / (float(N) * float(N));
+    Slab<F>::nat([&](int i, int r, int ky) { fbuf[r * (N + 1) + ky] = acc[i] * inv + a.eps; });
+    __syncthreads();
+    float* dp = a.dp + (size_t)b * N * N;
+    Slab<F>::tr([&](int, int r, int ky) { dp[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + r, N)] = fbuf[r * (N + 1) + ky]; });
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    FwdArgs f;
+    const float* G;         // (B,N,N) dL/d(dp)
+    float2* gO;             // (M,Z,Noy,Nox) scratch, zeroed
+    float2* gPhatT;         // (P,N,N) [kx][ky] scratch, zeroed
+    float* gprop;           // (B,3) sums  K_y S, K_x S, (Kz-k0) S ; zeroed
+    float* gshift;          // (Ntot,2) dense output, zeroed
+    float dx, k0;
+    int need_obj, need_probe, need_shift, need_prop;
+};
+
+// grid (N/ROWS, M, B): farT -> forward-y -> * 2 occu G~ -> inverse-y -> G2
+template <class F> __global__ void __launch_bounds__(NT) k_bwd_start(BwdArgs a) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.f.d;
+    const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    const float* G = a.G + (size_t)b * N * N;
+    Slab<F>::tr([&](int, int r, int ky) { fbuf[r * (N + 1) + ky] = G[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + r, N)]; });
+    __syncthreads();
+    const float oc2 = 2.0f * a.f.occu[m];
+    float Greg[Slab<F>::EPT];
+    Slab<F>::nat([&](int i, int r, int ky) { Greg[i] = oc2 * fbuf[r * (N + 1) + ky]; });
+    for (int p = 0; p < d.P; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const float2* src = a.f.farT + tile * N * N;
+        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+        __syncthreads();
+        F::forward(slab, ROWS, twN);
+        Slab<F>::nat([&](int i, int r, int ky) {
+            float2 v = slab[r * F::RS + F::apos(ky)];
+            slab[r * F::RS + F::apos(ky)] = cscale(v, Greg[i]);
+        });
+        __syncthreads();
+        F::inverse(slab, ROWS, twN);
+        float2* dst = a.f.G2 + tile * N * N;
+        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        __syncthreads();
+    }
+}
+
+// grid (N/ROWS, M, B).  out_mode: 0 = forward-x and store transposed to G1 (z>0, or z==0 with shifted probes),
+//                                 1 = store gpsi_0 untransformed (natural) to G1 (z==0, unshifted probes), 2 = nothing
+template <class F> __global__ void __launch_bounds__(NT) k_bwd_da(BwdArgs a, int z, int out_mode) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.f.d;
+    const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    const int64_t n0 = a.f.idx[b];
+    const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
+    const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
+    float2 Oreg[Slab<F>::EPT], accO[Slab<F>::EPT];
+    Slab<F>::nat([&](int i, int r, int x) {
+        Oreg[i] = Oz[(size_t)(cy + y0 + r) * d.Nox + cx + x];
+        accO[i] = make_float2(0.f, 0.f);
+    });
+    for (int p = 0; p < d.P; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const float2* src = a.f.G2 + tile * N * N;
+        Slab<F>::nat([&](int, int r, int kx) { slab[r * F::RS + F::apos(kx)] = src[(size_t)(y0 + r) * N + kx]; });
+        __syncthreads();
+        F::inverse(slab, ROWS, twN);
+        const float2* st = a.f.stash + (tile * d.Z + z) * N * N;
+        float2* dst = a.f.G1 + tile * N * N;
+        Slab<F>::nat([&](int i, int r, int x) {
+            float2 gphi = cscale(slab[r * F::RS + F::addr(x)], 1.0f / N);
+            float2 psi = st[(size_t)(y0 + r) * N + x];
+            accO[i] = cadd(accO[i], cmulc(gphi, psi));            // conj(psi) * gphi
+            float2 gpsi = cmulc(gphi, Oreg[i]);                   // conj(O) * gphi
+            if (out_mode == 0) slab[r * F::RS + F::addr(x)] = gpsi;
+            else if (out_mode == 1) dst[(size_t)(y0 + r) * N + x] = gpsi;
+        });
+        __syncthreads();
+        if (out_mode == 0) {
+            F::forward(slab, ROWS, twN);
+            Slab<F>::tr([&](int, int r, int q) { dst[(size_t)q * N + y0 + r] = slab[r * F::RS + F::apos(q)]; });
+            __syncthreads();
+        }
+    }
+    if (a.need_obj) {
+        float2* gOz = a.gO + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
+        Slab<F>::nat([&](int i, int r, int x) { red_add_f2(gOz + (size_t)(cy + y0 + r) * d.Nox + cx + x, accO[i]); });
+    }
+}
+
+// grid (N/ROWS, M, B), z >= 1: G1 -> forward-y -> *conj(H) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
+template <class F> __global__ void __launch_bounds__(NT) k_bwd_bc(BwdArgs a, int z) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.f.d;
+    const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    float2 Hreg[Slab<F>::EPT];
+    load_prop<F>(a.f, b, kx0, Hreg);
+    float s3[3] = {0.f, 0.f, 0.f};
+    float Kyr[Slab<F>::EPT], Kxr[Slab<F>::EPT], Kzr[Slab<F>::EPT];
+    if (a.need_prop) {
+        Slab<F>::nat([&](int i, int r, int ky) {
+            float Ky = kgrid(ky, N, a.dx), Kx = kgrid(kx0 + r, N, a.dx);
+            float k2 = Kx * Kx + Ky * Ky;
+            Kyr[i] = Ky; Kxr[i] = Kx;
+            Kzr[i] = -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0);     // Kz - k0, cancellation-free
+        });
+    }
+    const float invN2 = 1.0f / (float(N) * float(N));
+    for (int p = 0; p < d.P; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const float2* src = a.f.G1 + tile * N * N;
+        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+        __syncthreads();
+        F::forward(slab, ROWS, twN);
+        const float2* ph = a.need_prop ? a.f.phis + (tile * (d.Z - 1) + (z - 1)) * N * N : nullptr;
+        Slab<F>::nat([&](int i, int r, int ky) {
+            float2 v = cmulc(slab[r * F::RS + F::apos(ky)], Hreg[i]);   // conj(H) * F2(gpsi)
+            if (ph) {
+                float2 phi = ph[(size_t)(kx0 + r) * N + ky];
+                float s = (phi.x * v.y - phi.y * v.x) * invN2;           // Im(conj(Phi) * v) / N^2
+                s3[0] += Kyr[i] * s; s3[1] += Kxr[i] * s; s3[2] += Kzr[i] * s;
+            }
+            slab[r * F::RS + F::apos(ky)] = v;
+        });
+        __syncthreads();
+        F::inverse(slab, ROWS, twN);
+        float2* dst = a.f.G2 + tile * N * N;
+        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        __syncthreads();
+    }
+    if (a.need_prop) {
+        block_sum<3>(s3, red);
+        if (threadIdx.x == 0) {
+            atomicAdd(a.gprop + 3 * b + 0, s3[0]);
+            atomicAdd(a.gprop + 3 * b + 1, s3[1]);
+            atomicAdd(a.gprop + 3 * b + 2, s3[2]);
+        }
+    }
+}
+
+// shifted probes: grid (N/ROWS, P, nchunk).  T = forward-y(sum_m G1[b,p,m]) / N^2 ; gPhatT += conj(w') T ;
+// shift gradients -2 pi sum kappa Im(conj(w') conj(Phat) T)
+template <class F> __global__ void __launch_bounds__(NT) k_bwd_probe(BwdArgs a, int bchunk) {
+    PTYB_SMEM_CARVE(F)
+    constexpr int N = F::N;
+    const Dims& d = a.f.d;
+    const int kx0 = blockIdx.x * ROWS, p = blockIdx.y;
+    const int b_lo = blockIdx.z * bchunk, b_hi = min(d.B, b_lo + bchunk);
+    float2 acc[Slab<F>::EPT], Ph[Slab<F>::EPT];
+    float kapy[Slab<F>::EPT], kapx[Slab<F>::EPT];
+    Slab<F>::nat([&](int i, int r, int ky) {
+        acc[i] = make_float2(0.f, 0.f);
+        Ph[i] = a.f.PhatT[((size_t)p * N + kx0 + r) * N + ky];
+        kapy[i] = float(shift_idx(ky, N)) / float(N);
+        kapx[i] = float(shift_idx(kx0 + r, N)) / float(N);
+    });
+    const float invN2 = 1.0f / (float(N) * float(N));
+    for (int b = b_lo; b < b_hi; ++b) {
+        const size_t tile0 = ((size_t)b * d.P + p) * d.M;
+        Slab<F>::nat([&](int, int r, int y) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int m = 0; m < d.M; ++m) v = cadd(v, a.f.G1[(tile0 + m) * N * N + (size_t)(kx0 + r) * N + y]);
+            slab[r * F::RS + F::addr(y)] = v;
+        });
+        __syncthreads();
+        F::forward(slab, ROWS, twN);
+        const float2* wy = a.f.wvec + ((size_t)b * 2 + 0) * N;
+        const float2* wx = a.f.wvec + ((size_t)b * 2 + 1) * N;
+        float s2[2] = {0.f, 0.f};
+        Slab<F>::nat([&](int i, int r, int ky) {
+            float2 T = cscale(slab[r * F::RS + F::apos(ky)], invN2);
+            float2 w = cmul(wy[ky], wx[kx0 + r]);
+            float2 cwT = cmulc(T, w);                                    // conj(w') * T
+            acc[i] = cadd(acc[i], cwT);
+            float q = cwT.y * Ph[i].x - cwT.x * Ph[i].y;                 // Im(conj(w') T conj(Phat))
+            s2[0] += kapy[i] * q; s2[1] += kapx[i] * q;
+        });
+        if (a.need_shift) {
+            block_sum<2>(s2, red);
+            if (threadIdx.x == 0) {
+                int64_t n0 = a.f.idx[b];
+                atomicAdd(a.gshift + 2 * n0 + 0, -6.283185307179586f * s2[0]);
+                atomicAdd(a.gshift + 2 * n0 + 1, -6.283185307179586f * s2[1]);
+            }
+        }
+        __syncthreads();
+    }
+    if (a.need_probe) {
+        float2* dst = a.gPhatT + (size_t)p * N * N;
+        Slab<F>::nat([&](int i, int r, int ky) { red_add_f2(dst + (size_t)(kx0 + r) * N + ky, acc[i]); });
+    }
+}
+
+// unshifted probes: g_probe[p][y][x] = sum_{b,m} G1[b,p,m][y][x] (natural layout).  grid (ceil(N*N/256), P)
+__global__ void k_bwd_probe_noshift(Dims d, const float2* __restrict__ G1, float2* __restrict__ gprobe) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (e >= d.N * d.N) return;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int b = 0; b < d.B; ++b)
+        for (int m = 0; m < d.M; ++m) acc = cadd(acc, G1[(((size_t)b * d.P + p) * d.M + m) * d.N * d.N + e]);
+    gprobe[(size_t)p * d.N * d.N + e] = acc;
+}
+
+// g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O))   (polar backward, forward.py:53)
+__global__ void k_obj_finish(const float2* __restrict__ gO, const float* __restrict__ a, const float* __restrict__ ph,
+                             float* __restrict__ ga, float* __restrict__ gp, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, c;
+    sincosf(ph[i], &s, &c);
+    float2 g = gO[i];
+    ga[i] = g.x * c + g.y * s;
+    gp[i] = a[i] * (g.y * c - g.x * s);
+}
+
+// tilt / thickness chain rule from the per-sample sums (models.py:336-356).  single block.
+__global__ void k_prop_finish(const float* __restrict__ gprop, const float* __restrict__ tilts, int tilt_mode,
+                              const int64_t* __restrict__ idx, int B, const float* __restrict__ dz, float* g_tilts,
+                              float* g_dz) {
+    float acc_dz = 0.f, acc_ty = 0.f, acc_tx = 0.f;
+    const float d = dz[0];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float Ay = gprop[3 * b], Ax = gprop[3 * b + 1], Az = gprop[3 * b + 2];
+        float thy = 0.f, thx = 0.f;
+        int64_t n0 = 0;
+        if (tilt_mode) {
+            n0 = tilt_mode == 2 ? idx[b] : 0;
+            thy = tilts[2 * n0] / 1e3f; thx = tilts[2 * n0 + 1] / 1e3f;
+        }
+        float cy = cosf(thy), cx = cosf(thx);
+        float gy = d * Ay / (cy * cy) / 1e3f, gx = d * Ax / (cx * cx) / 1e3f;
+        if (g_tilts) {
+            if (tilt_mode == 2) { atomicAdd(g_tilts + 2 * n0, gy); atomicAdd(g_tilts + 2 * n0 + 1, gx); }
+            else { acc_ty += gy; acc_tx += gx; }
+        }
+        acc_dz += Az + tanf(thy) * Ay + tanf(thx) * Ax;
+    }
+    __shared__ float red[3 * 32];
+    float v[3] = {acc_dz, acc_ty, acc_tx};
+    block_sum<3>(v, red);
+    if (threadIdx.x == 0) {
+        if (g_dz) g_dz[0] = v[0];
+        if (g_tilts && tilt_mode == 1) { g_tilts[0] = v[1]; g_tilts[1] = v[2]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses (losses.py:36-104)
+// ------------------------------------------------------------------------------------------------
+struct LossK {
+    int s_on, p_on, b_on;
+    float s_w, s_p, p_w, p_p, p_eps, b_w, b_p;
+};
+
+__device__ __forceinline__ float powp(float x, float p) { return p == 0.5f ? sqrtf(x) : (p == 1.0f ? x : powf(x, p)); }
+
+// stats: [0] sum (I^p-M^p)^2  [1] sum M^p  [2] sum (M^q log(I^q+e) - I^q)  [3] sum M^q  [4] sum M^r  [5] sum (Ibar^r - Mbar^r)^2
+__global__ void k_loss_partial(LossK k, const float* __restrict__ dp, const float* __restrict__ meas, const int64_t* __restrict__ idx,
+                               int B, int N, double* stats, float* pac) {
+    const size_t NN = (size_t)N * N, tot = (size_t)B * NN;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        size_t b = e / NN, pix = e - b * NN;
+        float I = dp[e], Mv = meas[(size_t)idx[b] * NN + pix];
+        if (k.s_on) { float mp = powp(Mv, k.s_p), df = powp(I, k.s_p) - mp; a0 += (double)df * df; a1 += mp; }
+        if (k.p_on) { float mq = powp(Mv, k.p_p), iq = powp(I, k.p_p); a2 += (double)(mq * logf(iq + k.p_eps) - iq); a3 += mq; }
+        if (k.b_on) { a4 += powp(Mv, k.b_p); atomicAdd(pac + pix, I); atomicAdd(pac + NN + pix, Mv); }
+    }
+    a0 = warp_sum_d(a0); a1 = warp_sum_d(a1); a2 = warp_sum_d(a2); a3 = warp_sum_d(a3); a4 = warp_sum_d(a4);
+    if ((threadIdx.x & 31) == 0) {
+        if (k.s_on) { atomicAdd(stats + 0, a0); atomicAdd(stats + 1, a1); }
+        if (k.p_on) { atomicAdd(stats + 2, a2); atomicAdd(stats + 3, a3); }
+        if (k.b_on) atomicAdd(stats + 4, a4);
+    }
+}
+
+__global__ void k_loss_final(LossK k, int B, int N, double* stats, const float* __restrict__ pac, float* losses3) {
+    const size_t NN = (size_t)N * N;
+    __shared__ double sh[32];
+    double acc = 0;
+    if (k.b_on) {
+        for (size_t i = threadIdx.x; i < NN; i += blockDim.x) {
+            float ib = pac[i] / B, mb = pac[NN + i] / B;
+            float df = powp(ib, k.b_p) - powp(mb, k.b_p);
+            acc += (double)df * df;
+        }
+        acc = warp_sum_d(acc);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += sh[i]; stats[5] = t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double nel = (double)B * NN;
+        losses3[0] = k.s_on ? float(k.s_w * sqrt(stats[0] / nel) / (stats[1] / nel)) : 0.f;
+        losses3[1] = k.p_on ? float(-k.p_w * (stats[2] / nel) / (stats[3] / nel)) : 0.f;
+        losses3[2] = k.b_on ? float(k.b_w * sqrt(stats[5] / NN) / (stats[4] / nel)) : 0.f;
+    }
+}
+
+__global__ void k_loss_grad(LossK k, const float* __restrict__ dp, const float* __restrict__ meas, const int64_t* __restrict__ idx,
+                            int B, int N, const double* __restrict__ stats, const float* __restrict__ pac,
+                            const float* __restrict__ up, float* __restrict__ G) {
+    const size_t NN = (size_t)N * N, tot = (size_t)B * NN;
+    const double nel = (double)tot;
+    float cs = 0.f, cp = 0.f, cb = 0.f;
+    if (k.s_on) cs = float(up[0] * k.s_w * k.s_p / (nel * sqrt(stats[0] / nel) * (stats[1] / nel)));
+    if (k.p_on) cp = float(-up[1] * k.p_w * k.p_p / (nel * (stats[3] / nel)));
+    if (k.b_on) cb = float(up[2] * k.b_w * k.b_p / (nel * sqrt(stats[5] / NN) * (stats[4] / nel)));
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        size_t b = e / NN, pix = e - b * NN;
+        float I = dp[e], g = 0.f;
+        if (k.s_on || k.p_on) {
+            float Mv = meas[(size_t)idx[b] * NN + pix];
+            if (k.s_on) g += cs * (powp(I, k.s_p) - powp(Mv, k.s_p)) * powp(I, k.s_p - 1.0f);
+            if (k.p_on) g += cp * (powp(Mv, k.p_p) / (powp(I, k.p_p) + k.p_eps) - 1.0f) * powp(I, k.p_p - 1.0f);
+        }
+        if (k.b_on) {
+            float ib = pac[pix] / B, mb = pac[NN + pix] / B;
+            g += cb * (powp(ib, k.b_p) - powp(mb, k.b_p)) * powp(ib, k.b_p - 1.0f);
+        }
+        G[e] = g;
+    }
+}
+
+// sparse: grid (ceil(N*N/256/8), M*Z, B): Ssum[m] += sum |phi|^n over the ROI
+__global__ void k_sparse_partial(Dims d, float order, const float* __restrict__ objp, const int32_t* __restrict__ crop,
+                                 const int64_t* __restrict__ idx, double* Ssum) {
+    int mz = blockIdx.y, b = blockIdx.z;
+    int64_t n0 = idx[b];
+    int cy = crop[2 * n0], cx = crop[2 * n0 + 1];
+    const float* pl = objp + (size_t)mz * d.Noy * d.Nox;
+    double acc = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.N * d.N; e += gridDim.x * blockDim.x) {
+        float v = fabsf(pl[(size_t)(cy + e / d.N) * d.Nox + cx + e % d.N]);
+        acc += order == 1.0f ? v : (order == 2.0f ? v * v : powf(v, order));
+    }
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(Ssum + mz / d.Z, acc);
+}
+
+__global__ void k_sparse_final(Dims d, float weight, float order, const float* __restrict__ occu, const double* __restrict__ Ssum,
+                               float* loss) {
+    if (threadIdx.x || blockIdx.x) return;
+    double cnt = (double)d.B * d.Z * d.N * d.N, t = 0;
+    for (int m = 0; m < d.M; ++m) t += occu[m] * pow(Ssum[m] / cnt, 1.0 / order);
+    loss[0] = float(weight * t);
+}
+
+__global__ void k_cover(Dims d, const int32_t* __restrict__ crop, const int64_t* __restrict__ idx, int32_t* cover) {
+    int b = blockIdx.y;
+    int64_t n0 = idx[b];
+    int cy = crop[2 * n0], cx = crop[2 * n0 + 1];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.N * d.N; e += gridDim.x * blockDim.x)
+        atomicAdd(cover + (size_t)(cy + e / d.N) * d.Nox + cx + e % d.N, 1);
+}
+
+__global__ void k_sparse_grad(Dims d, float weight, float order, const float* __restrict__ objp, const float* __restrict__ occu,
+                              const double* __restrict__ Ssum, const float* __restrict__ up, const int32_t* __restrict__ cover,
+                              float* __restrict__ g_objp) {
+    size_t plane = (size_t)d.Noy * d.Nox, n = plane * d.M * d.Z;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int m = int(i / (plane * d.Z));
+    int c = cover[i % plane];
+    if (!c) return;
+    double cnt = (double)d.B * d.Z * d.N * d.N;
+    float S = float(Ssum[m] / cnt);
+    float coef = up[0] * weight * occu[m] * powf(S, 1.0f / order - 1.0f) / float(cnt);
+    float v = objp[i], av = fabsf(v);
+    float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+    float pw = order == 1.0f ? 1.0f : (order == 2.0f ? av : powf(av, order - 1.0f));
+    g_objp[i] += coef * pw * sg * float(c);
+}
+
+}  // namespace ptyb

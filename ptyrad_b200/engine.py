@@ -1,0 +1,187 @@
+"""torch.autograd glue over the C ABI: tensors stay torch-owned, the arithmetic runs in libptyrad_b200.so.
+
+``MultisliceFunction`` replaces the autograd graph the reference builds for PtychoAD.forward
+(models.py:422-436 -> forward.py:20-80); ``DataLossFunction`` / ``SparseLossFunction`` replace the graph of
+CombinedLoss.forward (losses.py:36-104).  Saved state is per call (``ctx``), so the LBFGS closure, which runs
+several forwards before one backward (reconstruction.py:705-718), works.  All calls are pinned to float32
+(the reference may wrap them in autocast, reconstruction.py:794-799).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Cfg, LossCfg, ptr
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ptyrad_b200 runs on CUDA tensors only: the multislice hot path has no CPU fallback")
+
+
+def make_cfg(N, P, M, Z, Noy, Nox, Ntot, shift_probes, tilt_mode, stash_fourier, dx, lambd, eps=1e-10, path=_lib.PATH_AUTO):
+    if N not in _lib.SUPPORTED_N:
+        raise ValueError(f"pattern size N={N} is not supported by the CUDA kernels (supported: {_lib.SUPPORTED_N})")
+    c = Cfg()
+    c.N, c.P, c.M, c.Z, c.Noy, c.Nox, c.Ntot = N, P, M, Z, Noy, Nox, Ntot
+    c.shift_probes, c.tilt_mode, c.stash_fourier, c.path = int(shift_probes), int(tilt_mode), int(stash_fourier), int(path)
+    c.dx, c.lambd, c.eps = float(dx), float(lambd), float(eps)
+    return c
+
+
+def make_loss_cfg(lp: dict) -> LossCfg:
+    l = LossCfg()
+    s, p, b, sp = lp["loss_single"], lp["loss_poissn"], lp["loss_pacbed"], lp["loss_sparse"]
+    l.single_state, l.single_weight, l.single_pow = int(bool(s["state"])), float(s.get("weight", 1.0)), float(s.get("dp_pow", 0.5))
+    l.poissn_state, l.poissn_weight, l.poissn_pow, l.poissn_eps = int(bool(p["state"])), float(p.get("weight", 1.0)), float(p.get("dp_pow", 1.0)), float(p.get("eps", 1e-6))
+    l.pacbed_state, l.pacbed_weight, l.pacbed_pow = int(bool(b["state"])), float(b.get("weight", 1.0)), float(b.get("dp_pow", 0.2))
+    l.sparse_state, l.sparse_weight, l.sparse_order = int(bool(sp["state"])), float(sp.get("weight", 1.0)), float(sp.get("ln_order", 1))
+    return l
+
+
+def propagator(cfg: Cfg, dz: torch.Tensor) -> torch.Tensor:
+    """exp(i*dz*Kz) (N,N) complex64, evaluated in float64 on the device (models.py:222-223,341,355)."""
+    _require_cuda(dz)
+    H = torch.empty((cfg.N, cfg.N), dtype=torch.complex64, device=dz.device)
+    _lib.check(_lib.lib().ptyb200_propagator(C.byref(cfg), ptr(dz), ptr(H), _stream()))
+    return H
+
+
+def gather_patches(cfg: Cfg, idx, obja, objp, crop_pos):
+    _require_cuda(idx, obja, objp, crop_pos)
+    B = idx.numel()
+    out = torch.empty((B, cfg.M, cfg.Z, cfg.N, cfg.N, 2), dtype=torch.float32, device=obja.device)
+    _lib.check(_lib.lib().ptyb200_gather_patches(C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(crop_pos), ptr(out), _stream()))
+    return out
+
+
+class MultisliceFunction(torch.autograd.Function):
+    """dp = forward(obja, objp, tilts, dz, probe(real view), shifts); backward = hand-derived adjoint kernels."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, obja, objp, tilts, dz, probe, shifts, st):
+        # st: dict(cfg=Cfg, idx, crop_pos, H, occu, change_thickness)
+        _require_cuda(obja, objp, probe, st["idx"])
+        cfg = st["cfg"]
+        idx = st["idx"]
+        B = idx.numel()
+        obja, objp, probe = obja.contiguous(), objp.contiguous(), probe.contiguous()
+        tilts_c = tilts.contiguous() if cfg.tilt_mode else None
+        shifts_c = shifts.contiguous() if cfg.shift_probes else None
+        Hbase = propagator(cfg, dz) if st["change_thickness"] else st["H"]
+        ws_bytes = _lib.lib().ptyb200_workspace_bytes(C.byref(cfg), B)
+        if ws_bytes == 0:
+            _lib.check(1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=obja.device)
+        dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=obja.device)
+        _lib.check(_lib.lib().ptyb200_forward(
+            C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(st["crop_pos"]), ptr(probe), ptr(shifts_c), ptr(Hbase),
+            ptr(tilts_c), ptr(dz), ptr(st["occu"]), ptr(dp), ptr(ws), _stream()))
+        ctx.st, ctx.ws, ctx.Hbase = st, ws, Hbase
+        ctx.save_for_backward(obja, objp, tilts, dz, probe, shifts)
+        return dp
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, G):
+        obja, objp, tilts, dz, probe, shifts = ctx.saved_tensors
+        st, cfg = ctx.st, ctx.st["cfg"]
+        idx = st["idx"]
+        B = idx.numel()
+        n_obja, n_objp, n_tilts, n_dz, n_probe, n_shifts, _ = ctx.needs_input_grad
+        need = 0
+        g_obja = g_objp = g_probe = g_shifts = g_tilts = g_dz = None
+        if n_obja or n_objp:
+            need |= _lib.NEED_OBJ
+            g_obja, g_objp = torch.empty_like(obja), torch.empty_like(objp)
+        if n_probe:
+            need |= _lib.NEED_PROBE
+            g_probe = torch.empty_like(probe)
+        if n_shifts and cfg.shift_probes:
+            need |= _lib.NEED_SHIFTS
+            g_shifts = torch.empty_like(shifts)
+        if n_tilts and cfg.tilt_mode and cfg.Z > 1:
+            need |= _lib.NEED_TILTS
+            g_tilts = torch.empty_like(tilts)
+        if n_dz and st["change_thickness"] and cfg.Z > 1:
+            need |= _lib.NEED_DZ
+            g_dz = torch.empty_like(dz)
+        if need:
+            G = G.contiguous().float()
+            _lib.check(_lib.lib().ptyb200_backward(
+                C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(st["crop_pos"]), ptr(probe),
+                ptr(shifts if cfg.shift_probes else None), ptr(ctx.Hbase), ptr(tilts if cfg.tilt_mode else None), ptr(dz),
+                ptr(st["occu"]), ptr(G), ptr(ctx.ws), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), ptr(g_tilts),
+                ptr(g_dz), need, _stream()))
+        ctx.ws = None
+        # tensors that took no part in the forward get zero gradients, like unused leaves would get None
+        return (g_obja if n_obja else None, g_objp if n_objp else None, g_tilts if n_tilts else None,
+                g_dz if n_dz else None, g_probe if n_probe else None, g_shifts if n_shifts else None, None)
+
+
+class DataLossFunction(torch.autograd.Function):
+    """(single, poissn, pacbed) = f(dp, measurements[idx]); losses.py:36-89."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, dp, meas_all, idx, cfg, lcfg):
+        _require_cuda(dp, meas_all, idx)
+        dp = dp.contiguous()
+        B = dp.shape[0]
+        dev = dp.device
+        losses3 = torch.empty(3, dtype=torch.float32, device=dev)
+        stats = torch.empty(8, dtype=torch.float64, device=dev)
+        pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
+        _lib.check(_lib.lib().ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas_all), ptr(idx), B,
+                                                   ptr(losses3), ptr(stats), ptr(pac), _stream()))
+        ctx.save_for_backward(dp, meas_all, idx, stats)
+        ctx.pac, ctx.cfg, ctx.lcfg = pac, cfg, lcfg
+        return losses3
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, up):
+        dp, meas_all, idx, stats = ctx.saved_tensors
+        G = torch.empty_like(dp)
+        up = up.contiguous().float()
+        _lib.check(_lib.lib().ptyb200_loss_grad(C.byref(ctx.cfg), C.byref(ctx.lcfg), ptr(dp), ptr(meas_all), ptr(idx), dp.shape[0],
+                                                ptr(stats), ptr(ctx.pac), ptr(up), ptr(G), _stream()))
+        return G, None, None, None, None
+
+
+class SparseLossFunction(torch.autograd.Function):
+    """loss_sparse on the batch ROIs of objp without materialising the patches; losses.py:91-104."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, objp, crop_pos, idx, occu, cfg, lcfg):
+        _require_cuda(objp, crop_pos, idx, occu)
+        objp = objp.contiguous()
+        dev = objp.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(crop_pos), ptr(idx), idx.numel(),
+                                                     ptr(occu), ptr(loss), ptr(Ssum), _stream()))
+        ctx.save_for_backward(objp, crop_pos, idx, occu, Ssum)
+        ctx.cfg, ctx.lcfg = cfg, lcfg
+        return loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, up):
+        objp, crop_pos, idx, occu, Ssum = ctx.saved_tensors
+        cfg = ctx.cfg
+        g = torch.zeros_like(objp)
+        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=objp.device)
+        up = up.reshape(1).contiguous().float()
+        _lib.check(_lib.lib().ptyb200_sparse_grad(C.byref(cfg), C.byref(ctx.lcfg), ptr(objp), ptr(crop_pos), ptr(idx), idx.numel(),
+                                                  ptr(occu), ptr(Ssum), ptr(up), ptr(cover), ptr(g), _stream()))
+        return g, None, None, None, None, None

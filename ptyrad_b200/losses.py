@@ -1,0 +1,92 @@
+"""Drop-in ``CombinedLoss`` (reference ``src/ptyrad/losses.py:17-155``) backed by the CUDA library.
+
+Same constructor, same call signature ``loss_fn(model_DP, measured_DP, object_patches, omode_occu) -> (total, [single,
+poissn, pacbed, sparse, simlar])``, same key order of ``loss_params`` (it defines the log order,
+reconstruction.py:687,769); inactive terms are 0-dim zeros.  The three data terms are one native reduction +
+one native gradient kernel (``engine.DataLossFunction``); ``loss_sparse`` is evaluated on the batch ROIs natively when
+``object_patches`` is the ``LazyPatches`` handle our model hands out, and with plain tensor ops when a caller passes a
+materialised patch tensor.  ``loss_simlar`` (mixed-object regulariser) is tensor ops on materialised patches.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine
+from .models import LazyPatches, gaussian_blur5
+
+
+class CombinedLoss(torch.nn.Module):
+    def __init__(self, loss_params, device="cuda"):
+        super().__init__()
+        self.device = device
+        self.loss_params = loss_params
+        self._lcfg = engine.make_loss_cfg(loss_params)
+
+    # data terms -------------------------------------------------------------------------------------
+    def _data_losses(self, model_DP, measured_DP):
+        lp = self.loss_params
+        if not (lp["loss_single"]["state"] or lp["loss_poissn"]["state"] or lp["loss_pacbed"]["state"]):
+            z = torch.zeros((), dtype=torch.float32, device=model_DP.device)
+            return z, z.clone(), z.clone()
+        B, N = model_DP.shape[0], model_DP.shape[-1]
+        if isinstance(measured_DP, MeasurementView):
+            meas_all, idx = measured_DP.all, measured_DP.idx
+        else:
+            meas_all = measured_DP.contiguous().float()
+            idx = torch.arange(B, dtype=torch.int64, device=model_DP.device)
+        cfg = engine.make_cfg(N, 1, 1, 1, N, N, meas_all.shape[0], 0, 0, 0, 1.0, 1.0)
+        l3 = engine.DataLossFunction.apply(model_DP, meas_all, idx, cfg, self._lcfg)
+        return l3[0], l3[1], l3[2]
+
+    def get_loss_single(self, model_DP, measured_DP):
+        return self._data_losses(model_DP, measured_DP)[0]
+
+    def get_loss_poissn(self, model_DP, measured_DP):
+        return self._data_losses(model_DP, measured_DP)[1]
+
+    def get_loss_pacbed(self, model_DP, measured_DP):
+        return self._data_losses(model_DP, measured_DP)[2]
+
+    # object regularisers ----------------------------------------------------------------------------
+    def get_loss_sparse(self, objp_patches, omode_occu):
+        sp = self.loss_params["loss_sparse"]
+        if not sp["state"]:
+            return torch.zeros((), dtype=torch.float32, device=omode_occu.device)
+        if isinstance(objp_patches, LazyPatches):
+            m = objp_patches.model
+            return engine.SparseLossFunction.apply(m.opt_objp, m.crop_pos, objp_patches.idx, omode_occu, m._cfg(False), self._lcfg)
+        n = sp["ln_order"]
+        return sp["weight"] * (objp_patches.abs().pow(n).mean(dim=(0, 2, 3, 4)).pow(1.0 / n) * omode_occu).sum()
+
+    def get_loss_simlar(self, object_patches, omode_occu):
+        s = self.loss_params["loss_simlar"]
+        if not s["state"]:
+            return torch.zeros((), dtype=torch.float32, device=omode_occu.device)
+        if isinstance(object_patches, LazyPatches):
+            object_patches = object_patches.materialize()
+        sf = s.get("scale_factor")
+        tot = torch.zeros((), dtype=torch.float32, device=omode_occu.device)
+        for name, x in (("amplitude", object_patches[..., 0]), ("phase", object_patches[..., 1])):
+            if s["obj_type"] not in (name, "both"):
+                continue
+            if s.get("blur_std"):
+                x = gaussian_blur5(x, s["blur_std"])
+            if sf is not None and any(f != 1 for f in sf):
+                x = torch.nn.functional.interpolate(x, scale_factor=tuple(sf), mode="area")
+            tot = tot + (x * omode_occu[:, None, None, None]).std(1).mean()
+        return s["weight"] * tot
+
+    def forward(self, model_DP, measured_DP, object_patches, omode_occu):
+        single, poissn, pacbed = self._data_losses(model_DP, measured_DP)
+        objp = object_patches if isinstance(object_patches, LazyPatches) else object_patches[..., 1]
+        losses = [single, poissn, pacbed, self.get_loss_sparse(objp, omode_occu), self.get_loss_simlar(object_patches, omode_occu)]
+        return sum(losses), losses
+
+
+class MeasurementView:
+    """(all measurements, batch indices) pair: lets the native loss read rows ``idx`` of the (Ntot,N,N) array in place
+    instead of a gathered copy.  ``PtychoAD.get_measurements`` keeps returning a real tensor for compatibility; the fast
+    step (``ptyrad_b200.step.recon_batch``) passes this view."""
+
+    def __init__(self, all_meas, idx):
+        self.all, self.idx = all_meas, idx
