@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the multislice reconstruction step (BASELINE.json metric: diffraction patterns / s for a full
+forward + loss + backward + optimizer iteration; % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl ours|reference]
+
+One "step" = one batch of the workload through the hot path: zero-grad, forward, loss, adjoint, (gradient all-reduce),
+Adam step -- the body of the reference's recon_step loop (reconstruction.py:741-770).  N > 1 is launched by torchrun, one
+rank per GPU; scan positions shard across ranks (weak scaling: every rank runs a full `batch` of its own).
+
+Printed JSON (rank 0, one line): see README / DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "diffraction patterns/sec (fwd+bwd iter)"
+UNIT = "patterns/s"
+
+
+def bytes_per_pattern(c):
+    """compulsory = N^2(16 M Z + 4): ROI (a,phi) read + ROI gradient write + measurement read;
+    stash adds 16 P M Z N^2 (write + re-read of psi_z for the adjoint)."""
+    comp = c.N * c.N * (16 * c.M * c.Z + 4)
+    return comp, comp + 16 * c.P * c.M * c.Z * c.N * c.N
+
+
+def flop_per_pattern(c):
+    """n_fft = 2 P M (2Z-1) + 2P tile FFTs at 5 N^2 log2(N^2), plus ~ (6 mul-flops) pointwise complex work per FFT input."""
+    n_fft = 2 * c.P * c.M * (2 * c.Z - 1) + 2 * c.P
+    return n_fft * (5 * c.N * c.N * np.log2(c.N * c.N) + 8 * c.N * c.N)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(cfg, iv, mp, lp, batch_cpu, steps, warmup, threads):
+    """The oracle port of the reference's torch path, timed on the host cores (test infrastructure used as the baseline only)."""
+    import torch
+    from oracle.ptycho_torch import OracleTrainer
+    from ptyrad_b200.synthetic import random_batches
+    tr = OracleTrainer(iv, mp, lp, threads=threads)
+    batches = random_batches(iv["crop_pos"].shape[0], batch_cpu, seed=99)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        tr.step(batches[s % len(batches)][:batch_cpu])
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch_cpu / statistics.median(times), statistics.median(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch size")
+    ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from ptyrad_b200.synthetic import CONFIGS, make_inputs, random_batches
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg.batch
+    threads = os.cpu_count() or 1
+    workload = (f"{cfg.name}: {cfg.P} probe modes, {cfg.M} object modes, {cfg.Z} slices, {cfg.N}^2 patterns, "
+                f"{cfg.scan}x{cfg.scan} scan, batch {B}/GPU, Adam, loss_{cfg.loss}+sparse")
+    config = {"workload": workload, "cfg": cfg.name, "N": cfg.N, "P": cfg.P, "M": cfg.M, "Z": cfg.Z, "scan": cfg.scan,
+              "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+              "l2": "per-step working set (wave stash) >> 126 MB L2, no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64))
+        b_cpu = min(B, 64 if cfg.N <= 128 else 8)
+        rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), threads)
+        sample = f"{b_cpu} patterns/step of the {cfg.name} workload (same model, reduced batch), median step time"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from ptyrad_b200 import PtychoAD, CombinedLoss, MeasurementView, _lib
+    from ptyrad_b200.step import GradArena, recon_batch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64))
+    Ntot = iv["crop_pos"].shape[0]
+    model = PtychoAD(iv, mp, device=dev, verbose=False)
+    model.kernel_path = {"auto": _lib.PATH_AUTO, "general": _lib.PATH_GENERAL, "fused": _lib.PATH_FUSED}[args.path]
+    loss_fn = CombinedLoss(lp, device=dev)
+    opt = torch.optim.Adam(model.optimizable_params)
+    arena = GradArena(model)
+    # every rank runs its own batches (weak scaling): rank r takes batches r, r+world, ... of a seeded permutation
+    batches = random_batches(Ntot, B, seed=7)
+    batches = [b[:B] for b in batches]
+    my = [torch.as_tensor(batches[(i * world + rank) % len(batches)], device=dev) for i in range(max(4, min(len(batches), 64)))]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _lib.lib()
+    for s in range(args.warmup):
+        recon_batch(model, loss_fn, opt, my[s % len(my)], arena, world)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.ptyb200_timing_enable(1)
+    l0 = lib.ptyb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for s in range(args.steps):
+        last = recon_batch(model, loss_fn, opt, my[s % len(my)], arena, world)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = lib.ptyb200_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    import ctypes as C
+    tf, tb, nf, nb = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+    lib.ptyb200_timing_read(C.byref(tf), C.byref(tb), C.byref(nf), C.byref(nb))
+    lib.ptyb200_timing_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps * B * world / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ end-to-end: host buffers, H2D + D2H every step
+    e2e = None
+    if not args.no_e2e:
+        k2 = min(args.steps, 40)
+        nn = cfg.N * cfg.N
+        host_meas = [torch.from_numpy(np.ascontiguousarray(iv["measurements"][my[i % len(my)].cpu().numpy()])).pin_memory() for i in range(min(8, len(my)))]
+        host_idx = [my[i % len(my)].cpu().pin_memory() for i in range(len(host_meas))]
+        dev_meas = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
+        dev_idx = torch.empty(B, dtype=torch.int64, device=dev)
+        ar = torch.arange(B, device=dev)
+        host_loss = torch.empty(5, dtype=torch.float32).pin_memory()
+        sync_all()
+        t0 = time.perf_counter()
+        for s in range(k2):
+            j = s % len(host_meas)
+            dev_meas.copy_(host_meas[j], non_blocking=True)
+            dev_idx.copy_(host_idx[j], non_blocking=True)
+            l5 = recon_batch(model, loss_fn, opt, dev_idx, arena, world, measurements=MeasurementView(dev_meas, ar))
+            host_loss.copy_(l5, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        sync_all()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": k2 * B * world / dt, "unit": UNIT, "h2d_bytes_per_step": B * nn * 4 + B * 8, "d2h_bytes_per_step": 20,
+               "steps": k2, "api": "PtychoAD.forward + CombinedLoss + backward + Adam.step via ptyrad_b200.step.recon_batch"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    comp, stash = bytes_per_pattern(cfg)
+    # adjoint section (dominant): re-reads the stash, reads the ROIs, read-modify-writes the ROI gradients, reads G
+    bwd_bytes = B * (8 * cfg.P * cfg.M * cfg.Z + 16 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
+    fwd_bytes = B * (8 * cfg.P * cfg.M * cfg.Z + 8 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
+    ms_b = tb.value / max(1, nb.value)
+    ms_f = tf.value / max(1, nf.value)
+    ach_b = bwd_bytes / (ms_b * 1e-3) / 1e9 if ms_b > 0 else 0.0
+    flops = flop_per_pattern(cfg)
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "multislice adjoint section (ptyb200_backward)", "achieved": ach_b, "peak": peak,
+                     "unit": "GB/s", "frac": ach_b / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": ms_b,
+                     "share_of_step": ms_b / (ms / args.steps) if ms > 0 else None},
+        "roofline_forward": {"bound": "hbm", "achieved": fwd_bytes / (ms_f * 1e-3) / 1e9 if ms_f > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                             "ms_per_launch": ms_f},
+        "roofline_step": {"hbm_frac_stash_convention": value / world * stash / (peak * 1e9),
+                          "hbm_frac_compulsory": value / world * comp / (peak * 1e9),
+                          "fp32_tflops": value / world * flops / 1e12, "fp32_peak_nominal_tflops": fp32_peak,
+                          "fp32_frac": value / world * flops / 1e12 / fp32_peak, "bytes_per_pattern_stash": stash,
+                          "flop_per_pattern": flops},
+        "losses_last_step": [float(x) for x in last.cpu()],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        b_cpu = min(B, 64 if cfg.N <= 128 else 8)
+        rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, 6, 1, threads)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{b_cpu} patterns/step of the same workload, 1 warm-up + 6 timed steps, median ({med * 1e3:.0f} ms/step)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,14 @@ typedef struct ptyb200_loss_cfg {
 int         ptyb200_abi_version(void);
 const char* ptyb200_last_error(void);
 
+/* Instrumentation for bench.py (no reference counterpart): number of kernels this library has launched so far, and
+ * CUDA-event timing of the multislice forward / adjoint sections on the caller's stream (the sections exclude the
+ * small per-step setup and finish kernels).  timing_read synchronises on the recorded events, returns the summed
+ * milliseconds and the number of sections since the last read (at most 256 are kept), and resets. */
+long long   ptyb200_launch_count(void);
+void        ptyb200_timing_enable(int on);
+int         ptyb200_timing_read(double* ms_forward, double* ms_backward, int* n_forward, int* n_backward);
+
 /* Bytes of caller-owned scratch one forward/backward pair of batch size B needs (wave stash for the
  * adjoint, transposed wave buffers, complex object, gradient scratch).  One workspace per in-flight
  * forward: the LBFGS closure (reconstruction.py:705-718) keeps several alive. */

@@ -40,6 +40,9 @@ _P = C.c_void_p
 _SIGNATURES = {
     "ptyb200_abi_version": (C.c_int, []),
     "ptyb200_last_error": (C.c_char_p, []),
+    "ptyb200_launch_count": (C.c_longlong, []),
+    "ptyb200_timing_enable": (None, [C.c_int]),
+    "ptyb200_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ptyb200_workspace_bytes": (C.c_size_t, [C.POINTER(Cfg), C.c_int32]),
     "ptyb200_propagator": (C.c_int, [C.POINTER(Cfg), _P, _P, _P]),
     "ptyb200_gather_patches": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, _P, _P]),

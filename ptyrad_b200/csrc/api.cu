@@ -13,6 +13,26 @@ using namespace ptyb;
 namespace {
 
 thread_local std::string g_err;
+long long g_launches = 0;          // kernels launched by this library (bench.py reports it as gpu_launches)
+
+// optional per-section device timing (bench.py roofline): event pairs around the multislice forward / adjoint sections
+constexpr int kMaxEv = 256;
+struct Timing {
+    bool on = false;
+    cudaEvent_t ev[2][kMaxEv][2];
+    int n[2] = {0, 0};
+    bool created = false;
+} g_tm;
+void tm_mark(int section, int which, cudaStream_t st) {
+    if (!g_tm.on) return;
+    if (!g_tm.created) {
+        for (int s = 0; s < 2; ++s) for (int i = 0; i < kMaxEv; ++i) { cudaEventCreate(&g_tm.ev[s][i][0]); cudaEventCreate(&g_tm.ev[s][i][1]); }
+        g_tm.created = true;
+    }
+    if (g_tm.n[section] >= kMaxEv) return;
+    cudaEventRecord(g_tm.ev[section][g_tm.n[section]][which], st);
+    if (which == 1) ++g_tm.n[section];
+}
 
 int fail(const char* what, cudaError_t e, const char* file, int line) {
     char buf[512];
@@ -27,7 +47,7 @@ int fail_msg(const std::string& m) { g_err = m; return 2; }
         cudaError_t e_ = (call);                                        \
         if (e_ != cudaSuccess) return fail(#call, e_, __FILE__, __LINE__); \
     } while (0)
-#define CKL() CK(cudaGetLastError())
+#define CKL() do { ++g_launches; CK(cudaGetLastError()); } while (0)
 
 size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -202,6 +222,24 @@ LossK make_lossk(const ptyb200_loss_cfg& l) {
 extern "C" {
 
 int ptyb200_abi_version(void) { return PTYB200_ABI_VERSION; }
+long long ptyb200_launch_count(void) { return g_launches; }
+void ptyb200_timing_enable(int on) { g_tm.on = on != 0; g_tm.n[0] = g_tm.n[1] = 0; }
+int ptyb200_timing_read(double* ms_forward, double* ms_backward, int* n_forward, int* n_backward) {
+    double acc[2] = {0, 0};
+    for (int s = 0; s < 2; ++s)
+        for (int i = 0; i < g_tm.n[s]; ++i) {
+            float ms = 0.f;
+            CK(cudaEventSynchronize(g_tm.ev[s][i][1]));
+            CK(cudaEventElapsedTime(&ms, g_tm.ev[s][i][0], g_tm.ev[s][i][1]));
+            acc[s] += ms;
+        }
+    if (ms_forward) *ms_forward = acc[0];
+    if (ms_backward) *ms_backward = acc[1];
+    if (n_forward) *n_forward = g_tm.n[0];
+    if (n_backward) *n_backward = g_tm.n[1];
+    g_tm.n[0] = g_tm.n[1] = 0;
+    return 0;
+}
 const char* ptyb200_last_error(void) { return g_err.c_str(); }
 
 size_t ptyb200_workspace_bytes(const ptyb200_cfg* cfg, int32_t B) {
@@ -238,8 +276,10 @@ int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const f
     if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
         if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
+        tm_mark(0, 0, st);
         if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, w.fused, st, g_err)) return r; }
         else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
+        tm_mark(0, 1, st);
     });
     return 0;
 }
@@ -277,8 +317,10 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (need_dz) CK(cudaMemsetAsync(g_dz, 0, 4, st));
     if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
+        tm_mark(1, 0, st);
         if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, w.fused, (float2*)g_probe, w.tmpP, st, g_err)) return r; }
         else if (int r = backward_general<F>(*c, B, w, a, g_probe, st)) return r;
+        tm_mark(1, 1, st);
         if (use_fused(*c) && a.need_probe && c->shift_probes)
             if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, st)) return r;
     });

@@ -166,7 +166,7 @@ def test_adjoint_dot_product_full_size():
     (dp * G).sum().backward()
     d_objp = torch.randn(model.opt_objp.shape, device="cuda", generator=g)
     lhs_adj = float((model.opt_objp.grad.double() * d_objp.double()).sum())
-    h = 1e-2
+    h = 2e-3
     with torch.no_grad():
         model.opt_objp.add_(h * d_objp)
         dpp = model(idx)
