@@ -277,7 +277,7 @@ int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const f
     DISPATCH_N(c->N, {
         if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
         tm_mark(0, 0, st);
-        if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, w.fused, st, g_err)) return r; }
+        if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, w.fused, st, g_err, &g_launches)) return r; }
         else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
         tm_mark(0, 1, st);
     });
@@ -318,7 +318,7 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
         tm_mark(1, 0, st);
-        if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, w.fused, (float2*)g_probe, w.tmpP, st, g_err)) return r; }
+        if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)) return r; }
         else if (int r = backward_general<F>(*c, B, w, a, g_probe, st)) return r;
         tm_mark(1, 1, st);
         if (use_fused(*c) && a.need_probe && c->shift_probes)

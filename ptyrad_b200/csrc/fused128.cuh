@@ -1,12 +1,511 @@
-// Fused on-chip N = 128 multislice kernels (placeholder until the register-resident path lands).
+// Fused on-chip multislice kernels for N = 128 (sm_100a).
+//
+// One CTA of 512 threads keeps one 128x128 complex wave entirely in REGISTERS (32 complex values per thread,
+// 128 KB = half of the SM's register file) and carries it through every slice: transmission multiply, 2-D FFT,
+// propagator multiply, inverse 2-D FFT -- the wave never returns to HBM except for the one stash store per slice
+// that the adjoint needs.  Shared memory (132 KB) is only the exchange medium of the FFT:
+//
+//   layout R (real space)   thread t: x = t & 127, yl = t >> 7;          v[k] = psi[yl + 4k][x]
+//   layout F (Fourier)      thread t: w2 = t >> 5, l = t & 31, rsel = l >> 4, q = (l >> 2) & 3, vv = l & 3;
+//                                                                         v[u] = X[w2 + 16 rsel + 32 q][vv + 4u]
+//   forward 2-D FFT (R -> F): DFT32 over k in registers (y, stride 4)        -> exchange E1 through smem (CTA wide)
+//                             y-twiddle, 4x4 DFT (rest of y and of x), x-twiddle -> exchange E2 (warp local, same smem)
+//                             DFT32 over j in registers (x)
+//   inverse (F -> R): the same stages backwards with conjugate twiddles.
+//
+// So a 2-D FFT costs two shared-memory round trips (4 x 128 KB of smem traffic) instead of the eight of a row/column
+// slab FFT, the DFT32 twiddles are compile-time immediates, every global access of layout R is a 256-byte coalesced
+// row segment (ROI gather, stash, gradient scatter), and layout-F side tables (propagator, probe spectrum, dL/dI)
+// are pre-permuted so that they are read thread-privately and coalesced.  tools/proto_fused128.py is the NumPy
+// model of this index algebra.
+//
+// Forward: grid (P, M, B), one wave per CTA.  Adjoint: one CTA per (sample, object mode) looping over the probe modes
+// so that gO_z = sum_p conj(psi_z) gphi_z is accumulated in a CTA-private, L2-resident scratch and scattered into the
+// dense object gradient with ONE red.global.add.v2.f32 per pixel and slice.
 #pragma once
 #include "general_kernels.cuh"
 #include "../../include/ptyrad_b200.h"
 #include <string>
+#include <cstring>
 
-namespace ptyb { namespace fused128 {
-inline size_t scratch_bytes(const ptyb200_cfg&, int) { return 0; }
-inline bool covers(const ptyb200_cfg&) { return false; }
-inline int forward(const ptyb200_cfg&, int, FwdArgs, unsigned char*, cudaStream_t, std::string& err) { err = "fused path not built"; return 3; }
-inline int backward(const ptyb200_cfg&, int, BwdArgs, unsigned char*, float2*, float2*, cudaStream_t, std::string& err) { err = "fused path not built"; return 3; }
-}}
+namespace ptyb {
+namespace fused128 {
+
+constexpr int FN = 128;
+constexpr int FT = 512;                 // threads per CTA
+constexpr int CH = 528;                 // elements per chunk region (512 used by E1, 16 rows x 33 by E2)
+constexpr int E_ELEMS = 32 * CH;        // 16896 float2 = 135168 B
+constexpr int TILE = FN * FN;           // 16384
+constexpr size_t SMEM_BYTES = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + sizeof(float) * TILE + 128 * sizeof(float);
+
+struct Args {
+    FwdArgs f;
+    const float2* HF;       // (TILE) layout F, pre-scaled by 1/N^2
+    const float2* PhatF;    // (P, TILE) layout F, pre-scaled by 1/N^2
+    float* Ipart;           // (B, M, P, TILE) layout F partial intensities
+    float2* phisF;          // (B,P,M,Z-1,TILE) layout F or null
+    // adjoint only
+    const float* G;
+    float2* gO;
+    float2* gPhatF;         // (P, TILE) layout F
+    float2* gprobe;         // (P, N, N) natural (unshifted probes)
+    float* gprop;
+    float* gshift;
+    float2* acc;            // (slots, Z, TILE) CTA-private gO accumulators
+    float dx, k0;
+    int shift, need_obj, need_probe, need_shift, need_prop, units;
+};
+
+struct Geo {
+    int t, x, yl, w2, lane, rsel, e16, ky, vv;
+    __device__ __forceinline__ Geo() {
+        t = threadIdx.x; x = t & 127; yl = t >> 7; w2 = t >> 5; lane = t & 31;
+        rsel = lane >> 4; e16 = lane & 15; vv = lane & 3;
+        ky = w2 + 16 * rsel + 32 * ((lane >> 2) & 3);
+    }
+    __device__ __forceinline__ int kx(int u) const { return vv + 4 * u; }
+};
+
+// ---- the 2-D FFT over registers + shared memory -------------------------------------------------------------
+// tw[n] = exp(-2 pi i n / 128), n < 128 (shared memory)
+template <int DIR> __device__ __forceinline__ float2 twd(const float2* tw, int e) {
+    float2 w = tw[e];
+    if (DIR > 0) w.y = -w.y;
+    return w;
+}
+
+__device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const float2* tw, const Geo& g) {
+    Dft<32, -1>::run(v);
+    __syncthreads();                                   // earlier readers of E are done
+    {
+        float2* p = E + g.yl * 128 + g.x;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) p[r * CH] = v[r];
+    }
+    __syncthreads();
+    const int j = g.lane;
+    float2 xt[4];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) xt[c] = tw[j * c];
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) {
+        const int r = g.w2 + 16 * rs;
+        float2* ch = E + r * CH;
+        float2 a[4][4];                                // [yl][s]
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) a[y][s] = ch[y * 128 + j + 32 * s];
+        __syncwarp();
+#pragma unroll
+        for (int y = 1; y < 4; ++y) {
+            const float2 w = tw[y * r];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) a[y][s] = cmul(a[y][s], w);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {                  // DFT4 over yl -> q
+            float2 c[4] = {a[0][s], a[1][s], a[2][s], a[3][s]};
+            Dft<4, -1>::run(c);
+            a[0][s] = c[0]; a[1][s] = c[1]; a[2][s] = c[2]; a[3][s] = c[3];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                  // DFT4 over s -> vv, x-twiddle, store transposed
+            Dft<4, -1>::run(a[q]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float2 o = c ? cmul(a[q][c], xt[c]) : a[q][c];
+                ch[(q * 4 + c) * 33 + j] = o;
+            }
+        }
+    }
+    __syncwarp();
+    {
+        const float2* p = E + (g.w2 + 16 * g.rsel) * CH + g.e16 * 33;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = p[jj];
+    }
+    Dft<32, -1>::run(v);
+}
+
+__device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const float2* tw, const Geo& g) {
+    Dft<32, +1>::run(v);
+    __syncthreads();                                   // earlier readers of E are done
+    {
+        float2* p = E + (g.w2 + 16 * g.rsel) * CH + g.e16 * 33;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) p[jj] = v[jj];
+    }
+    __syncwarp();
+    const int j = g.lane;
+    float2 xt[4];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) xt[c] = cconj(tw[j * c]);
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) {
+        const int r = g.w2 + 16 * rs;
+        float2* ch = E + r * CH;
+        float2 a[4][4];                                // [q][vv]
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float2 o = ch[(q * 4 + c) * 33 + j];
+                a[q][c] = c ? cmul(o, xt[c]) : o;
+            }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Dft<4, +1>::run(a[q]);      // over vv -> s
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {                           // over q -> yl
+            float2 c[4] = {a[0][s], a[1][s], a[2][s], a[3][s]};
+            Dft<4, +1>::run(c);
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                float2 o = y ? cmulc(c[y], tw[y * r]) : c[y];   // conj(W^{yl r})
+                ch[y * 128 + j + 32 * s] = o;
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const float2* p = E + g.yl * 128 + g.x;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = p[r * CH];
+    }
+    Dft<32, +1>::run(v);
+}
+
+// ---- shared memory carve ----------------------------------------------------------------------------------------
+struct Smem {
+    float2* E;      // exchange buffer
+    float2* tw;     // 128
+    float2* wy;     // 128 shift ramp (y), wx, tilt ramps ey, ex
+    float2* wx;
+    float2* ey;
+    float2* ex;
+    float* fl;      // TILE floats: dL/dI in layout F (adjoint)
+    float* red;     // 128 floats (block_sum scratch)
+};
+__device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
+    Smem s;
+    s.E = reinterpret_cast<float2*>(raw);
+    s.tw = s.E + E_ELEMS;
+    s.wy = s.tw + 128; s.wx = s.wy + 128; s.ey = s.wx + 128; s.ex = s.ey + 128;
+    s.fl = reinterpret_cast<float*>(s.ex + 128);
+    s.red = s.fl + TILE;
+    return s;
+}
+
+__device__ __forceinline__ void load_tables(const Smem& s, const Args& a, int b) {
+    for (int n = threadIdx.x; n < 128; n += blockDim.x) {
+        float sn, cs;
+        sincospif(-2.0f * float(n) / 128.0f, &sn, &cs);
+        s.tw[n] = make_float2(cs, sn);
+        if (a.f.wvec) {
+            s.wy[n] = a.f.wvec[((size_t)b * 2 + 0) * 128 + n];
+            s.wx[n] = a.f.wvec[((size_t)b * 2 + 1) * 128 + n];
+        }
+        if (a.f.tvec) {
+            s.ey[n] = a.f.tvec[((size_t)b * 2 + 0) * 128 + n];
+            s.ex[n] = a.f.tvec[((size_t)b * 2 + 1) * 128 + n];
+        }
+    }
+}
+
+// ---- layout-F permutation helpers (setup / finish) --------------------------------------------------------------------
+// srcT is [kx][ky] (the general path's transposed spectra); dstF[c][u*512 + t]
+__global__ void k_permute_to_F(const float2* __restrict__ srcT, float2* __restrict__ dstF, float scale) {
+    const int c = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // u*512 + t
+    const int u = i >> 9, t = i & 511;
+    const int w2 = t >> 5, lane = t & 31;
+    const int ky = w2 + 16 * (lane >> 4) + 32 * ((lane >> 2) & 3), kx = (lane & 3) + 4 * u;
+    dstF[(size_t)c * TILE + i] = cscale(srcT[(size_t)c * TILE + kx * 128 + ky], scale);
+}
+__global__ void k_unpermute_from_F(const float2* __restrict__ srcF, float2* __restrict__ dstT) {
+    const int c = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = i >> 9, t = i & 511;
+    const int w2 = t >> 5, lane = t & 31;
+    const int ky = w2 + 16 * (lane >> 4) + 32 * ((lane >> 2) & 3), kx = (lane & 3) + 4 * u;
+    dstT[(size_t)c * TILE + kx * 128 + ky] = srcF[(size_t)c * TILE + i];
+}
+
+// dp[b][Y][X] = eps + sum_{m,p} Ipart[b,m,p][F index of (ky,kx)],  (Y,X) = fftshift(ky,kx).  grid (TILE/256, B)
+__global__ void k_dp_reduce(const float* __restrict__ Ipart, float* __restrict__ dp, int MP, float eps) {
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = pix >> 7, X = pix & 127;
+    const int ky = (Y + 64) & 127, kx = (X + 64) & 127;
+    const int r = ky & 31, w2 = r & 15, rsel = r >> 4, q = ky >> 5, vv = kx & 3, u = kx >> 2;
+    const int i = u * 512 + w2 * 32 + rsel * 16 + q * 4 + vv;
+    float acc = 0.f;
+    for (int c = 0; c < MP; ++c) acc += Ipart[((size_t)b * MP + c) * TILE + i];
+    dp[(size_t)b * TILE + pix] = acc + eps;
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve_smem(smem_raw);
+    const Geo g;
+    const Dims& d = a.f.d;
+    const int p = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
+    const int64_t n0 = a.f.idx[b];
+    const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
+    load_tables(s, a, b);
+    __syncthreads();
+    const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+    float2 v[32];
+    if (a.shift) {
+        const float2* ph = a.PhatF + (size_t)p * TILE + g.t;
+        const float2 wyv = s.wy[g.ky];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = cmul(ph[u * 512], cmul(wyv, s.wx[g.kx(u)]));
+        fft2_F_to_R(v, s.E, s.tw, g);
+    } else {
+        const float2* pr = a.f.probe + (size_t)p * TILE + g.yl * 128 + g.x;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = pr[k * 512];
+    }
+    const float2 eyv = a.f.tvec ? s.ey[g.ky] : make_float2(1.f, 0.f);
+    for (int z = 0; z < d.Z; ++z) {
+        float2* st = a.f.stash + (tile * d.Z + z) * TILE + g.yl * 128 + g.x;
+        const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+        const size_t ostr = (size_t)4 * d.Nox;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            st[k * 512] = v[k];
+            v[k] = cmul(v[k], Oz[k * ostr]);
+        }
+        fft2_R_to_F(v, s.E, s.tw, g);
+        if (z < d.Z - 1) {
+            const float2* hf = a.HF + g.t;
+            float2* ph = a.phisF ? a.phisF + (tile * (d.Z - 1) + z) * TILE + g.t : nullptr;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                if (ph) ph[u * 512] = v[u];
+                float2 h = hf[u * 512];
+                if (a.f.tvec) h = cmul(h, cmul(eyv, s.ex[g.kx(u)]));
+                v[u] = cmul(v[u], h);
+            }
+            fft2_F_to_R(v, s.E, s.tw, g);
+        }
+    }
+    // far field: partial intensity of this (object mode, probe mode) in layout F; k_dp_reduce sums and fftshifts
+    const float oc = a.f.occu[m] * (1.0f / (128.0f * 128.0f));
+    float* ip = a.Ipart + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) ip[u * 512] = oc * cabs2(v[u]);
+}
+
+// ---- adjoint --------------------------------------------------------------------------------------------------------
+// persistent over units (b, m): unit = blockIdx.x + i*gridDim.x; slot = blockIdx.x owns a (Z, TILE) accumulator
+__global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem s = carve_smem(smem_raw);
+    const Geo g;
+    const Dims& d = a.f.d;
+    float2* accb = a.acc + (size_t)blockIdx.x * d.Z * TILE + g.yl * 128 + g.x;
+    float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};           // Ky S, Kx S, (Kz-k0) S | shift-y, shift-x
+    for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
+        const int b = unit / d.M, m = unit % d.M;
+        const int64_t n0 = a.f.idx[b];
+        const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
+        __syncthreads();
+        load_tables(s, a, b);
+        {   // dL/dI in layout F, scaled: 2 occu_m G~ / N^2
+            const float sc = 2.0f * a.f.occu[m] * (1.0f / (128.0f * 128.0f));
+            const float* G = a.G + (size_t)b * TILE;
+            const int Yk = (g.ky + 64) & 127;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) s.fl[u * 512 + g.t] = sc * G[Yk * 128 + ((g.kx(u) + 64) & 127)];
+        }
+        __syncthreads();
+        const float2 eyv = a.f.tvec ? s.ey[g.ky] : make_float2(1.f, 0.f);
+        const size_t ostr = (size_t)4 * d.Nox;
+        s5[0] = s5[1] = s5[2] = 0.f;
+        for (int p = 0; p < d.P; ++p) {
+            const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+            float2 v[32];
+            {   // recompute the exit wave spectrum from the stashed psi_{Z-1}
+                const float2* st = a.f.stash + (tile * d.Z + (d.Z - 1)) * TILE + g.yl * 128 + g.x;
+                const float2* Oz = a.f.O + ((size_t)m * d.Z + (d.Z - 1)) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = cmul(st[k * 512], Oz[k * ostr]);
+            }
+            fft2_R_to_F(v, s.E, s.tw, g);
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = cscale(v[u], s.fl[u * 512 + g.t]);
+            fft2_F_to_R(v, s.E, s.tw, g);                 // gphi_{Z-1}
+            for (int z = d.Z - 1; z >= 0; --z) {
+                const float2* st = a.f.stash + (tile * d.Z + z) * TILE + g.yl * 128 + g.x;
+                const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+                float2* gOz = a.gO + ((size_t)m * d.Z + z) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+                float2* ac = accb + (size_t)z * TILE;
+                const int mode = !a.need_obj ? 4 : (d.P == 1 ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float2 psi = st[k * 512];
+                    float2 c = cmulc(v[k], psi);           // conj(psi) * gphi
+                    if (mode == 0) ac[k * 512] = c;
+                    else if (mode == 1) ac[k * 512] = cadd(ac[k * 512], c);
+                    else if (mode == 2) red_add_f2(gOz + k * ostr, cadd(ac[k * 512], c));
+                    else if (mode == 3) red_add_f2(gOz + k * ostr, c);
+                    v[k] = cmulc(v[k], Oz[k * ostr]);      // gpsi_z = conj(O_z) gphi_z
+                }
+                if (z > 0) {
+                    fft2_R_to_F(v, s.E, s.tw, g);
+                    const float2* hf = a.HF + g.t;
+                    const float2* ph = a.need_prop ? a.phisF + (tile * (d.Z - 1) + (z - 1)) * TILE + g.t : nullptr;
+                    const float Ky = a.need_prop ? kgrid(g.ky, 128, a.dx) : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        float2 h = hf[u * 512];
+                        if (a.f.tvec) h = cmul(h, cmul(eyv, s.ex[g.kx(u)]));
+                        v[u] = cmulc(v[u], h);             // conj(H)/N^2 * F2(gpsi)
+                        if (ph) {
+                            const float2 phi = ph[u * 512];
+                            const float sv = phi.x * v[u].y - phi.y * v[u].x;
+                            const float Kx = kgrid(g.kx(u), 128, a.dx);
+                            const float k2 = Kx * Kx + Ky * Ky;
+                            s5[0] += Ky * sv; s5[1] += Kx * sv; s5[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
+                        }
+                    }
+                    fft2_F_to_R(v, s.E, s.tw, g);
+                }
+            }
+            // v = gpsi_0 of this (probe mode, object mode)
+            if (a.need_probe || a.need_shift) {
+                if (a.shift) {
+                    fft2_R_to_F(v, s.E, s.tw, g);          // N^2 * T
+                    const float2* phf = a.PhatF + (size_t)p * TILE + g.t;      // Phat / N^2
+                    float2* gp = a.gPhatF + (size_t)p * TILE + g.t;
+                    const float2 wyv = s.wy[g.ky];
+                    const float kapy = float((g.ky + 64) & 127) * (1.0f / 128.0f);
+                    float sy = 0.f, sx = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        const float2 w = cmul(wyv, s.wx[g.kx(u)]);
+                        const float2 cw = cmulc(v[u], w);                      // conj(w') * N^2 T
+                        if (a.need_probe) red_add_f2(gp + u * 512, cscale(cw, 1.0f / (128.0f * 128.0f)));
+                        const float2 pv = phf[u * 512];
+                        const float qv = cw.y * pv.x - cw.x * pv.y;            // Im(conj(w') T conj(Phat))
+                        sy += kapy * qv;
+                        sx += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
+                    }
+                    s5[3] = sy; s5[4] = sx;
+                    if (a.need_shift) {
+                        float r2[2] = {sy, sx};
+                        block_sum<2>(r2, s.red);
+                        if (threadIdx.x == 0) {
+                            atomicAdd(a.gshift + 2 * n0 + 0, -6.283185307179586f * r2[0]);
+                            atomicAdd(a.gshift + 2 * n0 + 1, -6.283185307179586f * r2[1]);
+                        }
+                    }
+                } else if (a.need_probe) {
+                    float2* gp = a.gprobe + (size_t)p * TILE + g.yl * 128 + g.x;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) red_add_f2(gp + k * 512, v[k]);
+                }
+            }
+        }
+        if (a.need_prop) {
+            float r3[3] = {s5[0], s5[1], s5[2]};
+            block_sum<3>(r3, s.red);
+            if (threadIdx.x == 0) {
+                atomicAdd(a.gprop + 3 * b + 0, r3[0]);
+                atomicAdd(a.gprop + 3 * b + 1, r3[1]);
+                atomicAdd(a.gprop + 3 * b + 2, r3[2]);
+            }
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+constexpr int MAX_SLOTS = 148;
+
+struct Scratch {
+    float2 *HF, *PhatF, *gPhatF, *acc;
+    float* Ipart;
+    size_t total;
+};
+inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
+    Scratch s;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base + o; };
+    s.HF = (float2*)take((size_t)TILE * 8);
+    s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
+    s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
+    s.Ipart = (float*)take((size_t)B * c.M * c.P * TILE * 4);
+    s.acc = (float2*)take((size_t)MAX_SLOTS * c.Z * TILE * 8);
+    s.total = off;
+    return s;
+}
+inline bool covers(const ptyb200_cfg& c) { return c.N == 128; }
+inline size_t scratch_bytes(const ptyb200_cfg& c, int B) { return covers(c) ? carve_scratch(c, B, nullptr).total : 0; }
+
+inline int fail(std::string& err, const char* what, cudaError_t e) {
+    err = std::string("fused128: ") + what + ": " + cudaGetErrorString(e);
+    return 1;
+}
+#define F128_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(err, #call, e_); } while (0)
+
+inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc, float2* phis) {
+    Args a;
+    memset(&a, 0, sizeof a);
+    a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.Ipart = sc.Ipart; a.phisF = f.phis ? phis : nullptr;
+    a.gPhatF = sc.gPhatF; a.acc = sc.acc; a.shift = c.shift_probes;
+    return a;
+}
+
+// f.HT = transposed propagator [kx][ky]; f.PhatT = probe spectrum [kx][ky] (both made by setup_common)
+inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, unsigned char* scratch, cudaStream_t st, std::string& err, long long* launches) {
+    Scratch sc = carve_scratch(c, B, scratch);
+    Args a = make_args(c, f, sc, f.phis);
+    const float inv = 1.0f / (128.0f * 128.0f);
+    k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
+    F128_CK(cudaGetLastError()); ++*launches;
+    if (c.shift_probes) {
+        k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(f.PhatT, sc.PhatF, inv);
+        F128_CK(cudaGetLastError()); ++*launches;
+    }
+    F128_CK(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    k_forward<<<dim3(c.P, c.M, B), FT, SMEM_BYTES, st>>>(a);
+    F128_CK(cudaGetLastError()); ++*launches;
+    k_dp_reduce<<<dim3(TILE / 256, B), 256, 0, st>>>(sc.Ipart, f.dp, c.M * c.P, c.eps);
+    F128_CK(cudaGetLastError()); ++*launches;
+    return 0;
+}
+
+// adjoint; the caller zeroes gO / gPhatT / gprop / gshift and runs the probe-spectrum inverse FFT + object finish
+inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, unsigned char* scratch, float2* g_probe, float2* gPhatT,
+                    cudaStream_t st, std::string& err, long long* launches) {
+    Scratch sc = carve_scratch(c, B, scratch);
+    Args a = make_args(c, bw.f, sc, bw.f.phis);
+    a.G = bw.G; a.gO = bw.gO; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
+    a.dx = bw.dx; a.k0 = bw.k0;
+    a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
+    a.units = B * c.M;
+    if (a.need_probe) {
+        if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
+        else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
+    }
+    int dev = 0, sms = MAX_SLOTS;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = a.units < sms ? a.units : sms;
+    if (grid > MAX_SLOTS) grid = MAX_SLOTS;
+    F128_CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    k_backward<<<grid, FT, SMEM_BYTES, st>>>(a);
+    F128_CK(cudaGetLastError()); ++*launches;
+    if (a.need_probe && c.shift_probes) {
+        k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
+        F128_CK(cudaGetLastError()); ++*launches;
+    }
+    return 0;
+}
+
+}  // namespace fused128
+}  // namespace ptyb

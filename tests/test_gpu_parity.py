@@ -121,6 +121,41 @@ def test_tilt_and_thickness_gradients():
         _check(r, ref["dp"], ref["losses"], ref["grads"], label)
 
 
+@pytest.mark.parametrize("label", ["tilt_each+dz", "tilt_global", "noshift_single_slice", "noshift_multi", "poissn_pacbed"])
+def test_fused128_variants(label):
+    """Every branch of the fused N = 128 kernels (tilt ramps, propagator gradients, unshifted probes, Z = 1, mixed object
+    modes, all data losses) against the float64 oracle."""
+    from dataclasses import replace
+    from oracle.ptycho_torch import oracle_step
+    from ptyrad_b200 import _lib
+    from ptyrad_b200.synthetic import make_inputs, CONFIGS, default_loss_params
+    base = CONFIGS["T128"]
+    lp_over = None
+    if label == "tilt_each+dz":
+        cfg = replace(base, tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4)
+    elif label == "tilt_global":
+        cfg = replace(base, lr_tilts=1e-4, M=2)
+    elif label == "noshift_single_slice":
+        cfg = replace(base, lr_shifts=0.0, Z=1, P=1)
+    elif label == "noshift_multi":
+        cfg = replace(base, lr_shifts=0.0, P=3, M=2)
+    else:
+        cfg = replace(base, P=1)
+        lp_over = default_loss_params("single")
+        lp_over["loss_poissn"]["state"] = True
+        lp_over["loss_pacbed"]["state"] = True
+        lp_over["loss_sparse"]["ln_order"] = 2
+    iv, mp, lp = make_inputs(cfg, seed=31)
+    if label == "tilt_global":
+        iv["obj_tilts"] = np.array([[0.8, -0.5]], np.float32)
+    if lp_over is not None:
+        lp = lp_over
+    idx = np.array([0, 2, 5, 7, 11, 13, 15], dtype=np.int64)
+    ref = oracle_step(iv, mp, lp, idx, torch.float64)
+    r = _run(iv, mp, lp, idx, path=_lib.PATH_FUSED)
+    _check(r, ref["dp"], ref["losses"], ref["grads"], label)
+
+
 def test_frozen_parameters_cost_nothing_and_get_no_grad():
     from ptyrad_b200.synthetic import make_inputs
     iv, mp, lp = make_inputs("T64", seed=2)
