@@ -245,6 +245,30 @@ __global__ void k_dp_reduce(const float* __restrict__ Ipart, float* __restrict__
     dp[(size_t)b * TILE + pix] = acc + eps;
 }
 
+// ---- memory helpers -----------------------------------------------------------------------------------------------
+// fire-and-forget vector reduction; no "memory" clobber: nothing in these kernels reads the target back, and a clobber
+// would stop the compiler from hoisting the next loads above it
+__device__ __forceinline__ void red_f2(float2* addr, float2 v) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y));
+}
+// L2 prefetch of a contiguous range (TMA bulk prefetch: one instruction, no registers, no smem)
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+}
+// whole 128 KB tile: 32 lanes of warp 0 x 4 KB
+__device__ __forceinline__ void l2_prefetch_tile(const float2* tile) {
+    if (threadIdx.x < 32) l2_prefetch(tile + threadIdx.x * 512, 4096);
+}
+// the 128 ROI rows of one slice (1 KB each, 8-byte aligned -> round to 16)
+__device__ __forceinline__ void l2_prefetch_roi(const float2* plane, int cy, int cx, int Nox) {
+    if (threadIdx.x >= 32 && threadIdx.x < 160) {
+        const float2* row = plane + (size_t)(cy + threadIdx.x - 32) * Nox + cx;
+        l2_prefetch(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(row) & ~uintptr_t(15)), 1040);
+    }
+}
+
+constexpr int CHK = 4;     // pointwise phases load CHK values per stream ahead of use
+
 // ---- forward ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -254,170 +278,232 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     const int p = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
     const int64_t n0 = a.f.idx[b];
     const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
+    const float2* Oplane = a.f.O + (size_t)m * d.Z * d.Noy * d.Nox;
+    l2_prefetch_roi(Oplane, cy, cx, d.Nox);
     load_tables(s, a, b);
     __syncthreads();
     const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+    const size_t ostr = (size_t)4 * d.Nox;
+    const bool tilt = a.f.tvec != nullptr;
+    const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
     float2 v[32];
     if (a.shift) {
-        const float2* ph = a.PhatF + (size_t)p * TILE + g.t;
+        const float2* __restrict__ ph = a.PhatF + (size_t)p * TILE + g.t;
         const float2 wyv = s.wy[g.ky];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = cmul(ph[u * 512], cmul(wyv, s.wx[g.kx(u)]));
-        fft2_F_to_R(v, s.E, s.tw, g);
+        for (int u = 0; u < 32; ++u) v[u] = cmul(__ldg(ph + u * 512), cmul(wyv, s.wx[g.kx(u)]));
     } else {
-        const float2* pr = a.f.probe + (size_t)p * TILE + g.yl * 128 + g.x;
+        const float2* __restrict__ pr = a.f.probe + (size_t)p * TILE + g.yl * 128 + g.x;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = pr[k * 512];
+        for (int k = 0; k < 32; ++k) v[k] = __ldg(pr + k * 512);
     }
-    const float2 eyv = a.f.tvec ? s.ey[g.ky] : make_float2(1.f, 0.f);
-    for (int z = 0; z < d.Z; ++z) {
-        float2* st = a.f.stash + (tile * d.Z + z) * TILE + g.yl * 128 + g.x;
-        const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-        const size_t ostr = (size_t)4 * d.Nox;
+    for (int z = a.shift ? -1 : 0; z < d.Z; ++z) {
+        if (z >= 0) {
+            float2* __restrict__ st = a.f.stash + (tile * d.Z + z) * TILE + g.yl * 128 + g.x;
+            const float2* __restrict__ Oz = Oplane + (size_t)z * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+            if (z + 1 < d.Z) l2_prefetch_roi(Oplane + (size_t)(z + 1) * d.Noy * d.Nox, cy, cx, d.Nox);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            st[k * 512] = v[k];
-            v[k] = cmul(v[k], Oz[k * ostr]);
-        }
-        fft2_R_to_F(v, s.E, s.tw, g);
-        if (z < d.Z - 1) {
-            const float2* hf = a.HF + g.t;
-            float2* ph = a.phisF ? a.phisF + (tile * (d.Z - 1) + z) * TILE + g.t : nullptr;
+            for (int k0 = 0; k0 < 32; k0 += CHK) {
+                float2 o[CHK];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-                if (ph) ph[u * 512] = v[u];
-                float2 h = hf[u * 512];
-                if (a.f.tvec) h = cmul(h, cmul(eyv, s.ex[g.kx(u)]));
-                v[u] = cmul(v[u], h);
+                for (int i = 0; i < CHK; ++i) o[i] = __ldg(Oz + (k0 + i) * ostr);
+#pragma unroll
+                for (int i = 0; i < CHK; ++i) {
+                    st[(k0 + i) * 512] = v[k0 + i];
+                    v[k0 + i] = cmul(v[k0 + i], o[i]);
+                }
             }
-            fft2_F_to_R(v, s.E, s.tw, g);
+            fft2_R_to_F(v, s.E, s.tw, g);
+            if (z == d.Z - 1) break;
+            const float2* __restrict__ hf = a.HF + g.t;
+            float2* __restrict__ ph = a.phisF ? a.phisF + (tile * (d.Z - 1) + z) * TILE + g.t : nullptr;
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += CHK) {
+                float2 h[CHK];
+#pragma unroll
+                for (int i = 0; i < CHK; ++i) h[i] = __ldg(hf + (k0 + i) * 512);
+#pragma unroll
+                for (int i = 0; i < CHK; ++i) {
+                    const int u = k0 + i;
+                    if (ph) ph[u * 512] = v[u];
+                    if (tilt) h[i] = cmul(h[i], cmul(eyv, s.ex[g.kx(u)]));
+                    v[u] = cmul(v[u], h[i]);
+                }
+            }
         }
+        fft2_F_to_R(v, s.E, s.tw, g);
     }
     // far field: partial intensity of this (object mode, probe mode) in layout F; k_dp_reduce sums and fftshifts
     const float oc = a.f.occu[m] * (1.0f / (128.0f * 128.0f));
-    float* ip = a.Ipart + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
+    float* __restrict__ ip = a.Ipart + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
 #pragma unroll
     for (int u = 0; u < 32; ++u) ip[u * 512] = oc * cabs2(v[u]);
 }
 
 // ---- adjoint --------------------------------------------------------------------------------------------------------
-// persistent over units (b, m): unit = blockIdx.x + i*gridDim.x; slot = blockIdx.x owns a (Z, TILE) accumulator
+// gO accumulation over the probe modes.  MODE 0: first mode -> store; 1: middle -> read-modify-write;
+// 2: last mode -> scatter (accumulator + own) into the dense gradient; 3: single mode -> scatter own; 4: not wanted
+template <int MODE>
+__device__ __forceinline__ void accum_phase(float2 (&v)[32], const float2* __restrict__ st, const float2* __restrict__ Oz, size_t ostr,
+                                            float2* __restrict__ ac, float2* __restrict__ gOz) {
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += CHK) {
+        float2 ps[CHK], o[CHK], av[CHK];
+#pragma unroll
+        for (int i = 0; i < CHK; ++i) {
+            o[i] = __ldg(Oz + (k0 + i) * ostr);
+            if (MODE != 4) ps[i] = __ldg(st + (k0 + i) * 512);
+            if (MODE == 1 || MODE == 2) av[i] = ac[(k0 + i) * 512];
+        }
+#pragma unroll
+        for (int i = 0; i < CHK; ++i) {
+            const int k = k0 + i;
+            if (MODE != 4) {
+                float2 c = cmulc(v[k], ps[i]);                 // conj(psi) * gphi
+                if (MODE == 1 || MODE == 2) c = cadd(c, av[i]);
+                if (MODE == 0 || MODE == 1) ac[k * 512] = c;
+                else red_f2(gOz + k * ostr, c);
+            }
+            v[k] = cmulc(v[k], o[i]);                          // gpsi_z = conj(O_z) gphi_z
+        }
+    }
+}
+
+// persistent over units (b, m): unit = blockIdx.x + i*gridDim.x; slot = blockIdx.x owns a (Z, TILE) accumulator.
+// Per probe mode the loop runs "steps" s = Z .. 0 with ONE forward/inverse FFT call site:
+//   s = Z     : F2(psi_{Z-1} O_{Z-1}) * (2 occu G~ / N^2)            -> inverse -> gphi_{Z-1}
+//   s = z >= 1: F2(gpsi_z) * conj(H_n)/N^2 [+ propagator-gradient sums] -> inverse -> gphi_{z-1}
+//   s = 0     : F2(gpsi_0) -> probe-spectrum and shift gradients (only with shifted probes)
 __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
     const Geo g;
     const Dims& d = a.f.d;
     float2* accb = a.acc + (size_t)blockIdx.x * d.Z * TILE + g.yl * 128 + g.x;
-    float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};           // Ky S, Kx S, (Kz-k0) S | shift-y, shift-x
+    const bool tilt = a.f.tvec != nullptr;
+    const bool want_probe_fft = a.shift && (a.need_probe || a.need_shift);
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
         const int b = unit / d.M, m = unit % d.M;
         const int64_t n0 = a.f.idx[b];
         const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
+        const float2* Oplane = a.f.O + (size_t)m * d.Z * d.Noy * d.Nox;
         __syncthreads();
         load_tables(s, a, b);
         {   // dL/dI in layout F, scaled: 2 occu_m G~ / N^2
             const float sc = 2.0f * a.f.occu[m] * (1.0f / (128.0f * 128.0f));
-            const float* G = a.G + (size_t)b * TILE;
+            const float* __restrict__ G = a.G + (size_t)b * TILE;
             const int Yk = (g.ky + 64) & 127;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) s.fl[u * 512 + g.t] = sc * G[Yk * 128 + ((g.kx(u) + 64) & 127)];
+            for (int u = 0; u < 32; ++u) s.fl[u * 512 + g.t] = sc * __ldg(G + Yk * 128 + ((g.kx(u) + 64) & 127));
         }
         __syncthreads();
-        const float2 eyv = a.f.tvec ? s.ey[g.ky] : make_float2(1.f, 0.f);
+        const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
         const size_t ostr = (size_t)4 * d.Nox;
-        s5[0] = s5[1] = s5[2] = 0.f;
+        float s3[3] = {0.f, 0.f, 0.f};                  // Ky S, Kx S, (Kz-k0) S
         for (int p = 0; p < d.P; ++p) {
             const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+            const float2* stash_t = a.f.stash + tile * d.Z * TILE;
             float2 v[32];
-            {   // recompute the exit wave spectrum from the stashed psi_{Z-1}
-                const float2* st = a.f.stash + (tile * d.Z + (d.Z - 1)) * TILE + g.yl * 128 + g.x;
-                const float2* Oz = a.f.O + ((size_t)m * d.Z + (d.Z - 1)) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+            {   // exit wave psi_{Z-1} O_{Z-1}
+                const float2* __restrict__ st = stash_t + (size_t)(d.Z - 1) * TILE + g.yl * 128 + g.x;
+                const float2* __restrict__ Oz = Oplane + (size_t)(d.Z - 1) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = cmul(st[k * 512], Oz[k * ostr]);
-            }
-            fft2_R_to_F(v, s.E, s.tw, g);
+                for (int k0 = 0; k0 < 32; k0 += CHK) {
+                    float2 ps[CHK], o[CHK];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) v[u] = cscale(v[u], s.fl[u * 512 + g.t]);
-            fft2_F_to_R(v, s.E, s.tw, g);                 // gphi_{Z-1}
-            for (int z = d.Z - 1; z >= 0; --z) {
-                const float2* st = a.f.stash + (tile * d.Z + z) * TILE + g.yl * 128 + g.x;
-                const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-                float2* gOz = a.gO + ((size_t)m * d.Z + z) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-                float2* ac = accb + (size_t)z * TILE;
-                const int mode = !a.need_obj ? 4 : (d.P == 1 ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
+                    for (int i = 0; i < CHK; ++i) { ps[i] = __ldg(st + (k0 + i) * 512); o[i] = __ldg(Oz + (k0 + i) * ostr); }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float2 psi = st[k * 512];
-                    float2 c = cmulc(v[k], psi);           // conj(psi) * gphi
-                    if (mode == 0) ac[k * 512] = c;
-                    else if (mode == 1) ac[k * 512] = cadd(ac[k * 512], c);
-                    else if (mode == 2) red_add_f2(gOz + k * ostr, cadd(ac[k * 512], c));
-                    else if (mode == 3) red_add_f2(gOz + k * ostr, c);
-                    v[k] = cmulc(v[k], Oz[k * ostr]);      // gpsi_z = conj(O_z) gphi_z
+                    for (int i = 0; i < CHK; ++i) v[k0 + i] = cmul(ps[i], o[i]);
                 }
-                if (z > 0) {
-                    fft2_R_to_F(v, s.E, s.tw, g);
-                    const float2* hf = a.HF + g.t;
-                    const float2* ph = a.need_prop ? a.phisF + (tile * (d.Z - 1) + (z - 1)) * TILE + g.t : nullptr;
+            }
+            const int mode = !a.need_obj ? 4 : (d.P == 1 ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
+            for (int st_i = d.Z; st_i >= 0; --st_i) {
+                if (st_i == 0 && !want_probe_fft) break;
+                // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
+                const int zn = st_i == d.Z ? d.Z - 1 : st_i - 1;
+                if (st_i > 0) {
+                    l2_prefetch_tile(stash_t + (size_t)zn * TILE);
+                    l2_prefetch_roi(Oplane + (size_t)zn * d.Noy * d.Nox, cy, cx, d.Nox);
+                }
+                fft2_R_to_F(v, s.E, s.tw, g);
+                if (st_i == d.Z) {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) v[u] = cscale(v[u], s.fl[u * 512 + g.t]);
+                } else if (st_i >= 1) {
+                    const float2* __restrict__ hf = a.HF + g.t;
+                    const float2* __restrict__ ph = a.need_prop ? a.phisF + (tile * (d.Z - 1) + (st_i - 1)) * TILE + g.t : nullptr;
                     const float Ky = a.need_prop ? kgrid(g.ky, 128, a.dx) : 0.f;
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        float2 h = hf[u * 512];
-                        if (a.f.tvec) h = cmul(h, cmul(eyv, s.ex[g.kx(u)]));
-                        v[u] = cmulc(v[u], h);             // conj(H)/N^2 * F2(gpsi)
-                        if (ph) {
-                            const float2 phi = ph[u * 512];
-                            const float sv = phi.x * v[u].y - phi.y * v[u].x;
-                            const float Kx = kgrid(g.kx(u), 128, a.dx);
-                            const float k2 = Kx * Kx + Ky * Ky;
-                            s5[0] += Ky * sv; s5[1] += Kx * sv; s5[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
+                    for (int k0 = 0; k0 < 32; k0 += CHK) {
+                        float2 h[CHK], phi[CHK];
+#pragma unroll
+                        for (int i = 0; i < CHK; ++i) { h[i] = __ldg(hf + (k0 + i) * 512); if (ph) phi[i] = __ldg(ph + (k0 + i) * 512); }
+#pragma unroll
+                        for (int i = 0; i < CHK; ++i) {
+                            const int u = k0 + i;
+                            if (tilt) h[i] = cmul(h[i], cmul(eyv, s.ex[g.kx(u)]));
+                            v[u] = cmulc(v[u], h[i]);              // conj(H)/N^2 * F2(gpsi)
+                            if (ph) {
+                                const float sv = phi[i].x * v[u].y - phi[i].y * v[u].x;
+                                const float Kx = kgrid(g.kx(u), 128, a.dx);
+                                const float k2 = Kx * Kx + Ky * Ky;
+                                s3[0] += Ky * sv; s3[1] += Kx * sv; s3[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
+                            }
                         }
                     }
-                    fft2_F_to_R(v, s.E, s.tw, g);
-                }
-            }
-            // v = gpsi_0 of this (probe mode, object mode)
-            if (a.need_probe || a.need_shift) {
-                if (a.shift) {
-                    fft2_R_to_F(v, s.E, s.tw, g);          // N^2 * T
-                    const float2* phf = a.PhatF + (size_t)p * TILE + g.t;      // Phat / N^2
-                    float2* gp = a.gPhatF + (size_t)p * TILE + g.t;
+                } else {
+                    // st_i == 0: v = N^2 T of gpsi_0 (shifted probes): probe-spectrum and shift gradients
+                    const float2* __restrict__ phf = a.PhatF + (size_t)p * TILE + g.t;      // Phat / N^2
+                    float2* __restrict__ gp = a.gPhatF + (size_t)p * TILE + g.t;
                     const float2 wyv = s.wy[g.ky];
                     const float kapy = float((g.ky + 64) & 127) * (1.0f / 128.0f);
-                    float sy = 0.f, sx = 0.f;
+                    float r2[2] = {0.f, 0.f};
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {
                         const float2 w = cmul(wyv, s.wx[g.kx(u)]);
                         const float2 cw = cmulc(v[u], w);                      // conj(w') * N^2 T
-                        if (a.need_probe) red_add_f2(gp + u * 512, cscale(cw, 1.0f / (128.0f * 128.0f)));
-                        const float2 pv = phf[u * 512];
+                        if (a.need_probe) red_f2(gp + u * 512, cscale(cw, 1.0f / (128.0f * 128.0f)));
+                        const float2 pv = __ldg(phf + u * 512);
                         const float qv = cw.y * pv.x - cw.x * pv.y;            // Im(conj(w') T conj(Phat))
-                        sy += kapy * qv;
-                        sx += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
+                        r2[0] += kapy * qv;
+                        r2[1] += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
                     }
-                    s5[3] = sy; s5[4] = sx;
                     if (a.need_shift) {
-                        float r2[2] = {sy, sx};
                         block_sum<2>(r2, s.red);
                         if (threadIdx.x == 0) {
                             atomicAdd(a.gshift + 2 * n0 + 0, -6.283185307179586f * r2[0]);
                             atomicAdd(a.gshift + 2 * n0 + 1, -6.283185307179586f * r2[1]);
                         }
                     }
-                } else if (a.need_probe) {
-                    float2* gp = a.gprobe + (size_t)p * TILE + g.yl * 128 + g.x;
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) red_add_f2(gp + k * 512, v[k]);
+                    break;
                 }
+                fft2_F_to_R(v, s.E, s.tw, g);                                   // gphi_{zn}
+                {
+                    const float2* st = stash_t + (size_t)zn * TILE + g.yl * 128 + g.x;
+                    const float2* Oz = Oplane + (size_t)zn * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+                    float2* gOz = a.gO + ((size_t)m * d.Z + zn) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+                    float2* ac = accb + (size_t)zn * TILE;
+                    switch (mode) {
+                        case 0: accum_phase<0>(v, st, Oz, ostr, ac, gOz); break;
+                        case 1: accum_phase<1>(v, st, Oz, ostr, ac, gOz); break;
+                        case 2: accum_phase<2>(v, st, Oz, ostr, ac, gOz); break;
+                        case 3: accum_phase<3>(v, st, Oz, ostr, ac, gOz); break;
+                        default: accum_phase<4>(v, st, Oz, ostr, ac, gOz); break;
+                    }
+                }
+            }
+            if (!a.shift && a.need_probe) {               // unshifted probes: g_probe += gpsi_0 (natural layout)
+                float2* gp = a.gprobe + (size_t)p * TILE + g.yl * 128 + g.x;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) red_f2(gp + k * 512, v[k]);
             }
         }
         if (a.need_prop) {
-            float r3[3] = {s5[0], s5[1], s5[2]};
-            block_sum<3>(r3, s.red);
+            block_sum<3>(s3, s.red);
             if (threadIdx.x == 0) {
-                atomicAdd(a.gprop + 3 * b + 0, r3[0]);
-                atomicAdd(a.gprop + 3 * b + 1, r3[1]);
-                atomicAdd(a.gprop + 3 * b + 2, r3[2]);
+                atomicAdd(a.gprop + 3 * b + 0, s3[0]);
+                atomicAdd(a.gprop + 3 * b + 1, s3[1]);
+                atomicAdd(a.gprop + 3 * b + 2, s3[2]);
             }
         }
     }
