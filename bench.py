@@ -121,6 +121,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch size")
     ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused: one-launch Adam of this repo; torch: torch.optim.Adam (foreach)")
+    ap.add_argument("--flags", type=int, default=0, help="experimental kernel switches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -170,7 +172,13 @@ def main():
     model = PtychoAD(iv, mp, device=dev, verbose=False)
     model.kernel_path = {"auto": _lib.PATH_AUTO, "general": _lib.PATH_GENERAL, "fused": _lib.PATH_FUSED}[args.path]
     loss_fn = CombinedLoss(lp, device=dev)
-    opt = torch.optim.Adam(model.optimizable_params)
+    model.kernel_flags = args.flags
+    if args.optimizer == "fused":
+        from ptyrad_b200.optim import FusedAdam
+        opt = FusedAdam(model.optimizable_params)
+    else:
+        opt = torch.optim.Adam(model.optimizable_params)
+    config["optimizer"] = "Adam (" + args.optimizer + ")"
     arena = GradArena(model)
     # every rank runs its own batches (weak scaling): rank r takes batches r, r+world, ... of a seeded permutation
     batches = random_batches(Ntot, B, seed=7)

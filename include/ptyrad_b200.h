@@ -137,6 +137,14 @@ int ptyb200_sparse_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, cons
                         const int64_t* idx, int32_t B, const float* occu, const double* Ssum, const float* upstream,
                         int32_t* cover_scratch, float* g_objp, ptyb200_stream s);
 
+/* optimizer.step() for torch.optim.Adam defaults (reconstruction.py:759; built at reconstruction.py:285-368):
+ * one launch over up to 8 tensors with per-tensor learning rates.  The host arrays of pointers / lrs / numels are read
+ * during the call; step_counter is one device int64 that the call increments before use (bias correction), so no
+ * host synchronisation is needed. */
+int ptyb200_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const float* lrs, const int64_t* numels, float beta1, float beta2, float eps,
+                      int64_t* step_counter, ptyb200_stream s);
+
 #ifdef __cplusplus
 }
 #endif

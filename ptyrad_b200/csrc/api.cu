@@ -209,6 +209,8 @@ template <class F> int backward_general(const ptyb200_cfg& c, int B, const Works
     return 0;
 }
 
+__global__ void k_increment(long long* c) { c[0] += 1; }
+
 LossK make_lossk(const ptyb200_loss_cfg& l) {
     LossK k;
     k.s_on = l.single_state; k.s_w = l.single_weight; k.s_p = l.single_pow;
@@ -373,7 +375,7 @@ int ptyb200_sparse_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, con
     cudaStream_t st = (cudaStream_t)s;
     Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
     CK(cudaMemsetAsync(Ssum, 0, sizeof(double) * c->M, st));
-    dim3 g((c->N * c->N + 2047) / 2048, c->M * c->Z, B);
+    dim3 g(1, c->M * c->Z, B);
     k_sparse_partial<<<g, 256, 0, st>>>(d, lc->sparse_order, objp, crop_pos, idx, Ssum);
     CKL();
     k_sparse_final<<<1, 32, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, occu, Ssum, loss_out);
@@ -392,6 +394,30 @@ int ptyb200_sparse_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const 
     CKL();
     size_t n = (size_t)c->M * c->Z * c->Noy * c->Nox;
     k_sparse_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, objp, occu, Ssum, upstream, cover, g_objp);
+    CKL();
+    return 0;
+}
+
+int ptyb200_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const float* lrs, const int64_t* numels, float beta1, float beta2, float eps,
+                      int64_t* step_counter, ptyb200_stream s) {
+    if (count < 1 || count > 8) return fail_msg("adam_step handles 1..8 tensors per call");
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !lrs || !numels || !step_counter) return fail_msg("NULL argument");
+    AdamTensors a;
+    long long nmax = 0;
+    for (int i = 0; i < count; ++i) {
+        a.p[i] = params[i]; a.g[i] = grads[i]; a.m[i] = exp_avg[i]; a.v[i] = exp_avg_sq[i];
+        a.lr[i] = lrs[i]; a.n[i] = numels[i];
+        if (numels[i] > nmax) nmax = numels[i];
+    }
+    a.count = count; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    cudaStream_t st = (cudaStream_t)s;
+    k_increment<<<1, 1, 0, st>>>((long long*)step_counter);
+    CKL();
+    unsigned bx = (unsigned)((nmax + 1023) / 1024);
+    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx < 1) bx = 1;
+    k_adam<<<dim3(bx, count), 256, 0, st>>>(a, (const long long*)step_counter);
     CKL();
     return 0;
 }

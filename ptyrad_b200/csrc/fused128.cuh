@@ -53,7 +53,7 @@ struct Args {
     float* gshift;
     float2* acc;            // (slots, Z, TILE) CTA-private gO accumulators
     float dx, k0;
-    int shift, need_obj, need_probe, need_shift, need_prop, units;
+    int shift, need_obj, need_probe, need_shift, need_prop, units, direct_red;
 };
 
 struct Geo {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                     for (int i = 0; i < CHK; ++i) v[k0 + i] = cmul(ps[i], o[i]);
                 }
             }
-            const int mode = !a.need_obj ? 4 : (d.P == 1 ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
+            const int mode = !a.need_obj ? 4 : ((d.P == 1 || a.direct_red) ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
             for (int st_i = d.Z; st_i >= 0; --st_i) {
                 if (st_i == 0 && !want_probe_fft) break;
                 // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
@@ -574,6 +574,7 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, unsigned cha
     a.dx = bw.dx; a.k0 = bw.k0;
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
     a.units = B * c.M;
+    a.direct_red = c.reserved[0] & 1;
     if (a.need_probe) {
         if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
         else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));

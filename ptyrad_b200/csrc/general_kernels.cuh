@@ -704,20 +704,22 @@ __global__ void k_loss_grad(LossK k, const float* __restrict__ dp, const float* 
     }
 }
 
-// sparse: grid (ceil(N*N/256/8), M*Z, B): Ssum[m] += sum |phi|^n over the ROI
+// sparse: grid (1, M*Z, B): Ssum[m] += sum |phi|^n over the ROI (one double atomic per block)
 __global__ void k_sparse_partial(Dims d, float order, const float* __restrict__ objp, const int32_t* __restrict__ crop,
                                  const int64_t* __restrict__ idx, double* Ssum) {
     int mz = blockIdx.y, b = blockIdx.z;
     int64_t n0 = idx[b];
     int cy = crop[2 * n0], cx = crop[2 * n0 + 1];
     const float* pl = objp + (size_t)mz * d.Noy * d.Nox;
-    double acc = 0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d.N * d.N; e += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < d.N * d.N; e += blockDim.x) {
         float v = fabsf(pl[(size_t)(cy + e / d.N) * d.Nox + cx + e % d.N]);
         acc += order == 1.0f ? v : (order == 2.0f ? v * v : powf(v, order));
     }
-    acc = warp_sum_d(acc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(Ssum + mz / d.Z, acc);
+    __shared__ float red[32];
+    float r1[1] = {acc};
+    block_sum<1>(r1, red);
+    if (threadIdx.x == 0) atomicAdd(Ssum + mz / d.Z, (double)r1[0]);
 }
 
 __global__ void k_sparse_final(Dims d, float weight, float order, const float* __restrict__ occu, const double* __restrict__ Ssum,
@@ -752,6 +754,43 @@ __global__ void k_sparse_grad(Dims d, float weight, float order, const float* __
     float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
     float pw = order == 1.0f ? 1.0f : (order == 2.0f ? av : powf(av, order - 1.0f));
     g_objp[i] += coef * pw * sg * float(c);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fused multi-tensor Adam (torch.optim.Adam semantics: no amsgrad, no weight decay, no maximize), reconstruction.py:759
+// ------------------------------------------------------------------------------------------------
+struct AdamTensors {
+    float* p[8];
+    const float* g[8];
+    float* m[8];
+    float* v[8];
+    float lr[8];
+    long long n[8];
+    int count;
+    float beta1, beta2, eps;
+};
+// step: device int64 counter (already incremented for this step)
+__global__ void k_adam(AdamTensors a, const long long* __restrict__ step) {
+    const int ti = blockIdx.y;
+    if (ti >= a.count) return;
+    const double t = (double)step[0];
+    const float bc1 = float(1.0 - pow((double)a.beta1, t));
+    const float bc2s = float(sqrt(1.0 - pow((double)a.beta2, t)));
+    const float step_size = a.lr[ti] / bc1;
+    float* __restrict__ p = a.p[ti];
+    const float* __restrict__ g = a.g[ti];
+    float* __restrict__ m = a.m[ti];
+    float* __restrict__ v = a.v[ti];
+    const long long n = a.n[ti];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * gi;
+        const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2s + a.eps;
+        p[i] -= step_size * (mi / denom);
+    }
 }
 
 }  // namespace ptyb

@@ -107,6 +107,7 @@ class PtychoAD(nn.Module):
             self.loss_iters, self.iter_times, self.dz_iters, self.avg_tilt_iters = [], [], [], []
             self._current_object_patches = None
             self.kernel_path = _lib.PATH_AUTO
+            self.kernel_flags = 0          # experimental kernel switches (cfg.reserved[0])
 
             self._validate(init_variables)
             self.create_grids()
@@ -212,8 +213,10 @@ class PtychoAD(nn.Module):
     def _cfg(self, stash_fourier):
         M, Z, Noy, Nox = self.opt_obja.shape
         P, N = self.opt_probe.shape[0], self.opt_probe.shape[1]
-        return engine.make_cfg(N, P, M, Z, Noy, Nox, self.crop_pos.shape[0], self.shift_probes, self._tilt_mode(), stash_fourier,
-                               self._dx_host, self._lambd_host, 1e-10, self.kernel_path)
+        cfg = engine.make_cfg(N, P, M, Z, Noy, Nox, self.crop_pos.shape[0], self.shift_probes, self._tilt_mode(), stash_fourier,
+                              self._dx_host, self._lambd_host, 1e-10, self.kernel_path)
+        cfg.reserved[0] = int(self.kernel_flags)
+        return cfg
 
     def _roi_tensor(self, idx):
         """Materialised, autograd-connected ROI tensor (B,M,Z,N,N,2): the gather of models.py:251-265."""

@@ -209,3 +209,25 @@ def test_adjoint_dot_product_full_size():
         dpm = model(idx)
     lhs_fd = float((((dpp.double() - dpm.double()) / (2 * h)) * G.double()).sum())
     assert abs(lhs_adj - lhs_fd) / abs(lhs_fd) < 2e-3
+
+
+def test_fused_adam_matches_torch_adam():
+    from ptyrad_b200.optim import FusedAdam
+    g = torch.Generator(device="cuda").manual_seed(3)
+    shapes = [(2, 3, 50, 60), (4, 32, 32, 2), (100, 2), ()]
+    lrs = [5e-4, 1e-4, 1e-4, 1e-3]
+    pa = [torch.randn(s, device="cuda", generator=g).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.Adam([dict(params=[p], lr=lr) for p, lr in zip(pa, lrs)])
+    ob = FusedAdam([dict(params=[p], lr=lr) for p, lr in zip(pb, lrs)])
+    for it in range(5):
+        for p, q in zip(pa, pb):
+            gr = torch.randn(p.shape, device="cuda", generator=g) * (10.0 ** (it - 2))
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        oa.step()
+        ob.step()
+    for p, q in zip(pa, pb):
+        torch.testing.assert_close(q, p, rtol=2e-6, atol=1e-7)
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert set(sa["state"][0].keys()) == set(sb["state"][0].keys())
