@@ -163,6 +163,14 @@ def main():
     from ptyrad_b200 import PtychoAD, CombinedLoss, MeasurementView, _lib
     from ptyrad_b200.step import GradArena, recon_batch
 
+    # libraries (NCCL's version banner) may write to fd 1: keep the real stdout for the one JSON line, send the rest to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -285,7 +293,7 @@ def main():
         rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, 6, 1, threads)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{b_cpu} patterns/step of the same workload, 1 warm-up + 6 timed steps, median ({med * 1e3:.0f} ms/step)"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
