@@ -43,6 +43,7 @@ struct Args {
     const float2* HF;       // (TILE) layout F, pre-scaled by 1/N^2
     const float2* PhatF;    // (P, TILE) layout F, pre-scaled by 1/N^2
     float* Ipart;           // (B, M, P, TILE) layout F partial intensities
+    float2* farF;           // (B, M, P, TILE) layout F far-field spectra F2(psi_{Z-1} O_{Z-1}) (unnormalised), kept for the adjoint
     float2* phisF;          // (B,P,M,Z-1,TILE) layout F or null
     // adjoint only
     const float* G;
@@ -130,7 +131,9 @@ __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const fl
 
 __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const float2* tw, const Geo& g) {
     Dft<32, +1>::run(v);
-    __syncthreads();                                   // earlier readers of E are done
+    // no CTA barrier here: this warp only writes its OWN two chunks, whose only foreign readers are the layout-R reads at
+    // the end of an earlier inverse FFT, and a forward FFT (two CTA barriers) always runs between two inverse FFTs
+    __syncwarp();
     {
         float2* p = E + (g.w2 + 16 * g.rsel) * CH + g.e16 * 33;
 #pragma unroll
@@ -336,8 +339,12 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     // far field: partial intensity of this (object mode, probe mode) in layout F; k_dp_reduce sums and fftshifts
     const float oc = a.f.occu[m] * (1.0f / (128.0f * 128.0f));
     float* __restrict__ ip = a.Ipart + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
+    float2* __restrict__ ff = a.farF + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
 #pragma unroll
-    for (int u = 0; u < 32; ++u) ip[u * 512] = oc * cabs2(v[u]);
+    for (int u = 0; u < 32; ++u) {
+        ip[u * 512] = oc * cabs2(v[u]);
+        ff[u * 512] = v[u];
+    }
 }
 
 // ---- adjoint --------------------------------------------------------------------------------------------------------
@@ -369,21 +376,27 @@ __device__ __forceinline__ void accum_phase(float2 (&v)[32], const float2* __res
     }
 }
 
-// persistent over units (b, m): unit = blockIdx.x + i*gridDim.x; slot = blockIdx.x owns a (Z, TILE) accumulator.
+// ACC = false (default): one CTA per (sample, object mode, probe mode); every mode scatters its conj(psi_z) gphi_z straight
+//   into the dense (L2-resident) object gradient with red.global.add.v2.f32 -- no accumulator traffic, all units independent.
+// ACC = true: persistent CTAs over units (sample, object mode) looping over the probe modes; the sum over modes is kept in a
+//   CTA-private accumulator (plain loads/stores; slot = blockIdx.x) and scattered once per pixel and slice.
 // Per probe mode the loop runs "steps" s = Z .. 0 with ONE forward/inverse FFT call site:
-//   s = Z     : F2(psi_{Z-1} O_{Z-1}) * (2 occu G~ / N^2)            -> inverse -> gphi_{Z-1}
+//   s = Z     : (stashed) F2(psi_{Z-1} O_{Z-1}) * (2 occu G~ / N^2)     -> inverse -> gphi_{Z-1}
 //   s = z >= 1: F2(gpsi_z) * conj(H_n)/N^2 [+ propagator-gradient sums] -> inverse -> gphi_{z-1}
 //   s = 0     : F2(gpsi_0) -> probe-spectrum and shift gradients (only with shifted probes)
+template <bool ACC>
 __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
     const Geo g;
     const Dims& d = a.f.d;
-    float2* accb = a.acc + (size_t)blockIdx.x * d.Z * TILE + g.yl * 128 + g.x;
+    float2* accb = ACC ? a.acc + (size_t)blockIdx.x * d.Z * TILE + g.yl * 128 + g.x : nullptr;
     const bool tilt = a.f.tvec != nullptr;
     const bool want_probe_fft = a.shift && (a.need_probe || a.need_shift);
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
-        const int b = unit / d.M, m = unit % d.M;
+        int b, m, p_lo, p_hi;
+        if (ACC) { b = unit / d.M; m = unit % d.M; p_lo = 0; p_hi = d.P; }
+        else { p_lo = unit % d.P; p_hi = p_lo + 1; const int bm = unit / d.P; b = bm / d.M; m = bm % d.M; }
         const int64_t n0 = a.f.idx[b];
         const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
         const float2* Oplane = a.f.O + (size_t)m * d.Z * d.Noy * d.Nox;
@@ -400,23 +413,11 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
         const size_t ostr = (size_t)4 * d.Nox;
         float s3[3] = {0.f, 0.f, 0.f};                  // Ky S, Kx S, (Kz-k0) S
-        for (int p = 0; p < d.P; ++p) {
+        for (int p = p_lo; p < p_hi; ++p) {
             const size_t tile = ((size_t)b * d.P + p) * d.M + m;
             const float2* stash_t = a.f.stash + tile * d.Z * TILE;
+            const int mode = !a.need_obj ? 4 : ((!ACC || d.P == 1) ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
             float2 v[32];
-            {   // exit wave psi_{Z-1} O_{Z-1}
-                const float2* __restrict__ st = stash_t + (size_t)(d.Z - 1) * TILE + g.yl * 128 + g.x;
-                const float2* __restrict__ Oz = Oplane + (size_t)(d.Z - 1) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-#pragma unroll
-                for (int k0 = 0; k0 < 32; k0 += CHK) {
-                    float2 ps[CHK], o[CHK];
-#pragma unroll
-                    for (int i = 0; i < CHK; ++i) { ps[i] = __ldg(st + (k0 + i) * 512); o[i] = __ldg(Oz + (k0 + i) * ostr); }
-#pragma unroll
-                    for (int i = 0; i < CHK; ++i) v[k0 + i] = cmul(ps[i], o[i]);
-                }
-            }
-            const int mode = !a.need_obj ? 4 : ((d.P == 1 || a.direct_red) ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
             for (int st_i = d.Z; st_i >= 0; --st_i) {
                 if (st_i == 0 && !want_probe_fft) break;
                 // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
@@ -425,10 +426,17 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                     l2_prefetch_tile(stash_t + (size_t)zn * TILE);
                     l2_prefetch_roi(Oplane + (size_t)zn * d.Noy * d.Nox, cy, cx, d.Nox);
                 }
-                fft2_R_to_F(v, s.E, s.tw, g);
+                if (st_i < d.Z) fft2_R_to_F(v, s.E, s.tw, g);
                 if (st_i == d.Z) {
+                    const float2* __restrict__ ff = a.farF + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) v[u] = cscale(v[u], s.fl[u * 512 + g.t]);
+                    for (int k0 = 0; k0 < 32; k0 += CHK) {
+                        float2 f[CHK];
+#pragma unroll
+                        for (int i = 0; i < CHK; ++i) f[i] = __ldg(ff + (k0 + i) * 512);
+#pragma unroll
+                        for (int i = 0; i < CHK; ++i) v[k0 + i] = cscale(f[i], s.fl[(k0 + i) * 512 + g.t]);
+                    }
                 } else if (st_i >= 1) {
                     const float2* __restrict__ hf = a.HF + g.t;
                     const float2* __restrict__ ph = a.need_prop ? a.phisF + (tile * (d.Z - 1) + (st_i - 1)) * TILE + g.t : nullptr;
@@ -482,13 +490,18 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                     const float2* st = stash_t + (size_t)zn * TILE + g.yl * 128 + g.x;
                     const float2* Oz = Oplane + (size_t)zn * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
                     float2* gOz = a.gO + ((size_t)m * d.Z + zn) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-                    float2* ac = accb + (size_t)zn * TILE;
-                    switch (mode) {
-                        case 0: accum_phase<0>(v, st, Oz, ostr, ac, gOz); break;
-                        case 1: accum_phase<1>(v, st, Oz, ostr, ac, gOz); break;
-                        case 2: accum_phase<2>(v, st, Oz, ostr, ac, gOz); break;
-                        case 3: accum_phase<3>(v, st, Oz, ostr, ac, gOz); break;
-                        default: accum_phase<4>(v, st, Oz, ostr, ac, gOz); break;
+                    float2* ac = ACC ? accb + (size_t)zn * TILE : nullptr;
+                    if (ACC) {
+                        switch (mode) {
+                            case 0: accum_phase<0>(v, st, Oz, ostr, ac, gOz); break;
+                            case 1: accum_phase<1>(v, st, Oz, ostr, ac, gOz); break;
+                            case 2: accum_phase<2>(v, st, Oz, ostr, ac, gOz); break;
+                            case 3: accum_phase<3>(v, st, Oz, ostr, ac, gOz); break;
+                            default: accum_phase<4>(v, st, Oz, ostr, ac, gOz); break;
+                        }
+                    } else {
+                        if (mode == 3) accum_phase<3>(v, st, Oz, ostr, ac, gOz);
+                        else accum_phase<4>(v, st, Oz, ostr, ac, gOz);
                     }
                 }
             }
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
 constexpr int MAX_SLOTS = 148;
 
 struct Scratch {
-    float2 *HF, *PhatF, *gPhatF, *acc;
+    float2 *HF, *PhatF, *gPhatF, *acc, *farF;
     float* Ipart;
     size_t total;
 };
@@ -525,6 +538,7 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.Ipart = (float*)take((size_t)B * c.M * c.P * TILE * 4);
+    s.farF = (float2*)take((size_t)B * c.M * c.P * TILE * 8);
     s.acc = (float2*)take((size_t)MAX_SLOTS * c.Z * TILE * 8);
     s.total = off;
     return s;
@@ -541,7 +555,7 @@ inline int fail(std::string& err, const char* what, cudaError_t e) {
 inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc, float2* phis) {
     Args a;
     memset(&a, 0, sizeof a);
-    a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.Ipart = sc.Ipart; a.phisF = f.phis ? phis : nullptr;
+    a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.Ipart = sc.Ipart; a.farF = sc.farF; a.phisF = f.phis ? phis : nullptr;
     a.gPhatF = sc.gPhatF; a.acc = sc.acc; a.shift = c.shift_probes;
     return a;
 }
@@ -573,8 +587,9 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, unsigned cha
     a.G = bw.G; a.gO = bw.gO; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
     a.dx = bw.dx; a.k0 = bw.k0;
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
-    a.units = B * c.M;
-    a.direct_red = c.reserved[0] & 1;
+    const bool acc_mode = (c.reserved[0] & 1) != 0;     // experimental: accumulate over probe modes before scattering
+    a.units = acc_mode ? B * c.M : B * c.M * c.P;
+    a.direct_red = acc_mode ? 0 : 1;
     if (a.need_probe) {
         if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
         else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
@@ -582,10 +597,15 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, unsigned cha
     int dev = 0, sms = MAX_SLOTS;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = a.units < sms ? a.units : sms;
-    if (grid > MAX_SLOTS) grid = MAX_SLOTS;
-    F128_CK(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    k_backward<<<grid, FT, SMEM_BYTES, st>>>(a);
+    if (acc_mode) {
+        int grid = a.units < sms ? a.units : sms;
+        if (grid > MAX_SLOTS) grid = MAX_SLOTS;
+        F128_CK(cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        k_backward<true><<<grid, FT, SMEM_BYTES, st>>>(a);
+    } else {
+        F128_CK(cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        k_backward<false><<<a.units, FT, SMEM_BYTES, st>>>(a);
+    }
     F128_CK(cudaGetLastError()); ++*launches;
     if (a.need_probe && c.shift_probes) {
         k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
