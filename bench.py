@@ -123,6 +123,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused: one-launch Adam of this repo; torch: torch.optim.Adam (foreach)")
     ap.add_argument("--flags", type=int, default=0, help="experimental kernel switches")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -199,32 +200,53 @@ def main():
         torch.cuda.synchronize()
 
     lib = _lib.lib()
+    eager_fn = lambda ix: recon_batch(model, loss_fn, opt, ix, arena, world)
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        out = None
+        for s in range(steps):
+            out = fn(my[s % len(my)])
+        e1.record()
+        sync_all()
+        t_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms, out
+
     for s in range(args.warmup):
-        recon_batch(model, loss_fn, opt, my[s % len(my)], arena, world)
+        eager_fn(my[s % len(my)])
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # pass 1 (eager launches): per-section CUDA events inside the library + launch count
     lib.ptyb200_timing_enable(1)
     l0 = lib.ptyb200_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for s in range(args.steps):
-        last = recon_batch(model, loss_fn, opt, my[s % len(my)], arena, world)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
+    ms_eager, last = timed(eager_fn, args.steps)
     launches = lib.ptyb200_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     import ctypes as C
     tf, tb, nf, nb = C.c_double(), C.c_double(), C.c_int(), C.c_int()
     lib.ptyb200_timing_read(C.byref(tf), C.byref(tb), C.byref(nf), C.byref(nb))
     lib.ptyb200_timing_enable(0)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = ms_eager
+    step_fn = eager_fn
+    if not args.no_graph:
+        # pass 2 (headline): the identical step replayed as a CUDA graph (same kernels, no per-launch host cost)
+        from ptyrad_b200.step import GraphedStep
+        last_eager = last.clone()
+        saved = [p.detach().clone() for p in model.optimizable_tensors.values()]
+        step_fn = GraphedStep(model, loss_fn, opt, arena, B, world=world)
+        for s in range(args.warmup):
+            step_fn(my[s % len(my)])
+        ms, last = timed(step_fn, args.steps)
+        config["cuda_graph"] = True
+    clocks = sampler.stop() if rank == 0 else None
     value = args.steps * B * world / (ms * 1e-3)
 
     # ------------------------------------------------------------------ end-to-end: host buffers, H2D + D2H every step
@@ -238,13 +260,20 @@ def main():
         dev_idx = torch.empty(B, dtype=torch.int64, device=dev)
         ar = torch.arange(B, device=dev)
         host_loss = torch.empty(5, dtype=torch.float32).pin_memory()
+        if args.no_graph:
+            def e2e_step(j):
+                dev_meas.copy_(host_meas[j], non_blocking=True)
+                dev_idx.copy_(host_idx[j], non_blocking=True)
+                return recon_batch(model, loss_fn, opt, dev_idx, arena, world, measurements=MeasurementView(dev_meas, ar))
+        else:
+            g2 = GraphedStep(model, loss_fn, opt, arena, B, world=world, stream_measurements=True)
+            e2e_step = lambda j: g2(host_idx[j], host_meas[j])       # H2D of indices + patterns into the graph's static inputs
+        for s in range(3):
+            e2e_step(s % len(host_meas))
         sync_all()
         t0 = time.perf_counter()
         for s in range(k2):
-            j = s % len(host_meas)
-            dev_meas.copy_(host_meas[j], non_blocking=True)
-            dev_idx.copy_(host_idx[j], non_blocking=True)
-            l5 = recon_batch(model, loss_fn, opt, dev_idx, arena, world, measurements=MeasurementView(dev_meas, ar))
+            l5 = e2e_step(s % len(host_meas))
             host_loss.copy_(l5, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         sync_all()
@@ -256,9 +285,17 @@ def main():
         e2e = {"value": k2 * B * world / dt, "unit": UNIT, "h2d_bytes_per_step": B * nn * 4 + B * 8, "d2h_bytes_per_step": 20,
                "steps": k2, "api": "PtychoAD.forward + CombinedLoss + backward + Adam.step via ptyrad_b200.step.recon_batch"}
 
-    if rank != 0:
+    def finish():
+        # captured NCCL graphs can dead-lock destroy_process_group(); everything is synchronised and printed by now, so leave
+        # through os._exit after a last barrier
+        sys.stdout.flush(); sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peak, peak_src = measured_peaks()
@@ -275,10 +312,12 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "eager": {"value": args.steps * B * world / (ms_eager * 1e-3), "ms_per_step": ms_eager / args.steps,
+                  "note": "same steps launched kernel by kernel; section timings and gpu_launches come from this pass"},
         "roofline": {"bound": "hbm", "kernel": "multislice adjoint section (ptyb200_backward)", "achieved": ach_b, "peak": peak,
                      "unit": "GB/s", "frac": ach_b / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": ms_b,
-                     "share_of_step": ms_b / (ms / args.steps) if ms > 0 else None},
+                     "share_of_step": ms_b / (ms_eager / args.steps) if ms_eager > 0 else None},
         "roofline_forward": {"bound": "hbm", "achieved": fwd_bytes / (ms_f * 1e-3) / 1e9 if ms_f > 0 else 0.0, "peak": peak, "unit": "GB/s",
                              "ms_per_launch": ms_f},
         "roofline_step": {"hbm_frac_stash_convention": value / world * stash / (peak * 1e9),
@@ -294,8 +333,7 @@ def main():
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{b_cpu} patterns/step of the same workload, 1 warm-up + 6 timed steps, median ({med * 1e3:.0f} ms/step)"}
     emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

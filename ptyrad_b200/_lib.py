@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libptyrad_b200.so")
+LIB_PATH = os.environ.get("PTYB_LIB") or os.path.join(_HERE, "lib", "libptyrad_b200.so")   # PTYB_LIB: kernel-variant experiments
 ABI_VERSION = 1
 
 NEED_OBJ, NEED_PROBE, NEED_SHIFTS, NEED_TILTS, NEED_DZ = 1, 2, 4, 8, 16

@@ -270,7 +270,10 @@ __device__ __forceinline__ void l2_prefetch_roi(const float2* plane, int cy, int
     }
 }
 
-constexpr int CHK = 4;     // pointwise phases load CHK values per stream ahead of use
+#ifndef F128_CHK
+#define F128_CHK 4
+#endif
+constexpr int CHK = F128_CHK;     // pointwise phases load CHK values per stream ahead of use
 
 // ---- forward ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {

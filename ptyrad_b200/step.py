@@ -83,3 +83,79 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         optimizer.step()
     model.clear_cache()
     return torch.stack([l.detach().reshape(()) for l in losses])
+
+
+class GraphedStep:
+    """`recon_batch` captured once into a CUDA graph and replayed per batch (sync-free, launch-free step).
+
+    At the reference's default batch size (32) the per-batch work on a B200 is a few tens of microseconds while ~40 kernel
+    launches plus autograd bookkeeping cost ~1 ms of host time; replaying a graph removes that.  One instance handles one batch
+    size (``make_batches`` yields at most two distinct sizes).  The scan indices are the only per-step input: they are copied
+    into a static device buffer.  Parameter storage must stay put between replays; constraints that rebind ``opt_*.data``
+    (constraints.py:38-224) are handled by ``_rebind`` (values are copied back into the captured storage).
+    """
+
+    def __init__(self, model, loss_fn, optimizer, arena: GradArena, batch_size: int, grad_accumulation: int = 1, warmup: int = 2,
+                 world: int = 1, stream_measurements: bool = False):
+        if model.meas_padded is not None or model.meas_scale_factors is not None:
+            raise NotImplementedError("GraphedStep reads the measurements in place; on-the-fly pad/resample is not captured")
+        self.model, self.loss_fn, self.opt, self.arena = model, loss_fn, optimizer, arena
+        self.B = int(batch_size)
+        dev = model.opt_obja.device
+        self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.params = list(model.optimizable_tensors.values())
+        # stream_measurements: this batch's patterns are copied into `self.meas` before every replay (dataset in host memory)
+        self.meas = None
+        mv = None
+        if stream_measurements:
+            N = model.opt_probe.shape[1]
+            self.meas = torch.zeros((self.B, N, N), dtype=torch.float32, device=dev)
+            mv = MeasurementView(self.meas, torch.arange(self.B, device=dev))
+        # warm-up and capture must not change the model: snapshot parameters and optimizer state, restore afterwards
+        # (a fresh optimizer is assumed: its state is zeroed again after the capture)
+        snap_p = [p.detach().clone() for p in self.params]
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for i in range(warmup):
+                recon_batch(model, loss_fn, optimizer, self.idx, arena, world, grad_accumulation, measurements=mv)
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        torch.cuda.synchronize(dev)
+        self._restore(snap_p, zero_opt=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = recon_batch(model, loss_fn, optimizer, self.idx, arena, world, grad_accumulation, measurements=mv)
+        self._restore(snap_p, zero_opt=True)
+        self._ptrs = [p.data_ptr() for p in self.params]
+        self._store = [p.data for p in self.params]
+
+    def _restore(self, snap_p, zero_opt):
+        with torch.no_grad():
+            for p, s in zip(self.params, snap_p):
+                p.data.copy_(s)
+            if zero_opt:
+                for st in self.opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+                if hasattr(self.opt, "_step_dev") and self.opt._step_dev is not None:
+                    self.opt._step_dev.zero_()
+
+    def _rebind(self):
+        for i, p in enumerate(self.params):
+            if p.data_ptr() != self._ptrs[i]:
+                with torch.no_grad():
+                    self._store[i].copy_(p.data)
+                p.data = self._store[i]
+
+    def __call__(self, indices, measurements=None):
+        self._rebind()
+        if self.meas is not None:
+            self.meas.copy_(measurements, non_blocking=True)
+        if not torch.is_tensor(indices):
+            indices = torch.as_tensor(np.asarray(indices, dtype=np.int64))
+        if indices.numel() != self.B:
+            raise ValueError(f"this graph was captured for batch size {self.B}, got {indices.numel()}")
+        self.idx.copy_(indices, non_blocking=True)
+        self.graph.replay()
+        return self.losses

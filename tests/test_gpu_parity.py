@@ -231,3 +231,31 @@ def test_fused_adam_matches_torch_adam():
         torch.testing.assert_close(q, p, rtol=2e-6, atol=1e-7)
     sa, sb = oa.state_dict(), ob.state_dict()
     assert set(sa["state"][0].keys()) == set(sb["state"][0].keys())
+
+
+def test_graphed_step_matches_eager_step():
+    """CUDA-graph replay of the step gives the same parameters as the eager step, also after a constraint-style rebind of .data."""
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch
+    from ptyrad_b200.synthetic import make_inputs
+    iv, mp, lp = make_inputs("T64", seed=8)
+    batches = [np.arange(0, 7), np.arange(7, 14), np.arange(14, 21)]
+    out = []
+    for graphed in (False, True):
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        opt = FusedAdam(model.optimizable_params)
+        arena = GradArena(model)
+        step = GraphedStep(model, loss_fn, opt, arena, 7) if graphed else (lambda ix: recon_batch(model, loss_fn, opt, ix, arena))
+        ls = []
+        for it in range(2):
+            for b in batches:
+                ls.append(step(b).clone())
+            with torch.no_grad():                                  # what CombinedConstraint does: rebind .data
+                model.opt_objp.data = model.opt_objp.data.clamp(min=0).contiguous()
+        torch.cuda.synchronize()
+        out.append((torch.stack(ls).cpu().numpy(), {k: v.detach().cpu().numpy() for k, v in model.optimizable_tensors.items()}))
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=2e-5, atol=1e-7)
+    for k in out[0][1]:
+        assert rel(out[1][1][k], out[0][1][k]) < 1e-5, k
