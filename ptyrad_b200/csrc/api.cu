@@ -149,8 +149,10 @@ template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace
                                     const float* objp, const float* probe, const float* shifts, const float* Hbase,
                                     const float* tilts, const float* dz, cudaStream_t st) {
     const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
-    k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
-    CKL();
+    if (!use_fused(c)) {                       // the fused path builds its own packed copy of the complex object
+        k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
+        CKL();
+    }
     dim3 tb(32, 8), tg((c.N + 31) / 32, (c.N + 31) / 32);
     k_transpose<<<tg, tb, 0, st>>>((const float2*)Hbase, w.HT, c.N);
     CKL();
@@ -279,7 +281,7 @@ int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const f
     DISPATCH_N(c->N, {
         if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
         tm_mark(0, 0, st);
-        if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, w.fused, st, g_err, &g_launches)) return r; }
+        if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches)) return r; }
         else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
         tm_mark(0, 1, st);
     });
@@ -311,7 +313,7 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (need_dz && !g_dz) return fail_msg("g_dz is NULL");
     if (a.need_prop && !c->stash_fourier) return fail_msg("tilt/thickness gradients need cfg.stash_fourier = 1 in the forward");
     const size_t obj = (size_t)c->M * c->Z * c->Noy * c->Nox;
-    if (a.need_obj) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
+    if (a.need_obj && !use_fused(*c)) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
     if (a.need_probe && c->shift_probes) CK(cudaMemsetAsync(w.gPhatT, 0, (size_t)c->P * c->N * c->N * 8, st));
     if (need_mask & PTYB200_NEED_SHIFTS) CK(cudaMemsetAsync(g_shifts, 0, (size_t)c->Ntot * 2 * 4, st));
     if (need_t || need_dz) CK(cudaMemsetAsync(w.gprop, 0, (size_t)B * 3 * 4, st));
@@ -320,13 +322,13 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
         tm_mark(1, 0, st);
-        if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)) return r; }
+        if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)) return r; }
         else if (int r = backward_general<F>(*c, B, w, a, g_probe, st)) return r;
         tm_mark(1, 1, st);
         if (use_fused(*c) && a.need_probe && c->shift_probes)
             if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, st)) return r;
     });
-    if (a.need_obj) {
+    if (a.need_obj && !use_fused(*c)) {
         k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj);
         CKL();
     }

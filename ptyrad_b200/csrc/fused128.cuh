@@ -37,6 +37,8 @@ constexpr int CH = 528;                 // elements per chunk region (512 used b
 constexpr int E_ELEMS = 32 * CH;        // 16896 float2 = 135168 B
 constexpr int TILE = FN * FN;           // 16384
 constexpr size_t SMEM_BYTES = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + sizeof(float) * TILE + 128 * sizeof(float);
+// the forward does not use the dL/dI tile: a smaller carve-out leaves ~88 KB of L1
+constexpr size_t SMEM_BYTES_FWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + 16 * 4096;   // + stash staging
 
 struct Args {
     FwdArgs f;
@@ -44,6 +46,8 @@ struct Args {
     const float2* PhatF;    // (P, TILE) layout F, pre-scaled by 1/N^2
     float* Ipart;           // (B, M, P, TILE) layout F partial intensities
     float2* farF;           // (B, M, P, TILE) layout F far-field spectra F2(psi_{Z-1} O_{Z-1}) (unnormalised), kept for the adjoint
+    const float4* Opack;    // (M,Z,Noy,Nox) packed complex object
+    float4* gOpack;         // (M,Z,Noy,Nox) packed dense object-gradient scratch
     float2* phisF;          // (B,P,M,Z-1,TILE) layout F or null
     // adjoint only
     const float* G;
@@ -195,8 +199,8 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
     s.E = reinterpret_cast<float2*>(raw);
     s.tw = s.E + E_ELEMS;
     s.wy = s.tw + 128; s.wx = s.wy + 128; s.ey = s.wx + 128; s.ex = s.ey + 128;
-    s.fl = reinterpret_cast<float*>(s.ex + 128);
-    s.red = s.fl + TILE;
+    s.red = reinterpret_cast<float*>(s.ex + 128);     // 128 floats of block_sum scratch
+    s.fl = s.red + 128;                               // adjoint only (the forward launches with SMEM_BYTES_FWD)
     return s;
 }
 
@@ -216,23 +220,35 @@ __device__ __forceinline__ void load_tables(const Smem& s, const Args& a, int b)
     }
 }
 
-// ---- layout-F permutation helpers (setup / finish) --------------------------------------------------------------------
-// srcT is [kx][ky] (the general path's transposed spectra); dstF[c][u*512 + t]
+// ---- packed ("pair") layouts ----------------------------------------------------------------------------------------
+// Every buffer this path owns is laid out so that a thread's two consecutive register elements (2j, 2j+1) are ONE 16-byte
+// word: float4 index j*512 + t inside a tile (t = yl*128 + x in layout R, t = threadIdx in layout F).  The global phases are
+// bound by (LG instruction-queue slots) / (L2 latency), so halving the instruction count matters more than the bytes.
+//   stash, farF, phisF, HF, PhatF, gPhatF : pairs of complex;   Ipart : quads of float
+//   Opack [m][z][Y][X] = (O[Y][X], O[Y+4][X])   -- a thread's rows yl+4k and yl+4(k+1) of the ROI in one aligned load,
+//                                                   for any crop offset (the plain object is only 8-byte aligned)
+//   gOpack[m][z][Y][X] = (contribution to gO[Y][X], contribution to gO[Y+4][X])  -- one red.global.add.v4.f32
+__device__ __forceinline__ int p2_index(int u, int t) { return (((u >> 1) * 512 + t) << 1) + (u & 1); }   // float2 index
+__device__ __forceinline__ int p4_index(int u, int t) { return (((u >> 2) * 512 + t) << 2) + (u & 3); }   // float index
+
+__device__ __forceinline__ void f_coords(int i, int& ky, int& kx, int& u, int& t) {   // i = u*512 + t
+    u = i >> 9; t = i & 511;
+    const int w2 = t >> 5, lane = t & 31;
+    ky = w2 + 16 * (lane >> 4) + 32 * ((lane >> 2) & 3);
+    kx = (lane & 3) + 4 * u;
+}
+// srcT is [kx][ky] (the general path's transposed spectra) -> pair layout F, scaled
 __global__ void k_permute_to_F(const float2* __restrict__ srcT, float2* __restrict__ dstF, float scale) {
     const int c = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // u*512 + t
-    const int u = i >> 9, t = i & 511;
-    const int w2 = t >> 5, lane = t & 31;
-    const int ky = w2 + 16 * (lane >> 4) + 32 * ((lane >> 2) & 3), kx = (lane & 3) + 4 * u;
-    dstF[(size_t)c * TILE + i] = cscale(srcT[(size_t)c * TILE + kx * 128 + ky], scale);
+    int ky, kx, u, t;
+    f_coords(blockIdx.x * blockDim.x + threadIdx.x, ky, kx, u, t);
+    dstF[(size_t)c * TILE + p2_index(u, t)] = cscale(srcT[(size_t)c * TILE + kx * 128 + ky], scale);
 }
 __global__ void k_unpermute_from_F(const float2* __restrict__ srcF, float2* __restrict__ dstT) {
     const int c = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int u = i >> 9, t = i & 511;
-    const int w2 = t >> 5, lane = t & 31;
-    const int ky = w2 + 16 * (lane >> 4) + 32 * ((lane >> 2) & 3), kx = (lane & 3) + 4 * u;
-    dstT[(size_t)c * TILE + kx * 128 + ky] = srcF[(size_t)c * TILE + i];
+    int ky, kx, u, t;
+    f_coords(blockIdx.x * blockDim.x + threadIdx.x, ky, kx, u, t);
+    dstT[(size_t)c * TILE + kx * 128 + ky] = srcF[(size_t)c * TILE + p2_index(u, t)];
 }
 
 // dp[b][Y][X] = eps + sum_{m,p} Ipart[b,m,p][F index of (ky,kx)],  (Y,X) = fftshift(ky,kx).  grid (TILE/256, B)
@@ -242,145 +258,268 @@ __global__ void k_dp_reduce(const float* __restrict__ Ipart, float* __restrict__
     const int Y = pix >> 7, X = pix & 127;
     const int ky = (Y + 64) & 127, kx = (X + 64) & 127;
     const int r = ky & 31, w2 = r & 15, rsel = r >> 4, q = ky >> 5, vv = kx & 3, u = kx >> 2;
-    const int i = u * 512 + w2 * 32 + rsel * 16 + q * 4 + vv;
+    const int i = p4_index(u, w2 * 32 + rsel * 16 + q * 4 + vv);
     float acc = 0.f;
     for (int c = 0; c < MP; ++c) acc += Ipart[((size_t)b * MP + c) * TILE + i];
     dp[(size_t)b * TILE + pix] = acc + eps;
 }
 
+// Opack from (a, phi): O = a e^{i phi} (torch.polar, forward.py:53) written to [Y][X].xy and to [Y-4][X].zw
+__global__ void k_obj_polar_pack(const float* __restrict__ a, const float* __restrict__ ph, float4* __restrict__ Op, int Noy, int Nox,
+                                 size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, c;
+    sincosf(ph[i], &s, &c);
+    const float av = a[i];
+    const float2 o = make_float2(av * c, av * s);
+    const int Y = int((i / Nox) % Noy);
+    float2* lo = reinterpret_cast<float2*>(Op + i);
+    lo[0] = o;
+    if (Y + 4 >= Noy) lo[1] = make_float2(0.f, 0.f);
+    if (Y >= 4) reinterpret_cast<float2*>(Op + i - (size_t)4 * Nox)[1] = o;
+}
+// g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O)) with gO[Y][X] = gOpack[Y][X].xy + gOpack[Y-4][X].zw
+__global__ void k_obj_finish_pack(const float4* __restrict__ gOp, const float* __restrict__ a, const float* __restrict__ ph,
+                                  float* __restrict__ ga, float* __restrict__ gp, int Noy, int Nox, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Y = int((i / Nox) % Noy);
+    const float4 lo = gOp[i];
+    float2 g = make_float2(lo.x, lo.y);
+    if (Y >= 4) { const float4 up = gOp[i - (size_t)4 * Nox]; g.x += up.z; g.y += up.w; }
+    float s, c;
+    sincosf(ph[i], &s, &c);
+    ga[i] = g.x * c + g.y * s;
+    gp[i] = a[i] * (g.y * c - g.x * s);
+}
+
 // ---- memory helpers -----------------------------------------------------------------------------------------------
-// fire-and-forget vector reduction; no "memory" clobber: nothing in these kernels reads the target back, and a clobber
+// fire-and-forget vector reductions; no "memory" clobber: nothing in these kernels reads the target back, and a clobber
 // would stop the compiler from hoisting the next loads above it
 __device__ __forceinline__ void red_f2(float2* addr, float2 v) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y));
+}
+__device__ __forceinline__ void red_f4(float4* addr, float2 a, float2 b) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
 }
 // L2 prefetch of a contiguous range (TMA bulk prefetch: one instruction, no registers, no smem)
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
 }
 // whole 128 KB tile: 32 lanes of warp 0 x 4 KB
-__device__ __forceinline__ void l2_prefetch_tile(const float2* tile) {
-    if (threadIdx.x < 32) l2_prefetch(tile + threadIdx.x * 512, 4096);
+__device__ __forceinline__ void l2_prefetch_tile(const float4* tile) {
+    if (threadIdx.x < 32) l2_prefetch(tile + threadIdx.x * 256, 4096);
 }
-// the 128 ROI rows of one slice (1 KB each, 8-byte aligned -> round to 16)
-__device__ __forceinline__ void l2_prefetch_roi(const float2* plane, int cy, int cx, int Nox) {
-    if (threadIdx.x >= 32 && threadIdx.x < 160) {
-        const float2* row = plane + (size_t)(cy + threadIdx.x - 32) * Nox + cx;
-        l2_prefetch(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(row) & ~uintptr_t(15)), 1040);
+// the 64 packed ROI rows of one slice that this CTA reads (rows cy + yl + 8 j, yl < 4, j < 16; 2 KB each, 16-byte aligned)
+__device__ __forceinline__ void l2_prefetch_roi(const float4* plane, int cy, int cx, int Nox) {
+    if (threadIdx.x >= 32 && threadIdx.x < 96) {
+        const int i = threadIdx.x - 32;
+        l2_prefetch(plane + (size_t)(cy + (i & 3) + 8 * (i >> 2)) * Nox + cx, 2048);
     }
 }
+// L1 prefetch of the lines this warp will read in a pointwise phase: a warp reads 512 contiguous bytes per pair j
+// (4 lines of 128 B); lanes 0..3 cover pair j = jbase + (lane >> 2)... one instruction per thread covers 8 pairs:
+// lane l prefetches line (l & 3) of pair j0 + (l >> 2).  `base` is the warp's lane-0 address of pair 0, `stride` in float4.
+__device__ __forceinline__ void l1_prefetch_pairs(const float4* lane0_base, size_t stride, int j0, int lane) {
+    const float4* p = lane0_base + (size_t)(j0 + (lane >> 2)) * stride + (lane & 3) * 8;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+// TMA bulk copy shared -> global (asynchronous, issued by one lane; no LSU store traffic, no register reads at drain time)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// stash tile layout: [warp][j][lane] of 16-byte pairs -> each warp's data of 8 consecutive j is one contiguous 4 KB block
+__device__ __forceinline__ int stash_index(int t, int j) { return (((t >> 5) * 16 + j) << 5) + (t & 31); }
+
+__device__ __forceinline__ float2 lo2(float4 q) { return make_float2(q.x, q.y); }
+__device__ __forceinline__ float2 hi2(float4 q) { return make_float2(q.z, q.w); }
+__device__ __forceinline__ float4 pack2(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
 
 #ifndef F128_CHK
 #define F128_CHK 4
 #endif
-constexpr int CHK = F128_CHK;     // pointwise phases load CHK values per stream ahead of use
+#ifndef F128_L1PF
+#define F128_L1PF 0
+#endif
+#ifndef F128_STAGGER
+#define F128_STAGGER 0
+#endif
+#ifndef F128_EXP
+#define F128_EXP 0      // timing experiments only (results are wrong): 1 = no ROI loads, 2 = no stash stores, 4 = no propagator loads
+#endif
+constexpr int CH2 = F128_CHK;     // pointwise phases load CH2 16-byte words per stream ahead of use
 
 // ---- forward ------------------------------------------------------------------------------------------------------
+struct Ptrs {                       // per-CTA base pointers into the packed object copy
+    const float4* Oplane;           // Opack + m*Z*Noy*Nox
+    size_t plane;                   // Noy*Nox
+    size_t ostr;                    // 8*Nox (float4 units between consecutive pairs j)
+    size_t roi0;                    // (cy + yl)*Nox + cx + x
+};
+
 __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
     const Geo g;
     const Dims& d = a.f.d;
     const int p = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
+#if F128_STAGGER
+    {   // de-phase the SMs: identical CTAs started together would hit HBM with their stash bursts at the same instants
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (lin < 148u) __nanosleep((lin % F128_STAGGER) * (15000u / F128_STAGGER));
+    }
+#endif
     const int64_t n0 = a.f.idx[b];
     const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
-    const float2* Oplane = a.f.O + (size_t)m * d.Z * d.Noy * d.Nox;
+    const size_t plane = (size_t)d.Noy * d.Nox;
+    const float4* Oplane = a.Opack + (size_t)m * d.Z * plane;
     l2_prefetch_roi(Oplane, cy, cx, d.Nox);
     load_tables(s, a, b);
     __syncthreads();
     const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-    const size_t ostr = (size_t)4 * d.Nox;
+    const size_t ostr = (size_t)8 * d.Nox;
+    const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+    const int tR = g.yl * 128 + g.x;
     const bool tilt = a.f.tvec != nullptr;
     const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
     float2 v[32];
     if (a.shift) {
-        const float2* __restrict__ ph = a.PhatF + (size_t)p * TILE + g.t;
+        const float4* __restrict__ ph = reinterpret_cast<const float4*>(a.PhatF) + (size_t)p * (TILE / 2) + g.t;
         const float2 wyv = s.wy[g.ky];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = cmul(__ldg(ph + u * 512), cmul(wyv, s.wx[g.kx(u)]));
+        for (int j = 0; j < 16; ++j) {
+            const float4 q = __ldg(ph + j * 512);
+            v[2 * j] = cmul(lo2(q), cmul(wyv, s.wx[g.kx(2 * j)]));
+            v[2 * j + 1] = cmul(hi2(q), cmul(wyv, s.wx[g.kx(2 * j + 1)]));
+        }
     } else {
-        const float2* __restrict__ pr = a.f.probe + (size_t)p * TILE + g.yl * 128 + g.x;
+        const float2* __restrict__ pr = a.f.probe + (size_t)p * TILE + tR;
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __ldg(pr + k * 512);
     }
     for (int z = a.shift ? -1 : 0; z < d.Z; ++z) {
         if (z >= 0) {
-            float2* __restrict__ st = a.f.stash + (tile * d.Z + z) * TILE + g.yl * 128 + g.x;
-            const float2* __restrict__ Oz = Oplane + (size_t)z * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-            if (z + 1 < d.Z) l2_prefetch_roi(Oplane + (size_t)(z + 1) * d.Noy * d.Nox, cy, cx, d.Nox);
+            float4* st = reinterpret_cast<float4*>(a.f.stash) + (tile * d.Z + z) * (TILE / 2);
+            const float4* __restrict__ Oz = Oplane + (size_t)z * plane + roi0;
+            if (z + 1 < d.Z) l2_prefetch_roi(Oplane + (size_t)(z + 1) * plane, cy, cx, d.Nox);
+            // psi_z -> stash through a per-warp 4 KB staging block and one TMA bulk store per half (8 pairs): the stores
+            // leave the LSU path, so the FFT's shared-memory traffic is not queued behind a 128 KB store burst
+            float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += CHK) {
-                float2 o[CHK];
+            for (int h = 0; h < 2; ++h) {
+                if (g.lane == 0) bulk_wait_read0();
+                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < CHK; ++i) o[i] = __ldg(Oz + (k0 + i) * ostr);
+                for (int j0 = 0; j0 < 8; j0 += CH2) {
+                    float4 o[CH2];
 #pragma unroll
-                for (int i = 0; i < CHK; ++i) {
-                    st[(k0 + i) * 512] = v[k0 + i];
-                    v[k0 + i] = cmul(v[k0 + i], o[i]);
+                    for (int i = 0; i < CH2; ++i) o[i] = __ldg(Oz + (h * 8 + j0 + i) * ostr);
+#pragma unroll
+                    for (int i = 0; i < CH2; ++i) {
+                        const int j = h * 8 + j0 + i, k = 2 * j;
+                        sw[(j0 + i) * 32] = pack2(v[k], v[k + 1]);
+                        v[k] = cmul(v[k], lo2(o[i]));
+                        v[k + 1] = cmul(v[k + 1], hi2(o[i]));
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (g.lane == 0) {
+                    bulk_store(st + stash_index(g.t & ~31, h * 8), sw, 4096);
+                    bulk_commit();
                 }
             }
+#if F128_L1PF
+            {   // stage the propagator table (first 2/3) in L1 while the FFT runs
+                const float4* hf0 = reinterpret_cast<const float4*>(a.HF) + (g.t & ~31);
+                l1_prefetch_pairs(hf0, 512, 0, g.lane);
+                if (F128_L1PF > 1) l1_prefetch_pairs(hf0, 512, 8, g.lane);
+            }
+#endif
             fft2_R_to_F(v, s.E, s.tw, g);
             if (z == d.Z - 1) break;
-            const float2* __restrict__ hf = a.HF + g.t;
-            float2* __restrict__ ph = a.phisF ? a.phisF + (tile * (d.Z - 1) + z) * TILE + g.t : nullptr;
+            const float4* __restrict__ hf = reinterpret_cast<const float4*>(a.HF) + g.t;
+            float4* __restrict__ ph = a.phisF ? reinterpret_cast<float4*>(a.phisF) + (tile * (d.Z - 1) + z) * (TILE / 2) + g.t : nullptr;
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += CHK) {
-                float2 h[CHK];
+            for (int j0 = 0; j0 < 16; j0 += CH2) {
+                float4 h[CH2];
 #pragma unroll
-                for (int i = 0; i < CHK; ++i) h[i] = __ldg(hf + (k0 + i) * 512);
+                for (int i = 0; i < CH2; ++i) h[i] = __ldg(hf + (j0 + i) * 512);
 #pragma unroll
-                for (int i = 0; i < CHK; ++i) {
-                    const int u = k0 + i;
-                    if (ph) ph[u * 512] = v[u];
-                    if (tilt) h[i] = cmul(h[i], cmul(eyv, s.ex[g.kx(u)]));
-                    v[u] = cmul(v[u], h[i]);
+                for (int i = 0; i < CH2; ++i) {
+                    const int u = 2 * (j0 + i);
+                    if (ph) ph[(j0 + i) * 512] = pack2(v[u], v[u + 1]);
+                    float2 h0 = lo2(h[i]), h1 = hi2(h[i]);
+                    if (tilt) { h0 = cmul(h0, cmul(eyv, s.ex[g.kx(u)])); h1 = cmul(h1, cmul(eyv, s.ex[g.kx(u + 1)])); }
+                    v[u] = cmul(v[u], h0);
+                    v[u + 1] = cmul(v[u + 1], h1);
                 }
             }
+#if F128_L1PF
+            if (z + 1 < d.Z) {   // stage the next slice's ROI (first 2/3) in L1 while the inverse FFT runs
+                const float4* o0 = Oplane + (size_t)(z + 1) * plane + (size_t)(cy + g.yl) * d.Nox + cx + (g.x & ~31);
+                l1_prefetch_pairs(o0, ostr, 0, g.lane);
+                if (F128_L1PF > 1) l1_prefetch_pairs(o0, ostr, 8, g.lane);
+            }
+#endif
         }
         fft2_F_to_R(v, s.E, s.tw, g);
     }
-    // far field: partial intensity of this (object mode, probe mode) in layout F; k_dp_reduce sums and fftshifts
+    // far field: partial intensity of this (object mode, probe mode) in layout F (k_dp_reduce sums modes and fftshifts) and
+    // the spectrum itself for the adjoint
     const float oc = a.f.occu[m] * (1.0f / (128.0f * 128.0f));
-    float* __restrict__ ip = a.Ipart + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
-    float2* __restrict__ ff = a.farF + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
+    const size_t ft = ((size_t)b * d.M + m) * d.P + p;
+    float4* __restrict__ ip = reinterpret_cast<float4*>(a.Ipart) + ft * (TILE / 4) + g.t;
+    float4* __restrict__ ff = reinterpret_cast<float4*>(a.farF) + ft * (TILE / 2) + g.t;
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-        ip[u * 512] = oc * cabs2(v[u]);
-        ff[u * 512] = v[u];
-    }
+    for (int j = 0; j < 16; ++j) ff[j * 512] = pack2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        ip[j * 512] = make_float4(oc * cabs2(v[4 * j]), oc * cabs2(v[4 * j + 1]), oc * cabs2(v[4 * j + 2]), oc * cabs2(v[4 * j + 3]));
+    if (g.lane == 0) bulk_wait_all();       // the staging blocks must outlive the TMA reads; writes complete before exit
 }
 
 // ---- adjoint --------------------------------------------------------------------------------------------------------
 // gO accumulation over the probe modes.  MODE 0: first mode -> store; 1: middle -> read-modify-write;
-// 2: last mode -> scatter (accumulator + own) into the dense gradient; 3: single mode -> scatter own; 4: not wanted
+// 2: last mode -> scatter (accumulator + own) into the dense gradient; 3: scatter own (default); 4: not wanted
 template <int MODE>
-__device__ __forceinline__ void accum_phase(float2 (&v)[32], const float2* __restrict__ st, const float2* __restrict__ Oz, size_t ostr,
-                                            float2* __restrict__ ac, float2* __restrict__ gOz) {
+__device__ __forceinline__ void accum_phase(float2 (&v)[32], const float4* __restrict__ st, const float4* __restrict__ Oz, size_t ostr,
+                                            float4* __restrict__ ac, float4* __restrict__ gOz) {
 #pragma unroll
-    for (int k0 = 0; k0 < 32; k0 += CHK) {
-        float2 ps[CHK], o[CHK], av[CHK];
+    for (int j0 = 0; j0 < 16; j0 += CH2) {
+        float4 ps[CH2], o[CH2], av[CH2];
 #pragma unroll
-        for (int i = 0; i < CHK; ++i) {
-            o[i] = __ldg(Oz + (k0 + i) * ostr);
-            if (MODE != 4) ps[i] = __ldg(st + (k0 + i) * 512);
-            if (MODE == 1 || MODE == 2) av[i] = ac[(k0 + i) * 512];
+        for (int i = 0; i < CH2; ++i) {
+            o[i] = __ldg(Oz + (j0 + i) * ostr);
+            if (MODE != 4) ps[i] = __ldg(st + (j0 + i) * 32);
+            if (MODE == 1 || MODE == 2) av[i] = ac[(j0 + i) * 512];
         }
 #pragma unroll
-        for (int i = 0; i < CHK; ++i) {
-            const int k = k0 + i;
+        for (int i = 0; i < CH2; ++i) {
+            const int k = 2 * (j0 + i);
             if (MODE != 4) {
-                float2 c = cmulc(v[k], ps[i]);                 // conj(psi) * gphi
-                if (MODE == 1 || MODE == 2) c = cadd(c, av[i]);
-                if (MODE == 0 || MODE == 1) ac[k * 512] = c;
-                else red_f2(gOz + k * ostr, c);
+                float2 c0 = cmulc(v[k], lo2(ps[i])), c1 = cmulc(v[k + 1], hi2(ps[i]));     // conj(psi) * gphi
+                if (MODE == 1 || MODE == 2) { c0 = cadd(c0, lo2(av[i])); c1 = cadd(c1, hi2(av[i])); }
+                if (MODE == 0 || MODE == 1) ac[(j0 + i) * 512] = pack2(c0, c1);
+                else red_f4(gOz + (j0 + i) * ostr, c0, c1);
             }
-            v[k] = cmulc(v[k], o[i]);                          // gpsi_z = conj(O_z) gphi_z
+            v[k] = cmulc(v[k], lo2(o[i]));                     // gpsi_z = conj(O_z) gphi_z
+            v[k + 1] = cmulc(v[k + 1], hi2(o[i]));
         }
     }
 }
 
 // ACC = false (default): one CTA per (sample, object mode, probe mode); every mode scatters its conj(psi_z) gphi_z straight
-//   into the dense (L2-resident) object gradient with red.global.add.v2.f32 -- no accumulator traffic, all units independent.
+//   into the dense (L2-resident) object gradient with red.global.add.v4.f32 -- no accumulator traffic, all units independent.
 // ACC = true: persistent CTAs over units (sample, object mode) looping over the probe modes; the sum over modes is kept in a
 //   CTA-private accumulator (plain loads/stores; slot = blockIdx.x) and scattered once per pixel and slice.
 // Per probe mode the loop runs "steps" s = Z .. 0 with ONE forward/inverse FFT call site:
@@ -393,16 +532,18 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
     const Smem s = carve_smem(smem_raw);
     const Geo g;
     const Dims& d = a.f.d;
-    float2* accb = ACC ? a.acc + (size_t)blockIdx.x * d.Z * TILE + g.yl * 128 + g.x : nullptr;
+    const int tR = g.yl * 128 + g.x;
+    float4* accb = ACC ? reinterpret_cast<float4*>(a.acc) + (size_t)blockIdx.x * d.Z * (TILE / 2) + tR : nullptr;
     const bool tilt = a.f.tvec != nullptr;
     const bool want_probe_fft = a.shift && (a.need_probe || a.need_shift);
+    const size_t plane = (size_t)d.Noy * d.Nox;
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
         int b, m, p_lo, p_hi;
         if (ACC) { b = unit / d.M; m = unit % d.M; p_lo = 0; p_hi = d.P; }
         else { p_lo = unit % d.P; p_hi = p_lo + 1; const int bm = unit / d.P; b = bm / d.M; m = bm % d.M; }
         const int64_t n0 = a.f.idx[b];
         const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
-        const float2* Oplane = a.f.O + (size_t)m * d.Z * d.Noy * d.Nox;
+        const float4* Oplane = a.Opack + (size_t)m * d.Z * plane;
         __syncthreads();
         load_tables(s, a, b);
         {   // dL/dI in layout F, scaled: 2 occu_m G~ / N^2
@@ -414,11 +555,12 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         }
         __syncthreads();
         const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
-        const size_t ostr = (size_t)4 * d.Nox;
+        const size_t ostr = (size_t)8 * d.Nox;
+        const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
         float s3[3] = {0.f, 0.f, 0.f};                  // Ky S, Kx S, (Kz-k0) S
         for (int p = p_lo; p < p_hi; ++p) {
             const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-            const float2* stash_t = a.f.stash + tile * d.Z * TILE;
+            const float4* stash_t = reinterpret_cast<const float4*>(a.f.stash) + tile * d.Z * (TILE / 2);
             const int mode = !a.need_obj ? 4 : ((!ACC || d.P == 1) ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
             float2 v[32];
             for (int st_i = d.Z; st_i >= 0; --st_i) {
@@ -426,58 +568,74 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                 // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
                 const int zn = st_i == d.Z ? d.Z - 1 : st_i - 1;
                 if (st_i > 0) {
-                    l2_prefetch_tile(stash_t + (size_t)zn * TILE);
-                    l2_prefetch_roi(Oplane + (size_t)zn * d.Noy * d.Nox, cy, cx, d.Nox);
+                    l2_prefetch_tile(stash_t + (size_t)zn * (TILE / 2));
+                    l2_prefetch_roi(Oplane + (size_t)zn * plane, cy, cx, d.Nox);
                 }
                 if (st_i < d.Z) fft2_R_to_F(v, s.E, s.tw, g);
                 if (st_i == d.Z) {
-                    const float2* __restrict__ ff = a.farF + (((size_t)b * d.M + m) * d.P + p) * TILE + g.t;
+                    const float4* __restrict__ ff = reinterpret_cast<const float4*>(a.farF) + (((size_t)b * d.M + m) * d.P + p) * (TILE / 2) + g.t;
 #pragma unroll
-                    for (int k0 = 0; k0 < 32; k0 += CHK) {
-                        float2 f[CHK];
+                    for (int j0 = 0; j0 < 16; j0 += CH2) {
+                        float4 f[CH2];
 #pragma unroll
-                        for (int i = 0; i < CHK; ++i) f[i] = __ldg(ff + (k0 + i) * 512);
+                        for (int i = 0; i < CH2; ++i) f[i] = __ldg(ff + (j0 + i) * 512);
 #pragma unroll
-                        for (int i = 0; i < CHK; ++i) v[k0 + i] = cscale(f[i], s.fl[(k0 + i) * 512 + g.t]);
+                        for (int i = 0; i < CH2; ++i) {
+                            const int u = 2 * (j0 + i);
+                            v[u] = cscale(lo2(f[i]), s.fl[u * 512 + g.t]);
+                            v[u + 1] = cscale(hi2(f[i]), s.fl[(u + 1) * 512 + g.t]);
+                        }
                     }
                 } else if (st_i >= 1) {
-                    const float2* __restrict__ hf = a.HF + g.t;
-                    const float2* __restrict__ ph = a.need_prop ? a.phisF + (tile * (d.Z - 1) + (st_i - 1)) * TILE + g.t : nullptr;
+                    const float4* __restrict__ hf = reinterpret_cast<const float4*>(a.HF) + g.t;
+                    const float4* __restrict__ ph = a.need_prop ? reinterpret_cast<const float4*>(a.phisF) + (tile * (d.Z - 1) + (st_i - 1)) * (TILE / 2) + g.t : nullptr;
                     const float Ky = a.need_prop ? kgrid(g.ky, 128, a.dx) : 0.f;
 #pragma unroll
-                    for (int k0 = 0; k0 < 32; k0 += CHK) {
-                        float2 h[CHK], phi[CHK];
+                    for (int j0 = 0; j0 < 16; j0 += CH2) {
+                        float4 h[CH2], phi[CH2];
 #pragma unroll
-                        for (int i = 0; i < CHK; ++i) { h[i] = __ldg(hf + (k0 + i) * 512); if (ph) phi[i] = __ldg(ph + (k0 + i) * 512); }
+                        for (int i = 0; i < CH2; ++i) { h[i] = __ldg(hf + (j0 + i) * 512); if (ph) phi[i] = __ldg(ph + (j0 + i) * 512); }
 #pragma unroll
-                        for (int i = 0; i < CHK; ++i) {
-                            const int u = k0 + i;
-                            if (tilt) h[i] = cmul(h[i], cmul(eyv, s.ex[g.kx(u)]));
-                            v[u] = cmulc(v[u], h[i]);              // conj(H)/N^2 * F2(gpsi)
-                            if (ph) {
-                                const float sv = phi[i].x * v[u].y - phi[i].y * v[u].x;
-                                const float Kx = kgrid(g.kx(u), 128, a.dx);
-                                const float k2 = Kx * Kx + Ky * Ky;
-                                s3[0] += Ky * sv; s3[1] += Kx * sv; s3[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
+                        for (int i = 0; i < CH2; ++i) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int u = 2 * (j0 + i) + e;
+                                float2 hh = e ? hi2(h[i]) : lo2(h[i]);
+                                if (tilt) hh = cmul(hh, cmul(eyv, s.ex[g.kx(u)]));
+                                v[u] = cmulc(v[u], hh);              // conj(H)/N^2 * F2(gpsi)
+                                if (ph) {
+                                    const float2 pz = e ? hi2(phi[i]) : lo2(phi[i]);
+                                    const float sv = pz.x * v[u].y - pz.y * v[u].x;
+                                    const float Kx = kgrid(g.kx(u), 128, a.dx);
+                                    const float k2 = Kx * Kx + Ky * Ky;
+                                    s3[0] += Ky * sv; s3[1] += Kx * sv; s3[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
+                                }
                             }
                         }
                     }
                 } else {
                     // st_i == 0: v = N^2 T of gpsi_0 (shifted probes): probe-spectrum and shift gradients
-                    const float2* __restrict__ phf = a.PhatF + (size_t)p * TILE + g.t;      // Phat / N^2
-                    float2* __restrict__ gp = a.gPhatF + (size_t)p * TILE + g.t;
+                    const float4* __restrict__ phf = reinterpret_cast<const float4*>(a.PhatF) + (size_t)p * (TILE / 2) + g.t;   // Phat / N^2
+                    float4* __restrict__ gp = reinterpret_cast<float4*>(a.gPhatF) + (size_t)p * (TILE / 2) + g.t;
                     const float2 wyv = s.wy[g.ky];
                     const float kapy = float((g.ky + 64) & 127) * (1.0f / 128.0f);
+                    const float invN2 = 1.0f / (128.0f * 128.0f);
                     float r2[2] = {0.f, 0.f};
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        const float2 w = cmul(wyv, s.wx[g.kx(u)]);
-                        const float2 cw = cmulc(v[u], w);                      // conj(w') * N^2 T
-                        if (a.need_probe) red_f2(gp + u * 512, cscale(cw, 1.0f / (128.0f * 128.0f)));
-                        const float2 pv = __ldg(phf + u * 512);
-                        const float qv = cw.y * pv.x - cw.x * pv.y;            // Im(conj(w') T conj(Phat))
-                        r2[0] += kapy * qv;
-                        r2[1] += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 pq = __ldg(phf + j * 512);
+                        float2 cw[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int u = 2 * j + e;
+                            const float2 w = cmul(wyv, s.wx[g.kx(u)]);
+                            cw[e] = cmulc(v[u], w);                              // conj(w') * N^2 T
+                            const float2 pv = e ? hi2(pq) : lo2(pq);
+                            const float qv = cw[e].y * pv.x - cw[e].x * pv.y;    // Im(conj(w') T conj(Phat))
+                            r2[0] += kapy * qv;
+                            r2[1] += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
+                        }
+                        if (a.need_probe) red_f4(gp + j * 512, cscale(cw[0], invN2), cscale(cw[1], invN2));
                     }
                     if (a.need_shift) {
                         block_sum<2>(r2, s.red);
@@ -490,10 +648,10 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                 }
                 fft2_F_to_R(v, s.E, s.tw, g);                                   // gphi_{zn}
                 {
-                    const float2* st = stash_t + (size_t)zn * TILE + g.yl * 128 + g.x;
-                    const float2* Oz = Oplane + (size_t)zn * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-                    float2* gOz = a.gO + ((size_t)m * d.Z + zn) * d.Noy * d.Nox + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-                    float2* ac = ACC ? accb + (size_t)zn * TILE : nullptr;
+                    const float4* st = stash_t + (size_t)zn * (TILE / 2) + stash_index(g.t, 0);
+                    const float4* Oz = Oplane + (size_t)zn * plane + roi0;
+                    float4* gOz = a.gOpack + ((size_t)m * d.Z + zn) * plane + roi0;
+                    float4* ac = ACC ? accb + (size_t)zn * (TILE / 2) : nullptr;
                     if (ACC) {
                         switch (mode) {
                             case 0: accum_phase<0>(v, st, Oz, ostr, ac, gOz); break;
@@ -509,7 +667,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                 }
             }
             if (!a.shift && a.need_probe) {               // unshifted probes: g_probe += gpsi_0 (natural layout)
-                float2* gp = a.gprobe + (size_t)p * TILE + g.yl * 128 + g.x;
+                float2* gp = a.gprobe + (size_t)p * TILE + tR;
 #pragma unroll
                 for (int k = 0; k < 32; ++k) red_f2(gp + k * 512, v[k]);
             }
@@ -530,6 +688,7 @@ constexpr int MAX_SLOTS = 148;
 
 struct Scratch {
     float2 *HF, *PhatF, *gPhatF, *acc, *farF;
+    float4 *Opack, *gOpack;
     float* Ipart;
     size_t total;
 };
@@ -537,12 +696,16 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     Scratch s;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base + o; };
+    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    const bool acc_mode = (c.reserved[0] & 1) != 0;
     s.HF = (float2*)take((size_t)TILE * 8);
     s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
+    s.Opack = (float4*)take(obj * 16);
+    s.gOpack = (float4*)take(obj * 16);
     s.Ipart = (float*)take((size_t)B * c.M * c.P * TILE * 4);
     s.farF = (float2*)take((size_t)B * c.M * c.P * TILE * 8);
-    s.acc = (float2*)take((size_t)MAX_SLOTS * c.Z * TILE * 8);
+    s.acc = (float2*)take(acc_mode ? (size_t)MAX_SLOTS * c.Z * TILE * 8 : 0);
     s.total = off;
     return s;
 }
@@ -559,40 +722,48 @@ inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc,
     Args a;
     memset(&a, 0, sizeof a);
     a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.Ipart = sc.Ipart; a.farF = sc.farF; a.phisF = f.phis ? phis : nullptr;
+    a.Opack = sc.Opack; a.gOpack = sc.gOpack;
     a.gPhatF = sc.gPhatF; a.acc = sc.acc; a.shift = c.shift_probes;
     return a;
 }
 
 // f.HT = transposed propagator [kx][ky]; f.PhatT = probe spectrum [kx][ky] (both made by setup_common)
-inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, unsigned char* scratch, cudaStream_t st, std::string& err, long long* launches) {
+inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, const float* objp, unsigned char* scratch, cudaStream_t st,
+                   std::string& err, long long* launches) {
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, f, sc, f.phis);
     const float inv = 1.0f / (128.0f * 128.0f);
+    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    k_obj_polar_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, sc.Opack, c.Noy, c.Nox, obj);
+    F128_CK(cudaGetLastError()); ++*launches;
     k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
     F128_CK(cudaGetLastError()); ++*launches;
     if (c.shift_probes) {
         k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(f.PhatT, sc.PhatF, inv);
         F128_CK(cudaGetLastError()); ++*launches;
     }
-    F128_CK(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    k_forward<<<dim3(c.P, c.M, B), FT, SMEM_BYTES, st>>>(a);
+    F128_CK(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_FWD));
+    k_forward<<<dim3(c.P, c.M, B), FT, SMEM_BYTES_FWD, st>>>(a);
     F128_CK(cudaGetLastError()); ++*launches;
     k_dp_reduce<<<dim3(TILE / 256, B), 256, 0, st>>>(sc.Ipart, f.dp, c.M * c.P, c.eps);
     F128_CK(cudaGetLastError()); ++*launches;
     return 0;
 }
 
-// adjoint; the caller zeroes gO / gPhatT / gprop / gshift and runs the probe-spectrum inverse FFT + object finish
-inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, unsigned char* scratch, float2* g_probe, float2* gPhatT,
-                    cudaStream_t st, std::string& err, long long* launches) {
+// adjoint incl. the polar backward of the object gradient; the caller zeroes gPhatT / gprop / gshift and runs the
+// probe-spectrum inverse FFT
+inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float* obja, const float* objp, float* g_obja, float* g_objp,
+                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, long long* launches) {
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, bw.f, sc, bw.f.phis);
-    a.G = bw.G; a.gO = bw.gO; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
+    a.G = bw.G; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
     a.dx = bw.dx; a.k0 = bw.k0;
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
     const bool acc_mode = (c.reserved[0] & 1) != 0;     // experimental: accumulate over probe modes before scattering
     a.units = acc_mode ? B * c.M : B * c.M * c.P;
     a.direct_red = acc_mode ? 0 : 1;
+    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    if (a.need_obj) F128_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
     if (a.need_probe) {
         if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
         else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
@@ -612,6 +783,10 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, unsigned cha
     F128_CK(cudaGetLastError()); ++*launches;
     if (a.need_probe && c.shift_probes) {
         k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
+        F128_CK(cudaGetLastError()); ++*launches;
+    }
+    if (a.need_obj) {
+        k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj);
         F128_CK(cudaGetLastError()); ++*launches;
     }
     return 0;
