@@ -31,6 +31,9 @@
 namespace ptyb {
 namespace fused128 {
 
+#ifndef F128_TMA_RED
+#define F128_TMA_RED 0
+#endif
 constexpr int FN = 128;
 constexpr int FT = 512;                 // threads per CTA
 constexpr int CH = 528;                 // elements per chunk region (512 used by E1, 16 rows x 33 by E2)
@@ -38,6 +41,7 @@ constexpr int E_ELEMS = 32 * CH;        // 16896 float2 = 135168 B
 constexpr int TILE = FN * FN;           // 16384
 constexpr size_t SMEM_BYTES = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + sizeof(float) * TILE + 128 * sizeof(float);
 // the forward does not use the dL/dI tile: a smaller carve-out leaves ~88 KB of L1
+constexpr size_t SMEM_BYTES_BWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + (F128_TMA_RED ? 16 * 4096 : 0);
 constexpr size_t SMEM_BYTES_FWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + 16 * 4096;   // + stash staging
 
 struct Args {
@@ -191,7 +195,7 @@ struct Smem {
     float2* wx;
     float2* ey;
     float2* ex;
-    float* fl;      // TILE floats: dL/dI in layout F (adjoint)
+    float* fl;      // 64 KB: per-warp TMA staging blocks (16 warps x 4 KB)
     float* red;     // 128 floats (block_sum scratch)
 };
 __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
@@ -356,6 +360,13 @@ __device__ __forceinline__ float4 pack2(float2 a, float2 b) { return make_float4
 #ifndef F128_EXP
 #define F128_EXP 0      // timing experiments only (results are wrong): 1 = no ROI loads, 2 = no stash stores, 4 = no propagator loads
 #endif
+#ifndef F128_CHA
+#define F128_CHA 2
+#endif
+#ifndef F128_TMA_RED
+#define F128_TMA_RED 0
+#endif
+constexpr int CHA = F128_CHA;     // chunk of the two-stream (psi, O) adjoint phase
 constexpr int CH2 = F128_CHK;     // pointwise phases load CH2 16-byte words per stream ahead of use
 
 // ---- forward ------------------------------------------------------------------------------------------------------
@@ -491,6 +502,45 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 // ---- adjoint --------------------------------------------------------------------------------------------------------
 // gO accumulation over the probe modes.  MODE 0: first mode -> store; 1: middle -> read-modify-write;
 // 2: last mode -> scatter (accumulator + own) into the dense gradient; 3: scatter own (default); 4: not wanted
+// default scatter path (one CTA per probe mode): conj(psi_z) gphi_z is staged per warp in shared memory (8 pairs = 8 x 512 B)
+// and handed to the TMA engine as bulk reductions (cp.reduce.async.bulk ... add.f32) into the packed dense gradient --
+// the SM issues no RED instructions and keeps no registers alive for them.
+__device__ __forceinline__ void accum_phase_tma(float2 (&v)[32], const float4* __restrict__ st, const float4* __restrict__ Oz, size_t ostr,
+                                                float4* gOz_warp /* lane-0 address of pair 0 */, float4* sw, int lane, bool want) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (want) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j0 = 0; j0 < 8; j0 += CHA) {
+            float4 ps[CHA], o[CHA];
+#pragma unroll
+            for (int i = 0; i < CHA; ++i) {
+                o[i] = __ldg(Oz + (h * 8 + j0 + i) * ostr);
+                if (want) ps[i] = __ldg(st + (h * 8 + j0 + i) * 32);
+            }
+#pragma unroll
+            for (int i = 0; i < CHA; ++i) {
+                const int k = 2 * (h * 8 + j0 + i);
+                if (want) sw[(j0 + i) * 32] = pack2(cmulc(v[k], lo2(ps[i])), cmulc(v[k + 1], hi2(ps[i])));     // conj(psi) * gphi
+                v[k] = cmulc(v[k], lo2(o[i]));                     // gpsi_z = conj(O_z) gphi_z
+                v[k + 1] = cmulc(v[k + 1], hi2(o[i]));
+            }
+        }
+        if (want) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) bulk_reduce_add_f32(gOz_warp + (size_t)(h * 8 + jj) * ostr, sw - lane + jj * 32, 512);
+                bulk_commit();
+            }
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void accum_phase(float2 (&v)[32], const float4* __restrict__ st, const float4* __restrict__ Oz, size_t ostr,
                                             float4* __restrict__ ac, float4* __restrict__ gOz) {
@@ -546,13 +596,9 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         const float4* Oplane = a.Opack + (size_t)m * d.Z * plane;
         __syncthreads();
         load_tables(s, a, b);
-        {   // dL/dI in layout F, scaled: 2 occu_m G~ / N^2
-            const float sc = 2.0f * a.f.occu[m] * (1.0f / (128.0f * 128.0f));
-            const float* __restrict__ G = a.G + (size_t)b * TILE;
-            const int Yk = (g.ky + 64) & 127;
-#pragma unroll
-            for (int u = 0; u < 32; ++u) s.fl[u * 512 + g.t] = sc * __ldg(G + Yk * 128 + ((g.kx(u) + 64) & 127));
-        }
+        // dL/dI in layout F, scaled 2 occu_m G~ / N^2, is gathered from global memory in the (single) start phase per mode
+        const float gsc = 2.0f * a.f.occu[m] * (1.0f / (128.0f * 128.0f));
+        const float* __restrict__ Grow = a.G + (size_t)b * TILE + ((g.ky + 64) & 127) * 128;
         __syncthreads();
         const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
         const size_t ostr = (size_t)8 * d.Nox;
@@ -582,8 +628,8 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
 #pragma unroll
                         for (int i = 0; i < CH2; ++i) {
                             const int u = 2 * (j0 + i);
-                            v[u] = cscale(lo2(f[i]), s.fl[u * 512 + g.t]);
-                            v[u + 1] = cscale(hi2(f[i]), s.fl[(u + 1) * 512 + g.t]);
+                            v[u] = cscale(lo2(f[i]), gsc * __ldg(Grow + ((g.kx(u) + 64) & 127)));
+                            v[u + 1] = cscale(hi2(f[i]), gsc * __ldg(Grow + ((g.kx(u + 1) + 64) & 127)));
                         }
                     }
                 } else if (st_i >= 1) {
@@ -661,8 +707,13 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                             default: accum_phase<4>(v, st, Oz, ostr, ac, gOz); break;
                         }
                     } else {
+#if F128_TMA_RED       // measured slower than LSU reds on B200 (1.85 vs 1.67 ms per C2 batch): kept for reference
+                        float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
+                        accum_phase_tma(v, st, Oz, ostr, gOz - (g.x & 31), sw, g.lane, mode == 3);
+#else
                         if (mode == 3) accum_phase<3>(v, st, Oz, ostr, ac, gOz);
                         else accum_phase<4>(v, st, Oz, ostr, ac, gOz);
+#endif
                     }
                 }
             }
@@ -681,6 +732,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
             }
         }
     }
+    if (g.lane == 0) bulk_wait_all();       // staging blocks must outlive the TMA reads; reductions complete before exit
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
@@ -774,11 +826,11 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
     if (acc_mode) {
         int grid = a.units < sms ? a.units : sms;
         if (grid > MAX_SLOTS) grid = MAX_SLOTS;
-        F128_CK(cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        k_backward<true><<<grid, FT, SMEM_BYTES, st>>>(a);
+        F128_CK(cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));
+        k_backward<true><<<grid, FT, SMEM_BYTES_BWD, st>>>(a);
     } else {
-        F128_CK(cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        k_backward<false><<<a.units, FT, SMEM_BYTES, st>>>(a);
+        F128_CK(cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));
+        k_backward<false><<<a.units, FT, SMEM_BYTES_BWD, st>>>(a);
     }
     F128_CK(cudaGetLastError()); ++*launches;
     if (a.need_probe && c.shift_probes) {
