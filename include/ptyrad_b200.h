@@ -130,12 +130,13 @@ int ptyb200_loss_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const 
 /* loss_sparse (losses.py:91-104) evaluated on the ROIs without materialising the patches:
  * loss = weight * sum_m occu_m * (mean_{b,z,y,x} |phi_patch|^n)^(1/n);  Ssum (M doubles) kept for the gradient. */
 int ptyb200_sparse_forward(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
-                           const int64_t* idx, int32_t B, const float* occu, float* loss_out, double* Ssum, ptyb200_stream s);
+                           const int64_t* idx, int32_t B, const float* occu, float* loss_out, double* Ssum,
+                           int32_t* cover /* Noy*Nox int32, filled: ROIs of the batch covering each pixel */, ptyb200_stream s);
 
-/* g_objp (dense, += ) gets upstream * d(loss_sparse)/d(objp); cover_scratch = Noy*Nox int32 of scratch. */
+/* g_objp (dense, += ) gets upstream * d(loss_sparse)/d(objp); cover = the map ptyb200_sparse_forward filled. */
 int ptyb200_sparse_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
                         const int64_t* idx, int32_t B, const float* occu, const double* Ssum, const float* upstream,
-                        int32_t* cover_scratch, float* g_objp, ptyb200_stream s);
+                        const int32_t* cover, float* g_objp, ptyb200_stream s);
 
 /* optimizer.step() for torch.optim.Adam defaults (reconstruction.py:759; built at reconstruction.py:285-368):
  * one launch over up to 8 tensors with per-tensor learning rates.  The host arrays of pointers / lrs / numels are read

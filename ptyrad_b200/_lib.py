@@ -50,7 +50,7 @@ _SIGNATURES = {
     "ptyb200_backward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 17 + [C.c_uint32, _P]),
     "ptyb200_loss_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "ptyb200_loss_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
-    "ptyb200_sparse_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "ptyb200_sparse_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ptyb200_sparse_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ptyb200_adam_step": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P, _P]),
 }

@@ -347,10 +347,8 @@ int ptyb200_loss_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const
     LossK k = make_lossk(*lc);
     CK(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
     if (k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
-    size_t tot = (size_t)B * c->N * c->N;
-    unsigned blocks = (unsigned)((tot + 256 * 8 - 1) / (256 * 8));
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_loss_partial<<<blocks, 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac);
+    unsigned chunks = (unsigned)((c->N * c->N + 256 * 16 - 1) / (256 * 16));
+    k_loss_partial<<<dim3(chunks, B), 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac);
     CKL();
     k_loss_final<<<1, 256, 0, st>>>(k, B, c->N, stats, pac, losses3);
     CKL();
@@ -363,22 +361,25 @@ int ptyb200_loss_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const fl
     if (!c || !lc || !dp || !meas_all || !idx || !stats || !upstream3 || !G_out) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     LossK k = make_lossk(*lc);
-    size_t tot = (size_t)B * c->N * c->N;
-    unsigned blocks = (unsigned)((tot + 256 * 4 - 1) / (256 * 4));
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_loss_grad<<<blocks, 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac, upstream3, G_out);
+    unsigned chunks = (unsigned)((c->N * c->N + 256 * 8 - 1) / (256 * 8));
+    k_loss_grad<<<dim3(chunks, B), 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac, upstream3, G_out);
     CKL();
     return 0;
 }
 
 int ptyb200_sparse_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
-                           const int64_t* idx, int32_t B, const float* occu, float* loss_out, double* Ssum, ptyb200_stream s) {
-    if (!c || !lc || !objp || !crop_pos || !idx || !occu || !loss_out || !Ssum) return fail_msg("NULL argument");
+                           const int64_t* idx, int32_t B, const float* occu, float* loss_out, double* Ssum, int32_t* cover,
+                           ptyb200_stream s) {
+    if (!c || !lc || !objp || !crop_pos || !idx || !occu || !loss_out || !Ssum || !cover) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
     CK(cudaMemsetAsync(Ssum, 0, sizeof(double) * c->M, st));
-    dim3 g(1, c->M * c->Z, B);
-    k_sparse_partial<<<g, 256, 0, st>>>(d, lc->sparse_order, objp, crop_pos, idx, Ssum);
+    CK(cudaMemsetAsync(cover, 0, (size_t)c->Noy * c->Nox * 4, st));
+    k_cover<<<dim3((c->N * c->N + 1023) / 1024, B), 256, 0, st>>>(d, crop_pos, idx, cover);
+    CKL();
+    const size_t plane = (size_t)c->Noy * c->Nox;
+    unsigned chunks = (unsigned)((plane + 256 * 8 - 1) / (256 * 8));
+    k_sparse_partial<<<dim3(chunks, c->M * c->Z), 256, 0, st>>>(d, lc->sparse_order, objp, cover, Ssum);
     CKL();
     k_sparse_final<<<1, 32, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, occu, Ssum, loss_out);
     CKL();
@@ -387,13 +388,10 @@ int ptyb200_sparse_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, con
 
 int ptyb200_sparse_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* objp, const int32_t* crop_pos,
                         const int64_t* idx, int32_t B, const float* occu, const double* Ssum, const float* upstream,
-                        int32_t* cover, float* g_objp, ptyb200_stream s) {
+                        const int32_t* cover, float* g_objp, ptyb200_stream s) {
     if (!c || !lc || !objp || !crop_pos || !idx || !occu || !Ssum || !upstream || !cover || !g_objp) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
-    CK(cudaMemsetAsync(cover, 0, (size_t)c->Noy * c->Nox * 4, st));
-    k_cover<<<dim3((c->N * c->N + 1023) / 1024, B), 256, 0, st>>>(d, crop_pos, idx, cover);
-    CKL();
     size_t n = (size_t)c->M * c->Z * c->Noy * c->Nox;
     k_sparse_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, objp, occu, Ssum, upstream, cover, g_objp);
     CKL();

@@ -636,22 +636,26 @@ struct LossK {
 __device__ __forceinline__ float powp(float x, float p) { return p == 0.5f ? sqrtf(x) : (p == 1.0f ? x : powf(x, p)); }
 
 // stats: [0] sum (I^p-M^p)^2  [1] sum M^p  [2] sum (M^q log(I^q+e) - I^q)  [3] sum M^q  [4] sum M^r  [5] sum (Ibar^r - Mbar^r)^2
+// grid (chunks, B): block (c, b) handles a contiguous chunk of pattern b
 __global__ void k_loss_partial(LossK k, const float* __restrict__ dp, const float* __restrict__ meas, const int64_t* __restrict__ idx,
                                int B, int N, double* stats, float* pac) {
-    const size_t NN = (size_t)N * N, tot = (size_t)B * NN;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
-        size_t b = e / NN, pix = e - b * NN;
-        float I = dp[e], Mv = meas[(size_t)idx[b] * NN + pix];
-        if (k.s_on) { float mp = powp(Mv, k.s_p), df = powp(I, k.s_p) - mp; a0 += (double)df * df; a1 += mp; }
-        if (k.p_on) { float mq = powp(Mv, k.p_p), iq = powp(I, k.p_p); a2 += (double)(mq * logf(iq + k.p_eps) - iq); a3 += mq; }
+    const int NN = N * N, b = blockIdx.y;
+    const float* __restrict__ I_ = dp + (size_t)b * NN;
+    const float* __restrict__ M_ = meas + (size_t)idx[b] * NN;
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x) {
+        const float I = I_[pix], Mv = M_[pix];
+        if (k.s_on) { float mp = powp(Mv, k.s_p), df = powp(I, k.s_p) - mp; a0 += df * df; a1 += mp; }
+        if (k.p_on) { float mq = powp(Mv, k.p_p), iq = powp(I, k.p_p); a2 += mq * logf(iq + k.p_eps) - iq; a3 += mq; }
         if (k.b_on) { a4 += powp(Mv, k.b_p); atomicAdd(pac + pix, I); atomicAdd(pac + NN + pix, Mv); }
     }
-    a0 = warp_sum_d(a0); a1 = warp_sum_d(a1); a2 = warp_sum_d(a2); a3 = warp_sum_d(a3); a4 = warp_sum_d(a4);
-    if ((threadIdx.x & 31) == 0) {
-        if (k.s_on) { atomicAdd(stats + 0, a0); atomicAdd(stats + 1, a1); }
-        if (k.p_on) { atomicAdd(stats + 2, a2); atomicAdd(stats + 3, a3); }
-        if (k.b_on) atomicAdd(stats + 4, a4);
+    __shared__ float red[5 * 32];
+    float v[5] = {a0, a1, a2, a3, a4};
+    block_sum<5>(v, red);
+    if (threadIdx.x == 0) {
+        if (k.s_on) { atomicAdd(stats + 0, (double)v[0]); atomicAdd(stats + 1, (double)v[1]); }
+        if (k.p_on) { atomicAdd(stats + 2, (double)v[2]); atomicAdd(stats + 3, (double)v[3]); }
+        if (k.b_on) atomicAdd(stats + 4, (double)v[4]);
     }
 }
 
@@ -682,39 +686,44 @@ __global__ void k_loss_final(LossK k, int B, int N, double* stats, const float* 
 __global__ void k_loss_grad(LossK k, const float* __restrict__ dp, const float* __restrict__ meas, const int64_t* __restrict__ idx,
                             int B, int N, const double* __restrict__ stats, const float* __restrict__ pac,
                             const float* __restrict__ up, float* __restrict__ G) {
-    const size_t NN = (size_t)N * N, tot = (size_t)B * NN;
-    const double nel = (double)tot;
+    const int NN = N * N, b = blockIdx.y;
+    const double nel = (double)B * NN;
     float cs = 0.f, cp = 0.f, cb = 0.f;
     if (k.s_on) cs = float(up[0] * k.s_w * k.s_p / (nel * sqrt(stats[0] / nel) * (stats[1] / nel)));
     if (k.p_on) cp = float(-up[1] * k.p_w * k.p_p / (nel * (stats[3] / nel)));
     if (k.b_on) cb = float(up[2] * k.b_w * k.b_p / (nel * sqrt(stats[5] / NN) * (stats[4] / nel)));
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
-        size_t b = e / NN, pix = e - b * NN;
-        float I = dp[e], g = 0.f;
+    const float* __restrict__ I_ = dp + (size_t)b * NN;
+    const float* __restrict__ M_ = meas + (size_t)idx[b] * NN;
+    float* __restrict__ G_ = G + (size_t)b * NN;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x) {
+        const float I = I_[pix];
+        float g = 0.f;
         if (k.s_on || k.p_on) {
-            float Mv = meas[(size_t)idx[b] * NN + pix];
+            const float Mv = M_[pix];
             if (k.s_on) g += cs * (powp(I, k.s_p) - powp(Mv, k.s_p)) * powp(I, k.s_p - 1.0f);
             if (k.p_on) g += cp * (powp(Mv, k.p_p) / (powp(I, k.p_p) + k.p_eps) - 1.0f) * powp(I, k.p_p - 1.0f);
         }
         if (k.b_on) {
-            float ib = pac[pix] / B, mb = pac[NN + pix] / B;
+            const float ib = pac[pix] / B, mb = pac[NN + pix] / B;
             g += cb * (powp(ib, k.b_p) - powp(mb, k.b_p)) * powp(ib, k.b_p - 1.0f);
         }
-        G[e] = g;
+        G_[pix] = g;
     }
 }
 
-// sparse: grid (1, M*Z, B): Ssum[m] += sum |phi|^n over the ROI (one double atomic per block)
-__global__ void k_sparse_partial(Dims d, float order, const float* __restrict__ objp, const int32_t* __restrict__ crop,
-                                 const int64_t* __restrict__ idx, double* Ssum) {
-    int mz = blockIdx.y, b = blockIdx.z;
-    int64_t n0 = idx[b];
-    int cy = crop[2 * n0], cx = crop[2 * n0 + 1];
-    const float* pl = objp + (size_t)mz * d.Noy * d.Nox;
+// sparse: sum over the batch ROIs of |phi|^n == sum over object pixels of cover[px] * |phi[px]|^n, where cover counts
+// how many ROIs of the batch contain the pixel (k_cover).  grid (chunks, M*Z)
+__global__ void k_sparse_partial(Dims d, float order, const float* __restrict__ objp, const int32_t* __restrict__ cover, double* Ssum) {
+    const int mz = blockIdx.y;
+    const size_t plane = (size_t)d.Noy * d.Nox;
+    const float* pl = objp + (size_t)mz * plane;
     float acc = 0.f;
-    for (int e = threadIdx.x; e < d.N * d.N; e += blockDim.x) {
-        float v = fabsf(pl[(size_t)(cy + e / d.N) * d.Nox + cx + e % d.N]);
-        acc += order == 1.0f ? v : (order == 2.0f ? v * v : powf(v, order));
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < plane; e += (size_t)gridDim.x * blockDim.x) {
+        const int c = cover[e];
+        if (c) {
+            const float v = fabsf(pl[e]);
+            acc += float(c) * (order == 1.0f ? v : (order == 2.0f ? v * v : powf(v, order)));
+        }
     }
     __shared__ float red[32];
     float r1[1] = {acc};

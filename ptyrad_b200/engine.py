@@ -168,19 +168,19 @@ class SparseLossFunction(torch.autograd.Function):
         dev = objp.device
         loss = torch.empty((), dtype=torch.float32, device=dev)
         Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
+        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
         _lib.check(_lib.lib().ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(crop_pos), ptr(idx), idx.numel(),
-                                                     ptr(occu), ptr(loss), ptr(Ssum), _stream()))
-        ctx.save_for_backward(objp, crop_pos, idx, occu, Ssum)
+                                                     ptr(occu), ptr(loss), ptr(Ssum), ptr(cover), _stream()))
+        ctx.save_for_backward(objp, crop_pos, idx, occu, Ssum, cover)
         ctx.cfg, ctx.lcfg = cfg, lcfg
         return loss
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, up):
-        objp, crop_pos, idx, occu, Ssum = ctx.saved_tensors
+        objp, crop_pos, idx, occu, Ssum, cover = ctx.saved_tensors
         cfg = ctx.cfg
         g = torch.zeros_like(objp)
-        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=objp.device)
         up = up.reshape(1).contiguous().float()
         _lib.check(_lib.lib().ptyb200_sparse_grad(C.byref(cfg), C.byref(ctx.lcfg), ptr(objp), ptr(crop_pos), ptr(idx), idx.numel(),
                                                   ptr(occu), ptr(Ssum), ptr(up), ptr(cover), ptr(g), _stream()))
