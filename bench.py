@@ -299,6 +299,13 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this workload (per launch)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01", f"ncu_traffic_{cfg.name}.json")
+    if os.path.exists(tpath) and B == cfg.batch and args.path != "general":
+        tj = json.load(open(tpath))
+        kb = tj["kernels"]["k_backward"]
+        traffic, traffic_src = (kb["dram_read_gb"] + kb["dram_write_gb"]) * 1e9, "profiles/r01/" + os.path.basename(tpath)
     comp, stash = bytes_per_pattern(cfg)
     # adjoint section (dominant): re-reads the stash, reads the ROIs, read-modify-writes the ROI gradients, reads G
     bwd_bytes = B * (8 * cfg.P * cfg.M * cfg.Z + 16 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
@@ -315,7 +322,7 @@ def main():
         "eager": {"value": args.steps * B * world / (ms_eager * 1e-3), "ms_per_step": ms_eager / args.steps,
                   "note": "same steps launched kernel by kernel; section timings and gpu_launches come from this pass"},
         "roofline": {"bound": "hbm", "kernel": "multislice adjoint section (ptyb200_backward)", "achieved": ach_b, "peak": peak,
-                     "unit": "GB/s", "frac": ach_b / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": ach_b / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": ms_b,
                      "share_of_step": ms_b / (ms_eager / args.steps) if ms_eager > 0 else None},
         "roofline_forward": {"bound": "hbm", "achieved": fwd_bytes / (ms_f * 1e-3) / 1e9 if ms_f > 0 else 0.0, "peak": peak, "unit": "GB/s",

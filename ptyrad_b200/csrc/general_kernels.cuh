@@ -20,6 +20,9 @@ namespace ptyb {
 
 constexpr int ROWS = 16;   // slab height (rows per CTA)
 constexpr int NT = 256;    // threads per CTA
+#ifndef GEN_MINB
+#define GEN_MINB 1       // minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (256 * GEN_MINB))
+#endif
 
 struct Dims {
     int N, P, M, Z, Noy, Nox, B;
@@ -205,7 +208,7 @@ template <class F> struct Slab {
 // plain pass: FFT along the rows of `count` tiles, output transposed or not.  grid (N/ROWS, count)
 //   DIR=-1: natural in, frequency-ordered out;  DIR=+1: frequency-ordered (natural index) in, natural out
 // ------------------------------------------------------------------------------------------------
-template <class F, int DIR, bool TOUT> __global__ void __launch_bounds__(NT) k_pass(const float2* __restrict__ in, float2* __restrict__ out, float scale) {
+template <class F, int DIR, bool TOUT> __global__ void __launch_bounds__(NT, GEN_MINB) k_pass(const float2* __restrict__ in, float2* __restrict__ out, float scale) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const int r0 = blockIdx.x * ROWS;
@@ -254,7 +257,7 @@ struct FwdArgs {
 };
 
 // psi0 half-shifted: G2[b,p,0][y][kx] = (1/N) * inverse-y( PhatT[p][kx][ky] * wy[ky] * wx[kx] ).  grid (N/ROWS, B)
-template <class F> __global__ void __launch_bounds__(NT) k_init_shift(FwdArgs a) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_init_shift(FwdArgs a) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const int kx0 = blockIdx.x * ROWS, b = blockIdx.y;
@@ -274,7 +277,7 @@ template <class F> __global__ void __launch_bounds__(NT) k_init_shift(FwdArgs a)
 }
 
 // grid (N/ROWS, M, B).  src_mode: 0 = psi_z comes from G2 (inverse-x), 1 = psi_0 is the unshifted probe
-template <class F> __global__ void __launch_bounds__(NT) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.d;
@@ -326,7 +329,7 @@ template <class F> __device__ __forceinline__ void load_prop(const FwdArgs& a, i
 }
 
 // grid (N/ROWS, M, B): G1[kx][y] -> forward-y -> *H -> inverse-y -> G2[y][kx]
-template <class F> __global__ void __launch_bounds__(NT) k_fwd_bc(FwdArgs a, int z) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_bc(FwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.d;
@@ -354,7 +357,7 @@ template <class F> __global__ void __launch_bounds__(NT) k_fwd_bc(FwdArgs a, int
 }
 
 // grid (N/ROWS, B): dp[b][sh(ky)][sh(kx)] = eps + sum_{m,p} occu_m |forward-y(farT)|^2 / N^2
-template <class F> __global__ void __launch_bounds__(NT) k_fwd_final(FwdArgs a) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_final(FwdArgs a) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.d;
@@ -395,7 +398,7 @@ struct BwdArgs {
 };
 
 // grid (N/ROWS, M, B): farT -> forward-y -> * 2 occu G~ -> inverse-y -> G2
-template <class F> __global__ void __launch_bounds__(NT) k_bwd_start(BwdArgs a) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_start(BwdArgs a) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.f.d;
@@ -426,7 +429,7 @@ template <class F> __global__ void __launch_bounds__(NT) k_bwd_start(BwdArgs a) 
 
 // grid (N/ROWS, M, B).  out_mode: 0 = forward-x and store transposed to G1 (z>0, or z==0 with shifted probes),
 //                                 1 = store gpsi_0 untransformed (natural) to G1 (z==0, unshifted probes), 2 = nothing
-template <class F> __global__ void __launch_bounds__(NT) k_bwd_da(BwdArgs a, int z, int out_mode) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdArgs a, int z, int out_mode) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.f.d;
@@ -469,7 +472,7 @@ template <class F> __global__ void __launch_bounds__(NT) k_bwd_da(BwdArgs a, int
 }
 
 // grid (N/ROWS, M, B), z >= 1: G1 -> forward-y -> *conj(H) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
-template <class F> __global__ void __launch_bounds__(NT) k_bwd_bc(BwdArgs a, int z) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.f.d;
@@ -521,7 +524,7 @@ template <class F> __global__ void __launch_bounds__(NT) k_bwd_bc(BwdArgs a, int
 
 // shifted probes: grid (N/ROWS, P, nchunk).  T = forward-y(sum_m G1[b,p,m]) / N^2 ; gPhatT += conj(w') T ;
 // shift gradients -2 pi sum kappa Im(conj(w') conj(Phat) T)
-template <class F> __global__ void __launch_bounds__(NT) k_bwd_probe(BwdArgs a, int bchunk) {
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(BwdArgs a, int bchunk) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.f.d;
