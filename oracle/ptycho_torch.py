@@ -48,11 +48,11 @@ class OracleModel:
         # amplitude / phase are taken from the complex64 object in float32 first (models.py:99-100)
         self.obja = torch.abs(obj).to(torch.float32).to(rd).requires_grad_(True)
         self.objp = torch.angle(obj).to(torch.float32).to(rd).requires_grad_(True)
-        self.tilts = torch.as_tensor(np.asarray(iv["obj_tilts"]), dtype=torch.float32).to(rd).requires_grad_(True)
-        self.dz = torch.as_tensor(np.asarray(iv["slice_thickness"]), dtype=torch.float32).to(rd).requires_grad_(True)
+        self.tilts = torch.as_tensor(np.asarray(iv["obj_tilts"]), dtype=torch.float32).to(rd).clone().requires_grad_(True)   # clone: never alias the caller's arrays
+        self.dz = torch.as_tensor(np.asarray(iv["slice_thickness"]), dtype=torch.float32).to(rd).clone().requires_grad_(True)
         pr = torch.as_tensor(np.asarray(iv["probe"])).to(C64)
         self.probe = torch.view_as_real(pr).to(rd).clone().requires_grad_(True)      # (P,N,N,2) real view
-        self.shifts = torch.as_tensor(np.asarray(iv["probe_pos_shifts"]), dtype=torch.float32).to(rd).requires_grad_(True)
+        self.shifts = torch.as_tensor(np.asarray(iv["probe_pos_shifts"]), dtype=torch.float32).to(rd).clone().requires_grad_(True)
         self.occu = torch.as_tensor(np.asarray(iv["omode_occu"]), dtype=torch.float32).to(rd)
         self.H = torch.as_tensor(np.asarray(iv["H"])).to(C64).to(cd)
         self.meas = torch.as_tensor(np.asarray(iv["measurements"]), dtype=torch.float32).to(rd)
