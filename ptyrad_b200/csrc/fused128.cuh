@@ -19,9 +19,11 @@
 // are pre-permuted so that they are read thread-privately and coalesced.  tools/proto_fused128.py is the NumPy
 // model of this index algebra.
 //
-// Forward: grid (P, M, B), one wave per CTA.  Adjoint: one CTA per (sample, object mode) looping over the probe modes
-// so that gO_z = sum_p conj(psi_z) gphi_z is accumulated in a CTA-private, L2-resident scratch and scattered into the
-// dense object gradient with ONE red.global.add.v2.f32 per pixel and slice.
+// Forward: grid (P, M, B), one wave per CTA; psi_z is stashed per slice through per-warp shared-memory staging blocks and
+// TMA bulk stores (cp.async.bulk), the far-field spectrum is kept for the adjoint.  Adjoint: one CTA per (sample, object
+// mode, probe mode); conj(psi_z) gphi_z is scattered straight into the packed, L2-resident dense object gradient with
+// red.global.add.v4.f32 (an accumulate-over-modes variant is kept behind cfg.reserved[0] & 1).  Every buffer this path owns
+// uses 16-byte "pair" layouts so that a thread's two consecutive elements are one 128-bit access.
 #pragma once
 #include "general_kernels.cuh"
 #include "../../include/ptyrad_b200.h"
@@ -322,13 +324,6 @@ __device__ __forceinline__ void l2_prefetch_roi(const float4* plane, int cy, int
         l2_prefetch(plane + (size_t)(cy + (i & 3) + 8 * (i >> 2)) * Nox + cx, 2048);
     }
 }
-// L1 prefetch of the lines this warp will read in a pointwise phase: a warp reads 512 contiguous bytes per pair j
-// (4 lines of 128 B); lanes 0..3 cover pair j = jbase + (lane >> 2)... one instruction per thread covers 8 pairs:
-// lane l prefetches line (l & 3) of pair j0 + (l >> 2).  `base` is the warp's lane-0 address of pair 0, `stride` in float4.
-__device__ __forceinline__ void l1_prefetch_pairs(const float4* lane0_base, size_t stride, int j0, int lane) {
-    const float4* p = lane0_base + (size_t)(j0 + (lane >> 2)) * stride + (lane & 3) * 8;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
 // TMA bulk copy shared -> global (asynchronous, issued by one lane; no LSU store traffic, no register reads at drain time)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -351,20 +346,8 @@ __device__ __forceinline__ float4 pack2(float2 a, float2 b) { return make_float4
 #ifndef F128_CHK
 #define F128_CHK 4
 #endif
-#ifndef F128_L1PF
-#define F128_L1PF 0
-#endif
-#ifndef F128_STAGGER
-#define F128_STAGGER 0
-#endif
-#ifndef F128_EXP
-#define F128_EXP 0      // timing experiments only (results are wrong): 1 = no ROI loads, 2 = no stash stores, 4 = no propagator loads
-#endif
 #ifndef F128_CHA
 #define F128_CHA 2
-#endif
-#ifndef F128_TMA_RED
-#define F128_TMA_RED 0
 #endif
 constexpr int CHA = F128_CHA;     // chunk of the two-stream (psi, O) adjoint phase
 constexpr int CH2 = F128_CHK;     // pointwise phases load CH2 16-byte words per stream ahead of use
@@ -383,12 +366,6 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     const Geo g;
     const Dims& d = a.f.d;
     const int p = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
-#if F128_STAGGER
-    {   // de-phase the SMs: identical CTAs started together would hit HBM with their stash bursts at the same instants
-        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        if (lin < 148u) __nanosleep((lin % F128_STAGGER) * (15000u / F128_STAGGER));
-    }
-#endif
     const int64_t n0 = a.f.idx[b];
     const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
     const size_t plane = (size_t)d.Noy * d.Nox;
@@ -449,13 +426,6 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
                     bulk_commit();
                 }
             }
-#if F128_L1PF
-            {   // stage the propagator table (first 2/3) in L1 while the FFT runs
-                const float4* hf0 = reinterpret_cast<const float4*>(a.HF) + (g.t & ~31);
-                l1_prefetch_pairs(hf0, 512, 0, g.lane);
-                if (F128_L1PF > 1) l1_prefetch_pairs(hf0, 512, 8, g.lane);
-            }
-#endif
             fft2_R_to_F(v, s.E, s.tw, g);
             if (z == d.Z - 1) break;
             const float4* __restrict__ hf = reinterpret_cast<const float4*>(a.HF) + g.t;
@@ -475,13 +445,6 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
                     v[u + 1] = cmul(v[u + 1], h1);
                 }
             }
-#if F128_L1PF
-            if (z + 1 < d.Z) {   // stage the next slice's ROI (first 2/3) in L1 while the inverse FFT runs
-                const float4* o0 = Oplane + (size_t)(z + 1) * plane + (size_t)(cy + g.yl) * d.Nox + cx + (g.x & ~31);
-                l1_prefetch_pairs(o0, ostr, 0, g.lane);
-                if (F128_L1PF > 1) l1_prefetch_pairs(o0, ostr, 8, g.lane);
-            }
-#endif
         }
         fft2_F_to_R(v, s.E, s.tw, g);
     }
