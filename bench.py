@@ -271,11 +271,23 @@ def main():
         for s in range(3):
             e2e_step(s % len(host_meas))
         sync_all()
-        t0 = time.perf_counter()
-        for s in range(k2):
-            l5 = e2e_step(s % len(host_meas))
-            host_loss.copy_(l5, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        nh = len(host_meas)
+        if args.no_graph:
+            t0 = time.perf_counter()
+            for s in range(k2):
+                l5 = e2e_step(s % nh)
+                host_loss.copy_(l5, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        else:
+            # every step still copies its own inputs host -> device and its result device -> host inside the timed region;
+            # the copy of batch s+1 runs on a side stream while batch s computes (what a streaming data loader does)
+            t0 = time.perf_counter()
+            g2.prefetch(host_idx[0], host_meas[0])
+            for s in range(k2):
+                l5 = g2.step_prefetched()
+                g2.prefetch(host_idx[(s + 1) % nh], host_meas[(s + 1) % nh])
+                host_loss.copy_(l5, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         sync_all()
         dt = time.perf_counter() - t0
         if world > 1:

@@ -21,7 +21,7 @@ namespace ptyb {
 constexpr int ROWS = 16;   // slab height (rows per CTA)
 constexpr int NT = 256;    // threads per CTA
 #ifndef GEN_MINB
-#define GEN_MINB 1       // minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (256 * GEN_MINB))
+#define GEN_MINB 2       // minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (256 * GEN_MINB))
 #endif
 
 struct Dims {
@@ -47,6 +47,15 @@ __device__ __forceinline__ void red_add_f2(float2* addr, float2 v) {
     atomicAdd(&addr->x, v.x);
     atomicAdd(&addr->y, v.y);
 #endif
+}
+
+// L2 prefetch of a contiguous range (TMA bulk prefetch; address and size multiples of 16 bytes)
+__device__ __forceinline__ void l2_prefetch_range(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes));
+}
+// every slab this path reads is 16 contiguous rows of a tile: warm the NEXT probe mode's slab while this one is processed
+template <int N> __device__ __forceinline__ void prefetch_slab(const float2* tile, int row0) {
+    if (threadIdx.x < ROWS) l2_prefetch_range(tile + (size_t)(row0 + threadIdx.x) * N, N * 8);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -300,6 +309,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdA
             });
         } else {
             const float2* src = a.G2 + (tile + msrc) * N * N;
+            if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
             Slab<F>::nat([&](int, int r, int kx) { slab[r * F::RS + F::apos(kx)] = src[(size_t)(y0 + r) * N + kx]; });
             __syncthreads();
             F::inverse(slab, ROWS, twN);
@@ -339,6 +349,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_bc(FwdA
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const float2* src = a.G1 + tile * N * N;
+        if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
         Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
         __syncthreads();
         F::forward(slab, ROWS, twN);
@@ -445,10 +456,14 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const float2* src = a.f.G2 + tile * N * N;
+        const float2* st = a.f.stash + (tile * d.Z + z) * N * N;
+        if (p + 1 < d.P) {
+            prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
+            prefetch_slab<N>(st + (size_t)d.M * d.Z * N * N, y0);
+        }
         Slab<F>::nat([&](int, int r, int kx) { slab[r * F::RS + F::apos(kx)] = src[(size_t)(y0 + r) * N + kx]; });
         __syncthreads();
         F::inverse(slab, ROWS, twN);
-        const float2* st = a.f.stash + (tile * d.Z + z) * N * N;
         float2* dst = a.f.G1 + tile * N * N;
         Slab<F>::nat([&](int i, int r, int x) {
             float2 gphi = cscale(slab[r * F::RS + F::addr(x)], 1.0f / N);
@@ -493,6 +508,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdA
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const float2* src = a.f.G1 + tile * N * N;
+        if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
         Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
         __syncthreads();
         F::forward(slab, ROWS, twN);

@@ -111,6 +111,13 @@ class GraphedStep:
             N = model.opt_probe.shape[1]
             self.meas = torch.zeros((self.B, N, N), dtype=torch.float32, device=dev)
             mv = MeasurementView(self.meas, torch.arange(self.B, device=dev))
+            # double buffering for `prefetch`: the next batch is copied host -> device on a side stream while this one runs
+            self._next_meas = torch.zeros_like(self.meas)
+            self._next_idx = torch.zeros_like(self.idx)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_done = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
         # warm-up and capture must not change the model: snapshot parameters and optimizer state, restore afterwards
         # (a fresh optimizer is assumed: its state is zeroed again after the capture)
         snap_p = [p.detach().clone() for p in self.params]
@@ -147,6 +154,25 @@ class GraphedStep:
                 with torch.no_grad():
                     self._store[i].copy_(p.data)
                 p.data = self._store[i]
+
+    def prefetch(self, indices, measurements):
+        """Start the host -> device copy of the NEXT batch (pinned tensors) on a side stream; pair with `step_prefetched`."""
+        self._copy_stream.wait_event(self._consumed)
+        with torch.cuda.stream(self._copy_stream):
+            self._next_idx.copy_(indices, non_blocking=True)
+            self._next_meas.copy_(measurements, non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+
+    def step_prefetched(self):
+        """Run the step on the batch handed to the last `prefetch` call."""
+        self._rebind()
+        cur = torch.cuda.current_stream(self.idx.device)
+        cur.wait_event(self._copy_done)
+        self.idx.copy_(self._next_idx, non_blocking=True)
+        self.meas.copy_(self._next_meas, non_blocking=True)
+        self._consumed.record(cur)
+        self.graph.replay()
+        return self.losses
 
     def __call__(self, indices, measurements=None):
         self._rebind()
