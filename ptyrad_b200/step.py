@@ -185,3 +185,77 @@ class GraphedStep:
         self.idx.copy_(indices, non_blocking=True)
         self.graph.replay()
         return self.losses
+
+
+def toggle_grad_requires(model, niter: int):
+    """requires_grad per optimisable tensor from its start_iter (reference reconstruction.py:783-790)."""
+    for name, start in model.start_iter.items():
+        model.optimizable_tensors[name].requires_grad = start is not None and niter >= start
+
+
+def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint_fn, niter, verbose=True, arena: GradArena | None = None,
+               world: int = 1, rank: int = 0, graphed: dict | None = None):
+    """One iteration over all batches: the non-LBFGS branch of the reference's ``recon_step`` (reconstruction.py:658-781) with the
+    same bookkeeping (``batch_losses`` dict in ``loss_params`` key order, ``model.loss_iters / iter_times / dz_iters /
+    avg_tilt_iters``, constraints once per iteration) but ONE host synchronisation per iteration instead of three per batch:
+    the per-batch losses stay on the device until the end of the iteration.
+
+    `graphed`: optional {batch_size: GraphedStep}; batches of a captured size are replayed as CUDA graphs.  With `world` > 1
+    every rank passes the same global batches and takes its own slice (split_batches=True semantics).  LBFGS needs the
+    closure-based loop of the reference and is not handled here.
+    """
+    import time
+    if isinstance(optimizer, torch.optim.LBFGS):
+        raise NotImplementedError("LBFGS: use the reference's closure loop (works unchanged with this model)")
+    dev = model.opt_obja.device
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    toggle_grad_requires(model, niter)
+    if arena is not None:
+        arena.attach()
+        arena.zero()
+    else:
+        optimizer.zero_grad()
+    per_batch = []
+    nb = len(batches)
+    for bi, batch in enumerate(batches):
+        mine = shard_indices(batch, rank, world) if world > 1 else batch
+        last_of_group = (bi + 1) % grad_accumulation == 0 or (bi + 1) == nb
+        g = graphed.get(len(mine)) if (graphed and grad_accumulation == 1) else None
+        if g is not None:
+            per_batch.append(g(mine).clone())
+            continue
+        dp = model(mine)
+        idx = model._current_object_patches.idx
+        if model.meas_padded is None and model.meas_scale_factors is None:
+            meas = MeasurementView(model.measurements, idx)
+        else:
+            meas = model.get_measurements(idx)
+        total, losses = loss_fn(dp, meas, model._current_object_patches, model.omode_occu)
+        (total / grad_accumulation).backward()
+        if last_of_group:
+            if world > 1:
+                arena.allreduce(world)
+            optimizer.step()
+            if arena is not None:
+                arena.zero()
+            else:
+                optimizer.zero_grad()
+        model.clear_cache()
+        per_batch.append(torch.stack([l.detach().reshape(()) for l in losses]))
+    if constraint_fn is not None:
+        constraint_fn(model, niter)
+    host = torch.stack(per_batch).cpu().numpy()                  # the one synchronisation of the iteration
+    iter_t = time.perf_counter() - t0
+    names = list(loss_fn.loss_params.keys())
+    batch_losses = {n: [host[i, j] for i in range(host.shape[0])] for j, n in enumerate(names)}
+    loss_iter = float(sum(np.mean(v) for v in batch_losses.values()))
+    if verbose and rank == 0:
+        print(f"Iter: {niter}, Total Loss: {loss_iter:.4f}, " + ", ".join(f"{n}: {np.mean(v):.4f}" for n, v in batch_losses.items()) +
+              f", in {iter_t:.3f} sec")
+    model.loss_iters.append((niter, loss_iter))
+    model.iter_times.append(iter_t)
+    model.dz_iters.append((niter, model.opt_slice_thickness.detach().cpu().numpy()))
+    model.avg_tilt_iters.append((niter, model.opt_obj_tilts.detach().mean(0).cpu().numpy()))
+    return batch_losses

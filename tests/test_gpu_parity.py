@@ -340,3 +340,56 @@ def test_grad_accumulation_and_frozen_start_iter():
     r2 = oracle_step(iv, mp, lp, b2, torch.float64)["grads"]
     for k in r1:
         assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), 0.5 * (r1[k] + r2[k])) < TOL_G[k], k
+
+
+def test_recon_step_iterations_with_start_iter_and_constraint():
+    """Iteration-level driver: start_iter toggling (probe starts at iteration 2), grad accumulation of 2, a constraint that rebinds
+    .data once per iteration, bookkeeping lists -- against the oracle trainer driven through the same schedule."""
+    import copy
+    from oracle.ptycho_torch import OracleModel, loss_terms
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.step import GradArena, recon_step
+    from ptyrad_b200.synthetic import make_inputs
+    iv, mp, lp = make_inputs("T64", seed=23)
+    mp = copy.deepcopy(mp)
+    mp["update_params"]["probe"]["start_iter"] = 2
+    batches = [np.arange(0, 6), np.arange(6, 12), np.arange(12, 19), np.arange(19, 25)]
+
+    def positivity(model, niter):
+        with torch.no_grad():
+            model.opt_objp.data = model.opt_objp.data.clamp(min=0.0).contiguous()
+
+    model = PtychoAD(iv, mp, device="cuda", verbose=False)
+    loss_fn = CombinedLoss(lp, device="cuda")
+    opt = torch.optim.Adam(model.optimizable_params)
+    arena = GradArena(model)
+    hist = [recon_step(batches, 2, model, opt, loss_fn, positivity, it, verbose=False, arena=arena) for it in (1, 2, 3)]
+    assert list(hist[0].keys()) == list(lp.keys()) and len(hist[0]["loss_single"]) == len(batches)
+    assert len(model.loss_iters) == 3 and len(model.iter_times) == 3 and len(model.dz_iters) == 3 and len(model.avg_tilt_iters) == 3
+
+    om = OracleModel(iv, mp, torch.float32)
+    groups = [dict(params=[t], lr=om.lr[k]) for k, t in om.params().items() if om.lr[k] != 0]
+    oopt = torch.optim.Adam(groups)
+    oh = []
+    for it in (1, 2, 3):
+        for k, t in om.params().items():
+            st = mp["update_params"][k]["start_iter"]
+            t.requires_grad_(st is not None and it >= st)
+        oopt.zero_grad()
+        ls = []
+        for bi, b in enumerate(batches):
+            dp, (a, p) = om.forward(b)
+            tot, _ = loss_terms(dp, om.meas[torch.as_tensor(b)], p, om.occu, lp, obja_patches=a)
+            (tot / 2).backward()
+            ls.append(float(tot.detach()))
+            if (bi + 1) % 2 == 0:
+                oopt.step()
+                oopt.zero_grad()
+        with torch.no_grad():
+            om.objp.data = om.objp.data.clamp(min=0.0)
+        oh.append(ls)
+    ours = [[sum(h[n][i] for n in h) for i in range(len(batches))] for h in hist]
+    np.testing.assert_allclose(np.array(ours), np.array(oh), rtol=3e-4)
+    assert rel(model.opt_objp.detach().cpu().numpy(), om.objp.detach().numpy()) < 1e-3
+    p0 = np.stack([iv["probe"].real, iv["probe"].imag], -1)
+    assert rel(model.opt_probe.detach().cpu().numpy() - p0, om.probe.detach().numpy() - p0) < 5e-2
