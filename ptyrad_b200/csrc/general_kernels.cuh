@@ -285,44 +285,63 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_init_shift(
     }
 }
 
-// grid (N/ROWS, M, B).  src_mode: 0 = psi_z comes from G2 (inverse-x), 1 = psi_0 is the unshifted probe
+// grid (N/ROWS, M, B).  src_mode: 0 = psi_z comes from G2 (inverse-x), 1 = psi_0 is the unshifted probe.
+// The last inverse stage, the pointwise work (stash, *O_z) and the first forward stage act on the same N1 elements
+// x = j + N2*k of one row, so they are fused in registers: one work item (row r, j) per thread, no smem round trip between.
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
+    static_assert(ROWS * N2 <= NT && ROWS * N1 <= NT, "one fused work item per thread");
     const Dims& d = a.d;
     const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
     const int64_t n0 = a.idx[b];
     const int cy = a.crop[2 * n0], cx = a.crop[2 * n0 + 1];
     const float2* Oz = a.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
-    float2 Oreg[Slab<F>::EPT];
-    Slab<F>::nat([&](int i, int r, int x) { Oreg[i] = Oz[(size_t)(cy + y0 + r) * d.Nox + cx + x]; });
+    const bool item = threadIdx.x < ROWS * N2;
+    const int r = threadIdx.x / N2, j = threadIdx.x % N2;
+    float2 Oreg[N1];
+    if (item) {
+#pragma unroll
+        for (int k = 0; k < N1; ++k) Oreg[k] = Oz[(size_t)(cy + y0 + r) * d.Nox + cx + j + N2 * k];
+    }
     const int msrc = (z == 0) ? 0 : m;
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M;
-        float2* st = a.stash + ((tile + m) * d.Z + z) * N * N;
-        if (src_mode == 1) {
-            const float2* pr = a.probe + (size_t)p * N * N;
-            Slab<F>::nat([&](int i, int r, int x) {
-                float2 psi = pr[(size_t)(y0 + r) * N + x];
-                st[(size_t)(y0 + r) * N + x] = psi;
-                slab[r * F::RS + F::addr(x)] = cmul(psi, Oreg[i]);
-            });
-        } else {
+        float2* st = a.stash + ((tile + m) * d.Z + z) * N * N + (size_t)(y0 + r) * N + j;
+        float2* row = slab + r * F::RS;
+        if (src_mode == 0) {
             const float2* src = a.G2 + (tile + msrc) * N * N;
             if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
-            Slab<F>::nat([&](int, int r, int kx) { slab[r * F::RS + F::apos(kx)] = src[(size_t)(y0 + r) * N + kx]; });
+            Slab<F>::nat([&](int, int rr, int kx) { slab[rr * F::RS + F::apos(kx)] = src[(size_t)(y0 + rr) * N + kx]; });
             __syncthreads();
-            F::inverse(slab, ROWS, twN);
-            Slab<F>::nat([&](int i, int r, int x) {
-                float2 psi = cscale(slab[r * F::RS + F::addr(x)], 1.0f / N);
-                st[(size_t)(y0 + r) * N + x] = psi;
-                slab[r * F::RS + F::addr(x)] = cmul(psi, Oreg[i]);
-            });
+            F::inverse_first(slab, ROWS, twN);
+        }
+        if (item) {
+            float2 v[N1];
+            if (src_mode == 0) {
+#pragma unroll
+                for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[F::addr(j + N2 * k1)];
+                Dft<N1, +1>::run(v);
+#pragma unroll
+                for (int k = 0; k < N1; ++k) v[k] = cscale(v[k], 1.0f / N);
+            } else {
+                const float2* pr = a.probe + (size_t)p * N * N + (size_t)(y0 + r) * N + j;
+#pragma unroll
+                for (int k = 0; k < N1; ++k) v[k] = pr[N2 * k];
+            }
+#pragma unroll
+            for (int k = 0; k < N1; ++k) {
+                st[N2 * k] = v[k];
+                v[k] = cmul(v[k], Oreg[k]);
+            }
+            Dft<N1, -1>::run(v);
+#pragma unroll
+            for (int k1 = 0; k1 < N1; ++k1) row[F::addr(j + N2 * k1)] = k1 ? cmul(v[k1], twN[j * k1]) : v[k1];
         }
         __syncthreads();
-        F::forward(slab, ROWS, twN);
+        F::forward_last(slab, ROWS);
         float2* dst = (last ? a.farT : a.G1) + (tile + m) * N * N;
-        Slab<F>::tr([&](int, int r, int q) { dst[(size_t)q * N + y0 + r] = slab[r * F::RS + F::apos(q)]; });
+        Slab<F>::tr([&](int, int rr, int q) { dst[(size_t)q * N + y0 + rr] = slab[rr * F::RS + F::apos(q)]; });
         __syncthreads();
     }
 }
@@ -338,31 +357,57 @@ template <class F> __device__ __forceinline__ void load_prop(const FwdArgs& a, i
     }
 }
 
-// grid (N/ROWS, M, B): G1[kx][y] -> forward-y -> *H -> inverse-y -> G2[y][kx]
+// propagator values of one fused work item (row kx0 + r, k1): ky = k1 + N1*k2, k2 < N2
+template <class F> __device__ __forceinline__ void load_prop_item(const FwdArgs& a, int b, int kx, int k1, float2 (&Hreg)[F::N2]) {
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) Hreg[k2] = a.HT[(size_t)kx * N + k1 + N1 * k2];
+    if (a.tvec) {
+        const float2* ey = a.tvec + ((size_t)b * 2 + 0) * N;
+        const float2 exv = a.tvec[((size_t)b * 2 + 1) * N + kx];
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) Hreg[k2] = cmul(Hreg[k2], cmul(ey[k1 + N1 * k2], exv));
+    }
+}
+
+// grid (N/ROWS, M, B): G1[kx][y] -> forward-y -> *H -> inverse-y -> G2[y][kx].  The last forward stage, the propagator multiply
+// and the first inverse stage act on the same N2 elements ky = k1 + N1*k2: fused in registers, one item (row, k1) per thread.
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_bc(FwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.d;
     const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
-    float2 Hreg[Slab<F>::EPT];
-    load_prop<F>(a, b, kx0, Hreg);
+    const bool item = threadIdx.x < ROWS * N1;
+    const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    float2 Hreg[N2];
+    if (item) load_prop_item<F>(a, b, kx0 + r, k1, Hreg);
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const float2* src = a.G1 + tile * N * N;
         if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
-        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+        Slab<F>::nat([&](int, int rr, int y) { slab[rr * F::RS + F::addr(y)] = src[(size_t)(kx0 + rr) * N + y]; });
         __syncthreads();
-        F::forward(slab, ROWS, twN);
-        float2* ph = a.phis ? a.phis + (tile * (d.Z - 1) + z) * N * N : nullptr;
-        Slab<F>::nat([&](int i, int r, int ky) {
-            float2 v = slab[r * F::RS + F::apos(ky)];
-            if (ph) ph[(size_t)(kx0 + r) * N + ky] = v;
-            slab[r * F::RS + F::apos(ky)] = cmul(v, Hreg[i]);
-        });
+        F::forward_first(slab, ROWS, twN);
+        if (item) {
+            float2* row = slab + r * F::RS;
+            float2* ph = a.phis ? a.phis + (tile * (d.Z - 1) + z) * N * N + (size_t)(kx0 + r) * N + k1 : nullptr;
+            float2 v[N2];
+#pragma unroll
+            for (int j = 0; j < N2; ++j) v[j] = row[F::addr(j + N2 * k1)];
+            Dft<N2, -1>::run(v);
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) {
+                if (ph) ph[N1 * k2] = v[k2];
+                v[k2] = cmul(v[k2], Hreg[k2]);
+            }
+            Dft<N2, +1>::run(v);
+#pragma unroll
+            for (int j = 0; j < N2; ++j) row[F::addr(j + N2 * k1)] = k1 ? cmulc(v[j], twN[j * k1]) : v[j];
+        }
         __syncthreads();
-        F::inverse(slab, ROWS, twN);
+        F::inverse_last(slab, ROWS);
         float2* dst = a.G2 + tile * N * N;
-        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        Slab<F>::tr([&](int, int rr, int y) { dst[(size_t)y * N + kx0 + rr] = cscale(slab[rr * F::RS + F::addr(y)], 1.0f / N); });
         __syncthreads();
     }
 }
@@ -439,93 +484,128 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_start(B
 }
 
 // grid (N/ROWS, M, B).  out_mode: 0 = forward-x and store transposed to G1 (z>0, or z==0 with shifted probes),
-//                                 1 = store gpsi_0 untransformed (natural) to G1 (z==0, unshifted probes), 2 = nothing
+//                                 1 = store gpsi_0 untransformed (natural) to G1 (z==0, unshifted probes), 2 = nothing.
+// Register-fused like k_fwd_da: inverse stage over k1, gO accumulation over the probe modes, conj(O_z) multiply and the first
+// forward stage all act on the item's N1 elements x = j + N2*k.
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdArgs a, int z, int out_mode) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
     const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
     const int64_t n0 = a.f.idx[b];
     const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
     const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
-    float2 Oreg[Slab<F>::EPT], accO[Slab<F>::EPT];
-    Slab<F>::nat([&](int i, int r, int x) {
-        Oreg[i] = Oz[(size_t)(cy + y0 + r) * d.Nox + cx + x];
-        accO[i] = make_float2(0.f, 0.f);
-    });
+    const bool item = threadIdx.x < ROWS * N2;
+    const int r = threadIdx.x / N2, j = threadIdx.x % N2;
+    const size_t roi = (size_t)(cy + y0 + r) * d.Nox + cx + j;
+    float2 Oreg[N1], accO[N1];
+    if (item) {
+#pragma unroll
+        for (int k = 0; k < N1; ++k) { Oreg[k] = Oz[roi + N2 * k]; accO[k] = make_float2(0.f, 0.f); }
+    }
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const float2* src = a.f.G2 + tile * N * N;
-        const float2* st = a.f.stash + (tile * d.Z + z) * N * N;
+        const float2* stt = a.f.stash + (tile * d.Z + z) * N * N;
         if (p + 1 < d.P) {
             prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
-            prefetch_slab<N>(st + (size_t)d.M * d.Z * N * N, y0);
+            prefetch_slab<N>(stt + (size_t)d.M * d.Z * N * N, y0);
         }
-        Slab<F>::nat([&](int, int r, int kx) { slab[r * F::RS + F::apos(kx)] = src[(size_t)(y0 + r) * N + kx]; });
+        Slab<F>::nat([&](int, int rr, int kx) { slab[rr * F::RS + F::apos(kx)] = src[(size_t)(y0 + rr) * N + kx]; });
         __syncthreads();
-        F::inverse(slab, ROWS, twN);
+        F::inverse_first(slab, ROWS, twN);
         float2* dst = a.f.G1 + tile * N * N;
-        Slab<F>::nat([&](int i, int r, int x) {
-            float2 gphi = cscale(slab[r * F::RS + F::addr(x)], 1.0f / N);
-            float2 psi = st[(size_t)(y0 + r) * N + x];
-            accO[i] = cadd(accO[i], cmulc(gphi, psi));            // conj(psi) * gphi
-            float2 gpsi = cmulc(gphi, Oreg[i]);                   // conj(O) * gphi
-            if (out_mode == 0) slab[r * F::RS + F::addr(x)] = gpsi;
-            else if (out_mode == 1) dst[(size_t)(y0 + r) * N + x] = gpsi;
-        });
+        if (item) {
+            float2* row = slab + r * F::RS;
+            const float2* st = stt + (size_t)(y0 + r) * N + j;
+            float2 v[N1];
+#pragma unroll
+            for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[F::addr(j + N2 * k1)];
+            Dft<N1, +1>::run(v);
+#pragma unroll
+            for (int k = 0; k < N1; ++k) {
+                const float2 gphi = cscale(v[k], 1.0f / N);
+                accO[k] = cadd(accO[k], cmulc(gphi, st[N2 * k]));          // conj(psi) * gphi
+                v[k] = cmulc(gphi, Oreg[k]);                                // conj(O) * gphi
+            }
+            if (out_mode == 0) {
+                Dft<N1, -1>::run(v);
+#pragma unroll
+                for (int k1 = 0; k1 < N1; ++k1) row[F::addr(j + N2 * k1)] = k1 ? cmul(v[k1], twN[j * k1]) : v[k1];
+            } else if (out_mode == 1) {
+#pragma unroll
+                for (int k = 0; k < N1; ++k) dst[(size_t)(y0 + r) * N + j + N2 * k] = v[k];
+            }
+        }
         __syncthreads();
         if (out_mode == 0) {
-            F::forward(slab, ROWS, twN);
-            Slab<F>::tr([&](int, int r, int q) { dst[(size_t)q * N + y0 + r] = slab[r * F::RS + F::apos(q)]; });
+            F::forward_last(slab, ROWS);
+            Slab<F>::tr([&](int, int rr, int q) { dst[(size_t)q * N + y0 + rr] = slab[rr * F::RS + F::apos(q)]; });
             __syncthreads();
         }
     }
-    if (a.need_obj) {
-        float2* gOz = a.gO + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
-        Slab<F>::nat([&](int i, int r, int x) { red_add_f2(gOz + (size_t)(cy + y0 + r) * d.Nox + cx + x, accO[i]); });
+    if (a.need_obj && item) {
+        float2* gOz = a.gO + ((size_t)m * d.Z + z) * d.Noy * d.Nox + roi;
+#pragma unroll
+        for (int k = 0; k < N1; ++k) red_add_f2(gOz + N2 * k, accO[k]);
     }
 }
 
-// grid (N/ROWS, M, B), z >= 1: G1 -> forward-y -> *conj(H) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
+// grid (N/ROWS, M, B), z >= 1: G1 -> forward-y -> *conj(H_n) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
+// (register-fused like k_fwd_bc)
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
     const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
-    float2 Hreg[Slab<F>::EPT];
-    load_prop<F>(a.f, b, kx0, Hreg);
+    const bool item = threadIdx.x < ROWS * N1;
+    const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    float2 Hreg[N2];
+    if (item) load_prop_item<F>(a.f, b, kx0 + r, k1, Hreg);
     float s3[3] = {0.f, 0.f, 0.f};
-    float Kyr[Slab<F>::EPT], Kxr[Slab<F>::EPT], Kzr[Slab<F>::EPT];
-    if (a.need_prop) {
-        Slab<F>::nat([&](int i, int r, int ky) {
-            float Ky = kgrid(ky, N, a.dx), Kx = kgrid(kx0 + r, N, a.dx);
-            float k2 = Kx * Kx + Ky * Ky;
-            Kyr[i] = Ky; Kxr[i] = Kx;
-            Kzr[i] = -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0);     // Kz - k0, cancellation-free
-        });
-    }
+    const float Kx = kgrid(kx0 + r, N, a.dx);
     const float invN2 = 1.0f / (float(N) * float(N));
+    float Kyr[N2], Kzr[N2];                                  // Ky and Kz - k0 of the item's elements (propagator gradients only)
+    if (a.need_prop) {
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) {
+            const float Ky = kgrid(k1 + N1 * k2, N, a.dx);
+            const float kk = Kx * Kx + Ky * Ky;
+            Kyr[k2] = Ky;
+            Kzr[k2] = -kk / (sqrtf(a.k0 * a.k0 - kk) + a.k0);   // Kz - k0, cancellation-free
+        }
+    }
     for (int p = 0; p < d.P; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const float2* src = a.f.G1 + tile * N * N;
         if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
-        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+        Slab<F>::nat([&](int, int rr, int y) { slab[rr * F::RS + F::addr(y)] = src[(size_t)(kx0 + rr) * N + y]; });
         __syncthreads();
-        F::forward(slab, ROWS, twN);
-        const float2* ph = a.need_prop ? a.f.phis + (tile * (d.Z - 1) + (z - 1)) * N * N : nullptr;
-        Slab<F>::nat([&](int i, int r, int ky) {
-            float2 v = cmulc(slab[r * F::RS + F::apos(ky)], Hreg[i]);   // conj(H) * F2(gpsi)
-            if (ph) {
-                float2 phi = ph[(size_t)(kx0 + r) * N + ky];
-                float s = (phi.x * v.y - phi.y * v.x) * invN2;           // Im(conj(Phi) * v) / N^2
-                s3[0] += Kyr[i] * s; s3[1] += Kxr[i] * s; s3[2] += Kzr[i] * s;
+        F::forward_first(slab, ROWS, twN);
+        if (item) {
+            float2* row = slab + r * F::RS;
+            const float2* ph = a.need_prop ? a.f.phis + (tile * (d.Z - 1) + (z - 1)) * N * N + (size_t)(kx0 + r) * N + k1 : nullptr;
+            float2 v[N2];
+#pragma unroll
+            for (int jj = 0; jj < N2; ++jj) v[jj] = row[F::addr(jj + N2 * k1)];
+            Dft<N2, -1>::run(v);
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) {
+                v[k2] = cmulc(v[k2], Hreg[k2]);                              // conj(H) * F2(gpsi)
+                if (ph) {
+                    const float2 phi = ph[N1 * k2];
+                    const float sv = (phi.x * v[k2].y - phi.y * v[k2].x) * invN2;   // Im(conj(Phi) * v) / N^2
+                    s3[0] += Kyr[k2] * sv; s3[1] += Kx * sv; s3[2] += Kzr[k2] * sv;
+                }
             }
-            slab[r * F::RS + F::apos(ky)] = v;
-        });
+            Dft<N2, +1>::run(v);
+#pragma unroll
+            for (int jj = 0; jj < N2; ++jj) row[F::addr(jj + N2 * k1)] = k1 ? cmulc(v[jj], twN[jj * k1]) : v[jj];
+        }
         __syncthreads();
-        F::inverse(slab, ROWS, twN);
+        F::inverse_last(slab, ROWS);
         float2* dst = a.f.G2 + tile * N * N;
-        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        Slab<F>::tr([&](int, int rr, int y) { dst[(size_t)y * N + kx0 + rr] = cscale(slab[rr * F::RS + F::addr(y)], 1.0f / N); });
         __syncthreads();
     }
     if (a.need_prop) {

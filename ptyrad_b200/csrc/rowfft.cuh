@@ -85,6 +85,26 @@ template <int N1_, int N2_> struct RowFFT {
         for (int it = threadIdx.x; it < rows * N2; it += blockDim.x) inv_stage1(slab + (it / N2) * RS, it % N2);
         __syncthreads();
     }
+    // half transforms, for kernels that fuse their pointwise work into the register stage in the middle:
+    //   inverse_first  : inverse stage over k2 (all rows), then barrier -> the caller runs inverse stage over k1 itself
+    //   forward_last   : forward stage over j (all rows), then barrier  -> after the caller ran the forward stage over k
+    //   forward_first / inverse_last likewise for the other nesting
+    __device__ static void inverse_first(float2* slab, int rows, const float2* twN) {
+        for (int it = threadIdx.x; it < rows * N1; it += blockDim.x) inv_stage2(slab + (it / N1) * RS, it % N1, twN);
+        __syncthreads();
+    }
+    __device__ static void forward_last(float2* slab, int rows) {
+        for (int it = threadIdx.x; it < rows * N1; it += blockDim.x) fwd_stage2(slab + (it / N1) * RS, it % N1);
+        __syncthreads();
+    }
+    __device__ static void forward_first(float2* slab, int rows, const float2* twN) {
+        for (int it = threadIdx.x; it < rows * N2; it += blockDim.x) fwd_stage1(slab + (it / N2) * RS, it % N2, twN);
+        __syncthreads();
+    }
+    __device__ static void inverse_last(float2* slab, int rows) {
+        for (int it = threadIdx.x; it < rows * N2; it += blockDim.x) inv_stage1(slab + (it / N2) * RS, it % N2);
+        __syncthreads();
+    }
     // twN table fill (exact via sincospif); call before first use, followed by __syncthreads()
     __device__ static void fill_twiddles(float2* twN) {
         for (int n = threadIdx.x; n < N; n += blockDim.x) {
