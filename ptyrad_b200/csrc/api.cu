@@ -62,7 +62,7 @@ Workspace carve(const ptyb200_cfg& c, int B, void* base) {
     Workspace w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return reinterpret_cast<unsigned char*>(base) + o; };
-    const size_t NN = (size_t)c.N * c.N, obj = (size_t)c.M * c.Z * c.Noy * c.Nox, tiles = (size_t)B * c.P * c.M;
+    const size_t NN = (size_t)c.N * c.N, obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox, tiles = (size_t)B * c.P * c.M;
     w.O = (float2*)take(obj * 8);
     w.gO = (float2*)take(obj * 8);
     w.PhatT = (float2*)take(c.P * NN * 8);
@@ -90,6 +90,7 @@ int check_cfg(const ptyb200_cfg* c, int B) {
     if (c->P < 1 || c->M < 1 || c->Z < 1 || B < 1) return fail_msg("P, M, Z and B must be >= 1");
     if (c->Noy < c->N || c->Nox < c->N) return fail_msg("object canvas smaller than the probe");
     if (c->tilt_mode < 0 || c->tilt_mode > 2) return fail_msg("tilt_mode must be 0, 1 or 2");
+    if ((c->reserved[1] & 1) && (c->Noy != c->N || c->Nox != c->N)) return fail_msg("patch mode needs Noy == Nox == N");
     return 0;
 }
 
@@ -133,7 +134,7 @@ template <class F> int fft2_tiles(const float2* in, float2* tmp, float2* out, in
 FwdArgs make_fwd_args(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const int32_t* crop, const float* probe,
                       const float* occu, float* dp) {
     FwdArgs a;
-    a.d = Dims{c.N, c.P, c.M, c.Z, c.Noy, c.Nox, B};
+    a.d = Dims{c.N, c.P, c.M, c.Z, c.Noy, c.Nox, B, (c.reserved[1] & 1)};
     a.idx = idx; a.crop = crop; a.O = w.O; a.probe = (const float2*)probe; a.PhatT = w.PhatT; a.HT = w.HT;
     a.wvec = c.shift_probes ? w.wvec : nullptr;
     a.tvec = c.tilt_mode ? w.tvec : nullptr;
@@ -148,7 +149,7 @@ bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && 
 template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const float* obja,
                                     const float* objp, const float* probe, const float* shifts, const float* Hbase,
                                     const float* tilts, const float* dz, cudaStream_t st) {
-    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     if (!use_fused(c)) {                       // the fused path builds its own packed copy of the complex object
         k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
         CKL();
@@ -261,7 +262,7 @@ int ptyb200_propagator(const ptyb200_cfg* c, const float* dz, float* H_out, ptyb
 int ptyb200_gather_patches(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
                            const int32_t* crop_pos, float* patches_out, ptyb200_stream s) {
     if (!c || !idx || !obja || !objp || !crop_pos || !patches_out) return fail_msg("NULL argument");
-    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B, 0};
     dim3 g((c->N * c->N + 1023) / 1024, c->M * c->Z, B);
     k_gather_patches<<<g, 256, 0, (cudaStream_t)s>>>(d, idx, obja, objp, crop_pos, patches_out);
     CKL();
@@ -273,7 +274,7 @@ int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const f
                     const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
                     ptyb200_stream s) {
     if (int r = check_cfg(c, B)) return r;
-    if (!idx || !obja || !objp || !crop_pos || !probe || !Hbase || !occu || !dp_out || !workspace) return fail_msg("NULL argument");
+    if (!idx || !obja || !objp || (!crop_pos && !(c->reserved[1] & 1)) || !probe || !Hbase || !occu || !dp_out || !workspace) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     Workspace w = carve(*c, B, workspace);
     FwdArgs a = make_fwd_args(*c, B, w, idx, crop_pos, probe, occu, dp_out);
@@ -294,7 +295,7 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
                      float* g_obja, float* g_objp, float* g_probe, float* g_shifts, float* g_tilts, float* g_dz,
                      uint32_t need_mask, ptyb200_stream s) {
     if (int r = check_cfg(c, B)) return r;
-    if (!idx || !obja || !objp || !crop_pos || !probe || !Hbase || !occu || !G || !workspace) return fail_msg("NULL argument");
+    if (!idx || !obja || !objp || (!crop_pos && !(c->reserved[1] & 1)) || !probe || !Hbase || !occu || !G || !workspace) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     Workspace w = carve(*c, B, workspace);
     BwdArgs a;
@@ -312,7 +313,7 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (need_t && (!g_tilts || !c->tilt_mode)) return fail_msg("tilt gradient requested without tilts");
     if (need_dz && !g_dz) return fail_msg("g_dz is NULL");
     if (a.need_prop && !c->stash_fourier) return fail_msg("tilt/thickness gradients need cfg.stash_fourier = 1 in the forward");
-    const size_t obj = (size_t)c->M * c->Z * c->Noy * c->Nox;
+    const size_t obj = (size_t)((c->reserved[1] & 1) ? B : 1) * c->M * c->Z * c->Noy * c->Nox;
     if (a.need_obj && !use_fused(*c)) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
     if (a.need_probe && c->shift_probes) CK(cudaMemsetAsync(w.gPhatT, 0, (size_t)c->P * c->N * c->N * 8, st));
     if (need_mask & PTYB200_NEED_SHIFTS) CK(cudaMemsetAsync(g_shifts, 0, (size_t)c->Ntot * 2 * 4, st));
@@ -372,7 +373,7 @@ int ptyb200_sparse_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, con
                            ptyb200_stream s) {
     if (!c || !lc || !objp || !crop_pos || !idx || !occu || !loss_out || !Ssum || !cover) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
-    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B, 0};
     CK(cudaMemsetAsync(Ssum, 0, sizeof(double) * c->M, st));
     CK(cudaMemsetAsync(cover, 0, (size_t)c->Noy * c->Nox * 4, st));
     k_cover<<<dim3((c->N * c->N + 1023) / 1024, B), 256, 0, st>>>(d, crop_pos, idx, cover);
@@ -391,7 +392,7 @@ int ptyb200_sparse_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const 
                         const int32_t* cover, float* g_objp, ptyb200_stream s) {
     if (!c || !lc || !objp || !crop_pos || !idx || !occu || !Ssum || !upstream || !cover || !g_objp) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
-    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B};
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B, 0};
     size_t n = (size_t)c->M * c->Z * c->Noy * c->Nox;
     k_sparse_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, objp, occu, Ssum, upstream, cover, g_objp);
     CKL();

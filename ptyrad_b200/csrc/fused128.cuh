@@ -366,10 +366,10 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     const Geo g;
     const Dims& d = a.f.d;
     const int p = blockIdx.x, m = blockIdx.y, b = blockIdx.z;
-    const int64_t n0 = a.f.idx[b];
-    const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
+    int cy, cx;
+    roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
     const size_t plane = (size_t)d.Noy * d.Nox;
-    const float4* Oplane = a.Opack + (size_t)m * d.Z * plane;
+    const float4* Oplane = a.Opack + (size_t)obj_mode(d, b, m) * d.Z * plane;
     l2_prefetch_roi(Oplane, cy, cx, d.Nox);
     load_tables(s, a, b);
     __syncthreads();
@@ -555,8 +555,9 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         if (ACC) { b = unit / d.M; m = unit % d.M; p_lo = 0; p_hi = d.P; }
         else { p_lo = unit % d.P; p_hi = p_lo + 1; const int bm = unit / d.P; b = bm / d.M; m = bm % d.M; }
         const int64_t n0 = a.f.idx[b];
-        const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
-        const float4* Oplane = a.Opack + (size_t)m * d.Z * plane;
+        int cy, cx;
+        roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
+        const float4* Oplane = a.Opack + (size_t)obj_mode(d, b, m) * d.Z * plane;
         __syncthreads();
         load_tables(s, a, b);
         // dL/dI in layout F, scaled 2 occu_m G~ / N^2, is gathered from global memory in the (single) start phase per mode
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                 {
                     const float4* st = stash_t + (size_t)zn * (TILE / 2) + stash_index(g.t, 0);
                     const float4* Oz = Oplane + (size_t)zn * plane + roi0;
-                    float4* gOz = a.gOpack + ((size_t)m * d.Z + zn) * plane + roi0;
+                    float4* gOz = a.gOpack + ((size_t)obj_mode(d, b, m) * d.Z + zn) * plane + roi0;
                     float4* ac = ACC ? accb + (size_t)zn * (TILE / 2) : nullptr;
                     if (ACC) {
                         switch (mode) {
@@ -711,7 +712,7 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     Scratch s;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base + o; };
-    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     const bool acc_mode = (c.reserved[0] & 1) != 0;
     s.HF = (float2*)take((size_t)TILE * 8);
     s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
@@ -748,7 +749,7 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, f, sc, f.phis);
     const float inv = 1.0f / (128.0f * 128.0f);
-    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     k_obj_polar_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, sc.Opack, c.Noy, c.Nox, obj);
     F128_CK(cudaGetLastError()); ++*launches;
     k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
@@ -777,7 +778,7 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
     const bool acc_mode = (c.reserved[0] & 1) != 0;     // experimental: accumulate over probe modes before scattering
     a.units = acc_mode ? B * c.M : B * c.M * c.P;
     a.direct_red = acc_mode ? 0 : 1;
-    const size_t obj = (size_t)c.M * c.Z * c.Noy * c.Nox;
+    const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     if (a.need_obj) F128_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
     if (a.need_probe) {
         if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));

@@ -26,7 +26,15 @@ constexpr int NT = 256;    // threads per CTA
 
 struct Dims {
     int N, P, M, Z, Noy, Nox, B;
+    int patch;      // 1: the "object" arrays are per-sample patches (B,M,Z,N,N) (pre-blurred ROIs); crop offsets are zero
 };
+// object plane index and ROI offset of sample b, object mode m
+__device__ __forceinline__ int obj_mode(const Dims& d, int b, int m) { return d.patch ? b * d.M + m : m; }
+__device__ __forceinline__ void roi_origin(const Dims& d, const int32_t* crop, const int64_t* idx, int b, int& cy, int& cx) {
+    if (d.patch) { cy = 0; cx = 0; return; }
+    const int64_t n0 = idx[b];
+    cy = crop[2 * n0]; cx = crop[2 * n0 + 1];
+}
 
 __device__ __forceinline__ int shift_idx(int k, int N) {  // (k + N/2) mod N  (fftshift == ifftshift for even N)
     int h = N >> 1;
@@ -294,9 +302,9 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdA
     static_assert(ROWS * N2 <= NT && ROWS * N1 <= NT, "one fused work item per thread");
     const Dims& d = a.d;
     const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
-    const int64_t n0 = a.idx[b];
-    const int cy = a.crop[2 * n0], cx = a.crop[2 * n0 + 1];
-    const float2* Oz = a.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
+    int cy, cx;
+    roi_origin(d, a.crop, a.idx, b, cy, cx);
+    const float2* Oz = a.O + ((size_t)obj_mode(d, b, m) * d.Z + z) * d.Noy * d.Nox;
     const bool item = threadIdx.x < ROWS * N2;
     const int r = threadIdx.x / N2, j = threadIdx.x % N2;
     float2 Oreg[N1];
@@ -343,17 +351,6 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdA
         float2* dst = (last ? a.farT : a.G1) + (tile + m) * N * N;
         Slab<F>::tr([&](int, int rr, int q) { dst[(size_t)q * N + y0 + rr] = slab[rr * F::RS + F::apos(q)]; });
         __syncthreads();
-    }
-}
-
-// propagator value at (ky, kx) for this sample, natural ownership registers
-template <class F> __device__ __forceinline__ void load_prop(const FwdArgs& a, int b, int kx0, float2 (&Hreg)[Slab<F>::EPT]) {
-    constexpr int N = F::N;
-    Slab<F>::nat([&](int i, int r, int ky) { Hreg[i] = a.HT[(size_t)(kx0 + r) * N + ky]; });
-    if (a.tvec) {
-        const float2* ey = a.tvec + ((size_t)b * 2 + 0) * N;
-        const float2* ex = a.tvec + ((size_t)b * 2 + 1) * N;
-        Slab<F>::nat([&](int i, int r, int ky) { Hreg[i] = cmul(Hreg[i], cmul(ey[ky], ex[kx0 + r])); });
     }
 }
 
@@ -492,9 +489,9 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
     constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
     const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
-    const int64_t n0 = a.f.idx[b];
-    const int cy = a.f.crop[2 * n0], cx = a.f.crop[2 * n0 + 1];
-    const float2* Oz = a.f.O + ((size_t)m * d.Z + z) * d.Noy * d.Nox;
+    int cy, cx;
+    roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
+    const float2* Oz = a.f.O + ((size_t)obj_mode(d, b, m) * d.Z + z) * d.Noy * d.Nox;
     const bool item = threadIdx.x < ROWS * N2;
     const int r = threadIdx.x / N2, j = threadIdx.x % N2;
     const size_t roi = (size_t)(cy + y0 + r) * d.Nox + cx + j;
@@ -545,7 +542,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
         }
     }
     if (a.need_obj && item) {
-        float2* gOz = a.gO + ((size_t)m * d.Z + z) * d.Noy * d.Nox + roi;
+        float2* gOz = a.gO + ((size_t)obj_mode(d, b, m) * d.Z + z) * d.Noy * d.Nox + roi;
 #pragma unroll
         for (int k = 0; k < N1; ++k) red_add_f2(gOz + N2 * k, accO[k]);
     }

@@ -210,12 +210,15 @@ class PtychoAD(nn.Module):
             return 0
         return 1 if self.opt_obj_tilts.shape[0] == 1 else 2
 
-    def _cfg(self, stash_fourier):
+    def _cfg(self, stash_fourier, patch_mode=False):
         M, Z, Noy, Nox = self.opt_obja.shape
         P, N = self.opt_probe.shape[0], self.opt_probe.shape[1]
+        if patch_mode:          # the "object" handed to the kernels is the (pre-blurred) per-sample ROI stack (B,M,Z,N,N)
+            Noy = Nox = N
         cfg = engine.make_cfg(N, P, M, Z, Noy, Nox, self.crop_pos.shape[0], self.shift_probes, self._tilt_mode(), stash_fourier,
                               self._dx_host, self._lambd_host, 1e-10, self.kernel_path)
         cfg.reserved[0] = int(self.kernel_flags)
+        cfg.reserved[1] = 1 if patch_mode else 0
         return cfg
 
     def _roi_tensor(self, idx):
@@ -231,9 +234,11 @@ class PtychoAD(nn.Module):
         return self._roi_tensor(self._index_tensor(indices))
 
     def get_obj_patches(self, indices):
-        if self.obj_preblur_std is not None and self.obj_preblur_std != 0:
-            raise NotImplementedError("obj_preblur_std is not supported by the CUDA path yet (SURVEY 8f, rank 2)")
-        return self.get_obj_ROI(indices)
+        """ROI tensor, Gaussian pre-blurred (5x5, reflect) on amplitude and phase if obj_preblur_std is set (models.py:267-284)."""
+        patches = self.get_obj_ROI(indices)
+        if self.obj_preblur_std is None or self.obj_preblur_std == 0:
+            return patches
+        return gaussian_blur5(patches.permute(5, 0, 1, 2, 3, 4), self.obj_preblur_std).permute(1, 2, 3, 4, 5, 0)
 
     def get_probes(self, indices):
         probe = self.get_complex_probe_view()
@@ -298,17 +303,24 @@ class PtychoAD(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def forward(self, indices):
         """dp_fwd (B,N,N) float32 for the scan indices of one batch (reference models.py:422-436)."""
-        if self.obj_preblur_std is not None and self.obj_preblur_std != 0:
-            raise NotImplementedError("obj_preblur_std is not supported by the CUDA path yet (SURVEY 8f, rank 2)")
         idx = self._index_tensor(indices)
         need_prop = (self.opt_obj_tilts.requires_grad and self.tilt_obj) or (self.opt_slice_thickness.requires_grad and self.change_thickness)
-        cfg = self._cfg(stash_fourier=bool(need_prop) and torch.is_grad_enabled())
+        preblur = self.obj_preblur_std is not None and self.obj_preblur_std != 0
+        cfg = self._cfg(stash_fourier=bool(need_prop) and torch.is_grad_enabled(), patch_mode=preblur)
         st = dict(cfg=cfg, idx=idx, crop_pos=self.crop_pos, H=self.H, occu=self.omode_occu, change_thickness=self.change_thickness)
-        dp = engine.MultisliceFunction.apply(self.opt_obja, self.opt_objp, self.opt_obj_tilts, self.opt_slice_thickness,
+        if preblur:
+            # pre-blurred ROIs: gather + blur are tensor ops (as in the reference), the multislice kernels take the per-sample
+            # patch stacks as their "object" (patch mode) and hand the patch gradients back to autograd
+            patches = self.get_obj_patches(idx)
+            obja, objp = patches[..., 0].contiguous(), patches[..., 1].contiguous()
+            self._current_object_patches = patches
+        else:
+            obja, objp = self.opt_obja, self.opt_objp
+            self._current_object_patches = LazyPatches(self, idx)
+        dp = engine.MultisliceFunction.apply(obja, objp, self.opt_obj_tilts, self.opt_slice_thickness,
                                              self.opt_probe, self.opt_probe_pos_shifts, st)
         if self.detector_blur_std is not None and self.detector_blur_std != 0:
             dp = gaussian_blur5(dp, self.detector_blur_std)
-        self._current_object_patches = LazyPatches(self, idx)
         return dp
 
 

@@ -66,7 +66,7 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
     else:
         optimizer.zero_grad()
     dp = model(indices)
-    idx = model._current_object_patches.idx
+    idx = model._index_tensor(indices)
     if measurements is not None:
         meas = measurements
     elif model.meas_padded is None and model.meas_scale_factors is None:
@@ -227,7 +227,7 @@ def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint
             per_batch.append(g(mine).clone())
             continue
         dp = model(mine)
-        idx = model._current_object_patches.idx
+        idx = model._index_tensor(mine)
         if model.meas_padded is None and model.meas_scale_factors is None:
             meas = MeasurementView(model.measurements, idx)
         else:

@@ -393,3 +393,42 @@ def test_recon_step_iterations_with_start_iter_and_constraint():
     assert rel(model.opt_objp.detach().cpu().numpy(), om.objp.detach().numpy()) < 1e-3
     p0 = np.stack([iv["probe"].real, iv["probe"].imag], -1)
     assert rel(model.opt_probe.detach().cpu().numpy() - p0, om.probe.detach().numpy() - p0) < 5e-2
+
+
+@pytest.mark.parametrize("cfg_name", ["T64", "T128"])
+def test_object_preblur_and_detector_blur(cfg_name):
+    """obj_preblur_std (5x5 Gaussian on the amplitude/phase ROIs, models.py:275-284) through the kernels' patch mode and
+    detector_blur_std (models.py:379-380), against the oracle with the same blurs (autograd carries the gradient through)."""
+    import copy
+    from oracle.ptycho_torch import OracleModel, loss_terms, _gauss5
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    iv, mp, lp = make_inputs(cfg_name, seed=29)
+    mp = copy.deepcopy(mp)
+    mp["obj_preblur_std"], mp["detector_blur_std"] = 1.0, 0.8
+    idx = np.arange(min(6, CONFIGS[cfg_name].scan ** 2))
+    model = PtychoAD(iv, mp, device="cuda", verbose=False)
+    loss_fn = CombinedLoss(lp, device="cuda")
+    dp = model(idx)
+    total, terms = loss_fn(dp, model.get_measurements(idx), model._current_object_patches, model.omode_occu)
+    total.backward()
+    om = OracleModel(iv, mp, torch.float64)
+    a, p = om.patches(idx)
+    a, p = _gauss5(a, 1.0), _gauss5(p, 1.0)
+    O = torch.polar(a, p).to(om.cd)
+    psi = om.probes(idx)[:, :, None]
+    Hn = om.propagators(idx)[:, None, None]
+    Z = O.shape[2]
+    for z in range(Z - 1):
+        psi = torch.fft.ifft2(Hn * torch.fft.fft2(psi * O[:, None, :, z]))
+    psi = psi * O[:, None, :, Z - 1]
+    far = torch.fft.fftshift(torch.fft.fft2(psi, norm="ortho"), dim=(-2, -1))
+    odp = (far.abs().square() * om.occu[:, None, None]).sum(dim=(1, 2)) + 1e-10
+    odp = _gauss5(odp, 0.8)
+    otot, oterms = loss_terms(odp, om.meas[torch.as_tensor(idx)], p, om.occu, lp, obja_patches=a)
+    otot.backward()
+    assert rel(dp.detach().cpu().numpy(), odp.detach().numpy()) < TOL_DP
+    assert abs(float(total.detach()) - float(otot.detach())) / abs(float(otot.detach())) < TOL_LOSS
+    for k, t in om.params().items():
+        if om.lr[k] != 0:
+            assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), t.grad.numpy()) < TOL_G[k], k

@@ -124,10 +124,6 @@ def test_validation_rejects_bad_inputs():
     bad = dict(iv); bad["probe"] = iv["probe"][:, :30, :30]
     with pytest.raises(ValueError):
         PtychoAD(bad, mp, device="cpu", verbose=False)
-    mp2 = dict(mp, obj_preblur_std=1.0)
-    m = PtychoAD(iv, mp2, device="cpu", verbose=False)
-    with pytest.raises(NotImplementedError):
-        m(np.array([0]))
 
 
 def test_loss_cfg_and_shard_indices():
