@@ -347,6 +347,27 @@ def main():
         "losses_last_step": [float(x) for x in last.cpu()],
     }
     if world == 1 and not args.no_cpu_baseline:
+        # like-for-like GPU baseline: the same torch-eager restatement of the reference (cuFFT + ATen + autograd + Adam) on this
+        # B200, full batch, resident inputs (SURVEY 8d asks for it next to the CPU number)
+        try:
+            from oracle.ptycho_torch import OracleTrainer
+            del step_fn
+            torch.cuda.empty_cache()
+            tg = OracleTrainer(iv, mp, lp, device=dev)
+            for s_ in range(3):
+                tg.step(my[s_ % len(my)])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ng = 10
+            for s_ in range(ng):
+                tg.step(my[s_ % len(my)])
+            torch.cuda.synchronize()
+            dtg = (time.perf_counter() - t0) / ng
+            out["torch_cuda_eager_baseline"] = {"value": B / dtg, "unit": UNIT, "ms_per_step": dtg * 1e3, "kind": "port",
+                                                "sample": f"{ng} steps of the full {B}-pattern batch, torch eager on the same GPU"}
+            del tg
+        except Exception as e:           # never let the extra baseline break the contract line
+            out["torch_cuda_eager_baseline"] = {"error": str(e)[:200]}
         b_cpu = min(B, 64 if cfg.N <= 128 else 8)
         rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, 6, 1, threads)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",

@@ -41,9 +41,10 @@ class OracleModel:
     """Holds the six optimisable tensors and the fixed buffers exactly as the reference model does
     (models.py:99-122), in `dtype` (float32 = like-for-like, float64 = arbiter)."""
 
-    def __init__(self, iv: dict, model_params: dict, dtype=torch.float32):
+    def __init__(self, iv: dict, model_params: dict, dtype=torch.float32, device="cpu"):
         rd, cd = dtype, _cdtype(dtype)
         self.rd, self.cd = rd, cd
+        self.device = torch.device(device)
         obj = torch.as_tensor(np.asarray(iv["obj"]))
         # amplitude / phase are taken from the complex64 object in float32 first (models.py:99-100)
         self.obja = torch.abs(obj).to(torch.float32).to(rd).requires_grad_(True)
@@ -66,17 +67,22 @@ class OracleModel:
         self.change_thickness = bool(lr["slice_thickness"] != 0)
         self.change_tilt = bool(lr["obj_tilts"] != 0)
         self.N = int(pr.shape[-1])
+        if self.device.type != "cpu":          # same restatement on another device (bench.py: torch-eager GPU baseline)
+            for name in ("obja", "objp", "tilts", "dz", "probe", "shifts"):
+                setattr(self, name, getattr(self, name).detach().to(self.device).requires_grad_(True))
+            for name in ("occu", "H", "meas", "crop", "dx", "lambd"):
+                setattr(self, name, getattr(self, name).to(self.device))
         self._grids()
 
     # --- grids (models.py:152-185, 210-223) ------------------------------------------------
     def _grids(self):
         N, rd = self.N, self.rd
-        g = (torch.arange(-(N // 2), N - N // 2) + 0.5).to(rd) / N
+        g = (torch.arange(-(N // 2), N - N // 2, device=self.device) + 0.5).to(rd) / N
         k1 = torch.fft.ifftshift(2 * math.pi * g / self.dx)
         self.Ky, self.Kx = torch.meshgrid(k1, k1, indexing="ij")
         self.k0 = 2 * math.pi / self.lambd
         self.Kz = torch.sqrt(self.k0 ** 2 - self.Kx ** 2 - self.Ky ** 2)
-        ar = torch.arange(N, dtype=torch.int32)
+        ar = torch.arange(N, dtype=torch.int32, device=self.device)
         self.ry, self.rx = torch.meshgrid(ar, ar, indexing="ij")
         self.sy = self.ry.to(rd) / N        # shift grid: j/N, j = 0..N-1 (not centred)
         self.sx = self.rx.to(rd) / N
@@ -90,9 +96,14 @@ class OracleModel:
                     probe=self.probe, probe_pos_shifts=self.shifts)
 
     # --- pieces ---------------------------------------------------------------------------
+    def _idx(self, idx):
+        if torch.is_tensor(idx):
+            return idx.to(device=self.device, dtype=torch.int64)
+        return torch.as_tensor(np.asarray(idx), dtype=torch.int64, device=self.device)
+
     def roi_index(self, idx):
         """int32 ROI addresses: gy = y + crop[n,0], gx = x + crop[n,1]  (models.py:261-262)."""
-        idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+        idx = self._idx(idx)
         gy = self.ry[None] + self.crop[idx, None, None, 0]
         gx = self.rx[None] + self.crop[idx, None, None, 1]
         return gy.long(), gx.long()
@@ -105,7 +116,7 @@ class OracleModel:
 
     def probes(self, idx):
         pc = torch.view_as_complex(self.probe)
-        idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+        idx = self._idx(idx)
         if not self.shift_probes:
             return pc[None].expand(len(idx), *pc.shape)
         s = self.shifts[idx]
@@ -114,7 +125,7 @@ class OracleModel:
         return torch.fft.ifft2(torch.fft.ifftshift(spec[None] * ramp, dim=(-2, -1)))
 
     def propagators(self, idx):
-        idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+        idx = self._idx(idx)
         glob = self.tilts.shape[0] == 1
         t = self.tilts if glob else self.tilts[idx]
         ty, tx = t[:, 0, None, None] / 1e3, t[:, 1, None, None] / 1e3
@@ -146,7 +157,7 @@ class OracleModel:
 # --- losses (losses.py:36-155) --------------------------------------------------------------
 
 def loss_terms(dp, meas, objp_patches, occu, lp: dict, obja_patches=None):
-    zero = lambda: torch.zeros((), dtype=dp.dtype)
+    zero = lambda: torch.zeros((), dtype=dp.dtype, device=dp.device)
     out = []
     s = lp["loss_single"]
     if s["state"]:
@@ -255,10 +266,10 @@ class OracleTrainer:
     """zero_grad -> forward -> measurements -> loss -> backward -> Adam.step on the CPU, the same
     sequence as the non-LBFGS branch of recon_step (reconstruction.py:738-772)."""
 
-    def __init__(self, iv, model_params, loss_params, threads: Optional[int] = None):
+    def __init__(self, iv, model_params, loss_params, threads: Optional[int] = None, device="cpu"):
         if threads:
             torch.set_num_threads(threads)
-        self.m = OracleModel(iv, model_params, torch.float32)
+        self.m = OracleModel(iv, model_params, torch.float32, device=device)
         self.lp = loss_params
         groups = [dict(params=[t], lr=self.m.lr[k]) for k, t in self.m.params().items() if self.m.lr[k] != 0]
         for k, t in self.m.params().items():
@@ -268,8 +279,8 @@ class OracleTrainer:
     def step(self, idx):
         self.opt.zero_grad()
         dp, (a, p) = self.m.forward(idx)
-        meas = self.m.meas[torch.as_tensor(np.asarray(idx), dtype=torch.int64)]
+        meas = self.m.meas[self.m._idx(idx)]
         total, terms = loss_terms(dp, meas, p, self.m.occu, self.lp, obja_patches=a)
         total.backward()
         self.opt.step()
-        return float(total.detach())
+        return float(total.detach()) if self.m.device.type == "cpu" else total.detach()

@@ -326,12 +326,14 @@ class PtychoAD(nn.Module):
 
 def gaussian_blur5(x, sigma):
     """5x5 Gaussian, reflect padding, on the last two dims (what torchvision's gaussian_blur(kernel_size=5) computes;
-    reference models.py:379-380).  Off the default path (detector_blur_std is None in the benchmark configs)."""
+    reference models.py:275-284,379-380).  Written as separable shifted sums rather than conv2d: cuDNN convolutions default to
+    TF32 (1e-3 errors in the gradient), elementwise float32 arithmetic does not.  Off the default path."""
     t = torch.arange(-2, 3, dtype=x.dtype, device=x.device)
     k = torch.exp(-0.5 * (t / sigma) ** 2)
     k = k / k.sum()
     sh = x.shape
-    y = torch.nn.functional.pad(x.reshape(-1, 1, sh[-2], sh[-1]), (2, 2, 2, 2), mode="reflect")
-    y = torch.nn.functional.conv2d(y, k.view(1, 1, 1, 5))
-    y = torch.nn.functional.conv2d(y, k.view(1, 1, 5, 1))
+    H, W = sh[-2], sh[-1]
+    y = torch.nn.functional.pad(x.reshape(-1, 1, H, W), (2, 2, 2, 2), mode="reflect")
+    y = sum(k[i] * y[..., :, i:i + W] for i in range(5))
+    y = sum(k[i] * y[..., i:i + H, :] for i in range(5))
     return y.reshape(sh)

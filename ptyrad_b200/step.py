@@ -111,6 +111,7 @@ class GraphedStep:
             N = model.opt_probe.shape[1]
             self.meas = torch.zeros((self.B, N, N), dtype=torch.float32, device=dev)
             mv = MeasurementView(self.meas, torch.arange(self.B, device=dev))
+            self._mv = mv            # the captured graph reads these buffers by address: keep them alive with the graph
             # double buffering for `prefetch`: the next batch is copied host -> device on a side stream while this one runs
             self._next_meas = torch.zeros_like(self.meas)
             self._next_idx = torch.zeros_like(self.idx)

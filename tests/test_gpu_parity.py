@@ -432,3 +432,37 @@ def test_object_preblur_and_detector_blur(cfg_name):
     for k, t in om.params().items():
         if om.lr[k] != 0:
             assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), t.grad.numpy()) < TOL_G[k], k
+
+
+def test_graphed_step_with_streamed_measurements_and_prefetch():
+    """GraphedStep(stream_measurements=True): patterns + indices arrive from pinned host memory (double-buffered prefetch);
+    same losses as the eager step that reads the resident measurement array."""
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch
+    from ptyrad_b200.synthetic import make_inputs
+    iv, mp, lp = make_inputs("T64", seed=37)
+    batches = [np.arange(0, 8), np.arange(8, 16), np.arange(16, 24), np.arange(3, 11)]
+    res = []
+    for streamed in (False, True):
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        opt = FusedAdam(model.optimizable_params)
+        arena = GradArena(model)
+        ls = []
+        if not streamed:
+            for b in batches:
+                ls.append(recon_batch(model, loss_fn, opt, b, arena).clone())
+        else:
+            g = GraphedStep(model, loss_fn, opt, arena, 8, stream_measurements=True)
+            hm = [torch.from_numpy(np.ascontiguousarray(iv["measurements"][b])).pin_memory() for b in batches]
+            hi = [torch.from_numpy(b.astype(np.int64)).pin_memory() for b in batches]
+            g.prefetch(hi[0], hm[0])
+            for i in range(len(batches)):
+                out = g.step_prefetched()
+                if i + 1 < len(batches):
+                    g.prefetch(hi[i + 1], hm[i + 1])
+                ls.append(out.clone())
+        torch.cuda.synchronize()
+        res.append(torch.stack(ls).cpu().numpy())
+    np.testing.assert_allclose(res[1], res[0], rtol=2e-5, atol=1e-7)

@@ -186,3 +186,15 @@ def test_gradient_exchange_world2_gloo():
     for rank, err, frozen_ok in res:
         assert frozen_ok
         assert all(v < 1e-6 for v in err.values()), (rank, err)
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under ptyrad_b200/ may import it (a product path through the oracle would void
+    every parity claim)."""
+    pkg = os.path.join(ROOT, "ptyrad_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "adjoint_np" not in txt and "ptycho_torch" not in txt, f
