@@ -86,7 +86,9 @@ class MultisliceFunction(torch.autograd.Function):
             C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(st["crop_pos"]), ptr(probe), ptr(shifts_c), ptr(Hbase),
             ptr(tilts_c), ptr(dz), ptr(st["occu"]), ptr(dp), ptr(ws), _stream()))
         ctx.st, ctx.ws, ctx.Hbase = st, ws, Hbase
-        ctx.save_for_backward(obja, objp, tilts, dz, probe, shifts)
+        # the contiguous tensors the kernels actually read (constraints may leave strided .data behind)
+        ctx.save_for_backward(obja, objp, tilts_c if tilts_c is not None else tilts, dz, probe,
+                              shifts_c if shifts_c is not None else shifts)
         return dp
 
     @staticmethod
