@@ -14,8 +14,8 @@
 //   inverse (F -> R): the same stages backwards with conjugate twiddles.
 //
 // So a 2-D FFT costs two shared-memory round trips (4 x 128 KB of smem traffic) instead of the eight of a row/column
-// slab FFT, the DFT32 twiddles are compile-time immediates, every global access of layout R is a 256-byte coalesced
-// row segment (ROI gather, stash, gradient scatter), and layout-F side tables (propagator, probe spectrum, dL/dI)
+// slab FFT, the DFT32 twiddles are compile-time immediates, every global access of layout R is a coalesced row
+// segment (ROI gather, gradient scatter; 512 B per warp with the packed layouts below), and layout-F side tables (propagator, probe spectrum, dL/dI)
 // are pre-permuted so that they are read thread-privately and coalesced.  tools/proto_fused128.py is the NumPy
 // model of this index algebra.
 //
@@ -41,8 +41,7 @@ constexpr int FT = 512;                 // threads per CTA
 constexpr int CH = 528;                 // elements per chunk region (512 used by E1, 16 rows x 33 by E2)
 constexpr int E_ELEMS = 32 * CH;        // 16896 float2 = 135168 B
 constexpr int TILE = FN * FN;           // 16384
-constexpr size_t SMEM_BYTES = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + sizeof(float) * TILE + 128 * sizeof(float);
-// the forward does not use the dL/dI tile: a smaller carve-out leaves ~88 KB of L1
+// exchange buffer + twiddle/ramp tables + reduction scratch (+ 16 per-warp 4 KB TMA staging blocks where used)
 constexpr size_t SMEM_BYTES_BWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + (F128_TMA_RED ? 16 * 4096 : 0);
 constexpr size_t SMEM_BYTES_FWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + 16 * 4096;   // + stash staging
 
