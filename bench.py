@@ -146,7 +146,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64))
+        iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64 and cfg.N <= 128))
         b_cpu = min(B, 64 if cfg.N <= 128 else 8)
         rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), threads)
         sample = f"{b_cpu} patterns/step of the {cfg.name} workload (same model, reduced batch), median step time"
@@ -176,7 +176,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64))
+    iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64 and cfg.N <= 128))
     Ntot = iv["crop_pos"].shape[0]
     model = PtychoAD(iv, mp, device=dev, verbose=False)
     model.kernel_path = {"auto": _lib.PATH_AUTO, "general": _lib.PATH_GENERAL, "fused": _lib.PATH_FUSED}[args.path]

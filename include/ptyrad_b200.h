@@ -49,7 +49,10 @@ typedef struct ptyb200_cfg {
     int32_t path;          /* PTYB200_PATH_* */
     int32_t reserved[5];   /* [0] bit 0: adjoint accumulates over probe modes before scattering (experimental);
                               [1] bit 0: PATCH MODE -- obja/objp (and their gradients) are per-sample ROI stacks (B,M,Z,N,N),
-                                  e.g. pre-blurred patches (models.py:275-284); needs Noy == Nox == N, crop_pos is ignored */
+                                  e.g. pre-blurred patches (models.py:275-284); needs Noy == Nox == N, crop_pos is ignored;
+                              [2] general path: samples per chunk (the slice sequence runs chunk by chunk so that the pass buffers
+                                  stay L2-resident), 0 = heuristic;  [3] general path: probe modes per CTA, 0 = heuristic.
+                                  [2] and [3] change the workspace size: use the same cfg for ptyb200_workspace_bytes */
     float   dx;            /* real-space pixel size (propagator k-grid, models.py:164-171) */
     float   lambd;         /* wavelength (Kz, models.py:222-223) */
     float   eps;           /* added to the intensities after the mode sum (forward.py:79); reference: 1e-10 */

@@ -5,6 +5,7 @@
 #include "fused128.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -58,6 +59,32 @@ struct Workspace {
     size_t total;
 };
 
+bool supported_N(int N) { return N == 16 || N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192 || N == 256; }
+bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && fused128::covers(c); }
+
+// General path: optionally the slice sequence runs on CHUNKS of the batch (pass buffers G1/G2 sized for one chunk, so that they can
+// stay L2-resident from the kernel that writes a tile to the kernel that reads it) with the probe modes split into per-CTA groups
+// (to keep the launches wide when the chunk is small).  Measured on B200 (profiles/r01/README.md, "chunked general path"): the
+// per-slice kernels are bound by shared-memory bandwidth and issue, not by HBM, so chunking only adds launch tails (C4: 74 ms
+// unchunked, 98-137 ms chunked) -- the default is therefore ONE chunk and all probe modes per CTA.  cfg.reserved[2] / [3] (or the
+// environment variables PTYB200_GEN_CHUNK / PTYB200_GEN_PG, for sweeps) select a cut; tests exercise ragged cuts.
+struct GenPlan { int chunk, pg, groups; };
+GenPlan gen_plan(const ptyb200_cfg& c, int B) {
+    GenPlan g;
+    int chunk = B, pg = c.P;
+    if (const char* e = getenv("PTYB200_GEN_CHUNK")) { if (atoi(e) > 0) chunk = atoi(e); }
+    if (c.reserved[2] > 0) chunk = c.reserved[2];
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    if (const char* e = getenv("PTYB200_GEN_PG")) { if (atoi(e) > 0) pg = atoi(e); }
+    if (c.reserved[3] > 0) pg = c.reserved[3];
+    if (pg < 1) pg = 1;
+    if (pg > c.P) pg = c.P;
+    g.chunk = chunk; g.pg = pg; g.groups = (c.P + pg - 1) / pg;
+    return g;
+}
+constexpr int kMinCtas = 296;      // 148 SMs x 2 resident CTAs
+
 Workspace carve(const ptyb200_cfg& c, int B, void* base) {
     Workspace w;
     size_t off = 0;
@@ -74,15 +101,14 @@ Workspace carve(const ptyb200_cfg& c, int B, void* base) {
     w.gprop = (float*)take((size_t)B * 3 * 4);
     w.stash = (float2*)take(tiles * c.Z * NN * 8);
     w.phis = (float2*)take(c.stash_fourier ? tiles * (c.Z > 1 ? c.Z - 1 : 0) * NN * 8 : 0);
-    w.G1 = (float2*)take(tiles * NN * 8);
-    w.G2 = (float2*)take(tiles * NN * 8);
-    w.farT = (float2*)take(tiles * NN * 8);
+    const size_t ctiles = use_fused(c) ? 0 : (size_t)gen_plan(c, B).chunk * c.P * c.M;    // pass buffers: one chunk of the batch
+    w.G1 = (float2*)take(ctiles * NN * 8);
+    w.G2 = (float2*)take(ctiles * NN * 8);
+    w.farT = (float2*)take(use_fused(c) ? 0 : tiles * NN * 8);
     w.fused = take(fused128::scratch_bytes(c, B));
     w.total = off;
     return w;
 }
-
-bool supported_N(int N) { return N == 16 || N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192 || N == 256; }
 
 int check_cfg(const ptyb200_cfg* c, int B) {
     if (!c) return fail_msg("cfg is NULL");
@@ -134,7 +160,7 @@ template <class F> int fft2_tiles(const float2* in, float2* tmp, float2* out, in
 FwdArgs make_fwd_args(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const int32_t* crop, const float* probe,
                       const float* occu, float* dp) {
     FwdArgs a;
-    a.d = Dims{c.N, c.P, c.M, c.Z, c.Noy, c.Nox, B, (c.reserved[1] & 1)};
+    a.d = Dims{c.N, c.P, c.M, c.Z, c.Noy, c.Nox, B, (c.reserved[1] & 1), 0, c.P};
     a.idx = idx; a.crop = crop; a.O = w.O; a.probe = (const float2*)probe; a.PhatT = w.PhatT; a.HT = w.HT;
     a.wvec = c.shift_probes ? w.wvec : nullptr;
     a.tvec = c.tilt_mode ? w.tvec : nullptr;
@@ -142,8 +168,6 @@ FwdArgs make_fwd_args(const ptyb200_cfg& c, int B, const Workspace& w, const int
     a.G1 = w.G1; a.G2 = w.G2; a.farT = w.farT; a.dp = dp; a.eps = c.eps;
     return a;
 }
-
-bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && fused128::covers(c); }
 
 // shared setup: complex object, transposed propagator, probe spectrum, per-sample ramps
 template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const float* obja,
@@ -173,42 +197,58 @@ template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace
 
 template <class F> int forward_general(const ptyb200_cfg& c, int B, const Workspace& w, FwdArgs a, cudaStream_t st) {
     const int nb = c.N / ROWS;
-    if (c.shift_probes) LAUNCH((k_init_shift<F>), dim3(nb, B), st, a);
-    for (int z = 0; z < c.Z; ++z) {
-        const int src_mode = (z == 0 && !c.shift_probes) ? 1 : 0;
-        LAUNCH((k_fwd_da<F>), dim3(nb, c.M, B), st, a, z, src_mode, z == c.Z - 1 ? 1 : 0);
-        if (z < c.Z - 1) LAUNCH((k_fwd_bc<F>), dim3(nb, c.M, B), st, a, z);
+    const GenPlan gp = gen_plan(c, B);
+    a.d.pg = gp.pg;
+    for (int b0 = 0; b0 < B; b0 += gp.chunk) {            // the whole slice sequence per chunk: G1/G2 never leave L2
+        const int nbc = B - b0 < gp.chunk ? B - b0 : gp.chunk;
+        a.d.b0 = b0;
+        const dim3 grid(nb, c.M * gp.groups, nbc);
+        if (c.shift_probes) LAUNCH((k_init_shift<F>), dim3(nb, gp.groups, nbc), st, a);
+        for (int z = 0; z < c.Z; ++z) {
+            const int src_mode = (z == 0 && !c.shift_probes) ? 1 : 0;
+            LAUNCH((k_fwd_da<F>), grid, st, a, z, src_mode, z == c.Z - 1 ? 1 : 0);
+            if (z < c.Z - 1) LAUNCH((k_fwd_bc<F>), grid, st, a, z);
+        }
     }
-    LAUNCH((k_fwd_final<F>), dim3(nb, B), st, a);
+    a.d.b0 = 0;
+    LAUNCH((k_fwd_final<F>), dim3(nb, B), st, a);        // far-field tiles of the whole batch
     return 0;
 }
 
 template <class F> int backward_general(const ptyb200_cfg& c, int B, const Workspace& w, BwdArgs a, float* g_probe, cudaStream_t st) {
     const int nb = c.N / ROWS;
     const bool want_p = a.need_probe || a.need_shift;
-    LAUNCH((k_bwd_start<F>), dim3(nb, c.M, B), st, a);
-    for (int z = c.Z - 1; z >= 0; --z) {
-        int out_mode = 0;
-        if (z == 0) out_mode = want_p ? (c.shift_probes ? 0 : 1) : 2;
-        LAUNCH((k_bwd_da<F>), dim3(nb, c.M, B), st, a, z, out_mode);
-        if (z > 0) LAUNCH((k_bwd_bc<F>), dim3(nb, c.M, B), st, a, z);
-    }
-    if (want_p) {
-        if (c.shift_probes) {
-            int per = nb * c.P;
-            int nchunk = (296 + per - 1) / per;
-            if (nchunk > B) nchunk = B;
-            if (nchunk < 1) nchunk = 1;
-            int bchunk = (B + nchunk - 1) / nchunk;
-            nchunk = (B + bchunk - 1) / bchunk;
-            LAUNCH((k_bwd_probe<F>), dim3(nb, c.P, nchunk), st, a, bchunk);
-            if (a.need_probe)
-                if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c.P, +1, st)) return r;
-        } else if (a.need_probe) {
-            k_bwd_probe_noshift<<<dim3((c.N * c.N + 255) / 256, c.P), 256, 0, st>>>(a.f.d, w.G1, (float2*)g_probe);
-            CKL();
+    const GenPlan gp = gen_plan(c, B);
+    a.f.d.pg = gp.pg;
+    for (int b0 = 0; b0 < B; b0 += gp.chunk) {
+        const int nbc = B - b0 < gp.chunk ? B - b0 : gp.chunk;
+        a.f.d.b0 = b0;
+        const dim3 grid(nb, c.M * gp.groups, nbc);
+        LAUNCH((k_bwd_start<F>), grid, st, a);
+        for (int z = c.Z - 1; z >= 0; --z) {
+            int out_mode = 0;
+            if (z == 0) out_mode = want_p ? (c.shift_probes ? 0 : 1) : 2;
+            LAUNCH((k_bwd_da<F>), grid, st, a, z, out_mode);
+            if (z > 0) LAUNCH((k_bwd_bc<F>), grid, st, a, z);
+        }
+        if (want_p) {                                     // gpsi_0 of this chunk is in G1
+            if (c.shift_probes) {
+                int per = nb * c.P;
+                int nsub = (kMinCtas + per - 1) / per;
+                if (nsub > nbc) nsub = nbc;
+                if (nsub < 1) nsub = 1;
+                int bsub = (nbc + nsub - 1) / nsub;
+                nsub = (nbc + bsub - 1) / bsub;
+                LAUNCH((k_bwd_probe<F>), dim3(nb, c.P, nsub), st, a, nbc, bsub);
+            } else if (a.need_probe) {
+                k_bwd_probe_noshift<<<dim3((c.N * c.N + 255) / 256, c.P), 256, 0, st>>>(a.f.d, nbc, b0 == 0 ? 1 : 0, w.G1, (float2*)g_probe);
+                CKL();
+            }
         }
     }
+    a.f.d.b0 = 0;
+    if (want_p && c.shift_probes && a.need_probe)
+        if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c.P, +1, st)) return r;
     return 0;
 }
 

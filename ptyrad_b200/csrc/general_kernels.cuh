@@ -9,8 +9,10 @@
 //                                   registers, one red.global per pixel), gpsi = conj(O_z) gphi, forward-x -> G1
 //                             BC^H: forward-y, *conj(H_n) [+ tilt/thickness sums], inverse-y     -> G2
 //
-// A CTA owns (sample, object mode, 16-row slab) and loops over the probe modes, so the O_z ROI, the propagator
-// values, the intensity accumulators and the object-gradient accumulators live in registers across the loop.
+// A CTA owns (sample, object mode, probe-mode group, 16-row slab) and loops over the probe modes of its group, so the O_z ROI,
+// the propagator values and the object-gradient accumulators live in registers across the loop.
+// The host can run the slice sequence on CHUNKS of the batch (api.cu: gen_plan; default one chunk): the pass buffers G1/G2 hold only
+// the chunk's tiles.
 // Works for N = N1*N2 with N1,N2 <= 16 (see dispatch in api.cu).  The N = 128 on-chip kernels are in fused128.cuh.
 #pragma once
 #include "rowfft.cuh"
@@ -23,11 +25,39 @@ constexpr int NT = 256;    // threads per CTA
 #ifndef GEN_MINB
 #define GEN_MINB 2       // minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (256 * GEN_MINB))
 #endif
+// the kernels with one cached table (k_fwd_da, k_fwd_bc, k_bwd_bc) fit 3 CTAs per SM (80 registers) without spilling up to N = 192
+// (measured: C5 +14 %); at N = 256 the 80-register build spills and is slower than 2 CTAs per SM (C4 -3 %, C3 -13 %)
+#ifndef GEN_MINB_LIGHT
+#define GEN_MINB_LIGHT(F) ((F::N) <= 192 ? 3 : 2)
+#endif
 
 struct Dims {
     int N, P, M, Z, Noy, Nox, B;
     int patch;      // 1: the "object" arrays are per-sample patches (B,M,Z,N,N) (pre-blurred ROIs); crop offsets are zero
+    int b0;         // first sample of the chunk this launch works on (grid z = sample inside the chunk)
+    int pg;         // probe modes per CTA (grid y = object mode + M * probe-mode group)
 };
+// chunk-local decomposition of a (nb, M*groups, chunk) grid
+struct Unit { int m, b, bl, p_lo, p_hi; };
+__device__ __forceinline__ Unit unit_of(const Dims& d) {
+    Unit u;
+    u.m = blockIdx.y % d.M;
+    u.p_lo = (blockIdx.y / d.M) * d.pg;
+    u.p_hi = min(d.P, u.p_lo + d.pg);
+    u.bl = blockIdx.z;
+    u.b = d.b0 + u.bl;
+    return u;
+}
+// accesses of the write-once / read-once streams (stash, far-field tiles, Fourier stash).  Streaming (evict-first, .cs) hints were
+// measured on B200 and rejected: no gain on the stores, and ld.global.cs on the stash / Fourier-stash reads made the C3 adjoint 27 %
+// slower (it defeats the L2 prefetch issued one probe mode ahead).  -DPTYB_STREAM_HINTS rebuilds that variant.
+#ifdef PTYB_STREAM_HINTS
+__device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
+__device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
+#else
+__device__ __forceinline__ void st_stream(float2* p, float2 v) { *p = v; }
+__device__ __forceinline__ float2 ld_stream(const float2* p) { return *p; }
+#endif
 // object plane index and ROI offset of sample b, object mode m
 __device__ __forceinline__ int obj_mode(const Dims& d, int b, int m) { return d.patch ? b * d.M + m : m; }
 __device__ __forceinline__ void roi_origin(const Dims& d, const int32_t* crop, const int64_t* idx, int b, int& cy, int& cx) {
@@ -273,58 +303,72 @@ struct FwdArgs {
     float eps;
 };
 
-// psi0 half-shifted: G2[b,p,0][y][kx] = (1/N) * inverse-y( PhatT[p][kx][ky] * wy[ky] * wx[kx] ).  grid (N/ROWS, B)
+// psi0 half-shifted: G2[b,p,0][y][kx] = (1/N) * inverse-y( PhatT[p][kx][ky] * wy[ky] * wx[kx] ).  grid (N/ROWS, groups, chunk)
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_init_shift(FwdArgs a) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
-    const int kx0 = blockIdx.x * ROWS, b = blockIdx.y;
+    const int kx0 = blockIdx.x * ROWS, bl = blockIdx.z, b = a.d.b0 + bl;
+    const int p_lo = blockIdx.y * a.d.pg, p_hi = min(a.d.P, p_lo + a.d.pg);
     const float2* wy = a.wvec + ((size_t)b * 2 + 0) * N;
     const float2* wx = a.wvec + ((size_t)b * 2 + 1) * N;
     float2 wreg[Slab<F>::EPT];
     Slab<F>::nat([&](int i, int r, int ky) { wreg[i] = cmul(wy[ky], wx[kx0 + r]); });
-    for (int p = 0; p < a.d.P; ++p) {
+    for (int p = p_lo; p < p_hi; ++p) {
         const float2* src = a.PhatT + (size_t)p * N * N;
         Slab<F>::nat([&](int i, int r, int ky) { slab[r * F::RS + F::apos(ky)] = cmul(src[(size_t)(kx0 + r) * N + ky], wreg[i]); });
         __syncthreads();
         F::inverse(slab, ROWS, twN);
-        float2* dst = a.G2 + ((size_t)b * a.d.P + p) * a.d.M * N * N;   // m = 0 slot
+        float2* dst = a.G2 + ((size_t)bl * a.d.P + p) * a.d.M * N * N;   // m = 0 slot
         Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
         __syncthreads();
     }
 }
 
-// grid (N/ROWS, M, B).  src_mode: 0 = psi_z comes from G2 (inverse-x), 1 = psi_0 is the unshifted probe.
-// The last inverse stage, the pointwise work (stash, *O_z) and the first forward stage act on the same N1 elements
-// x = j + N2*k of one row, so they are fused in registers: one work item (row r, j) per thread, no smem round trip between.
-template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
+// grid (N/ROWS, M*groups, chunk).  src_mode: 0 = psi_z comes from G2 (inverse-x), 1 = psi_0 is the unshifted probe.
+// Three register stages per probe mode, two shared-memory exchanges between them (4 smem passes instead of 8):
+//   A  item (row r, k1):  X[k1 + N1 k2] straight from global (128-byte segments), inverse DFT over k2, twiddle        -> smem
+//   B  item (row r, j):   inverse DFT over k1 -> psi_z[x = j + N2 k] -> stash, *O_z, forward DFT over k, twiddle     -> smem
+//   C  item (row rr, k1): forward DFT over j -> frequency q = k1 + N1 k2, stored straight to the transposed tile: the lanes run
+//      over the 16 rows of the slab, so each store instruction writes 128-byte segments and the odd row stride keeps the
+//      shared-memory reads conflict free.
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     static_assert(ROWS * N2 <= NT && ROWS * N1 <= NT, "one fused work item per thread");
     const Dims& d = a.d;
-    const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    const Unit un = unit_of(d);
+    const int y0 = blockIdx.x * ROWS, m = un.m, b = un.b;
     int cy, cx;
     roi_origin(d, a.crop, a.idx, b, cy, cx);
     const float2* Oz = a.O + ((size_t)obj_mode(d, b, m) * d.Z + z) * d.Noy * d.Nox;
-    const bool item = threadIdx.x < ROWS * N2;
-    const int r = threadIdx.x / N2, j = threadIdx.x % N2;
+    const bool itemA = threadIdx.x < ROWS * N1, itemB = threadIdx.x < ROWS * N2;
+    const int rA = threadIdx.x / N1, k1A = threadIdx.x % N1;          // stage A
+    const int r = threadIdx.x / N2, j = threadIdx.x % N2;             // stage B
+    const int rC = threadIdx.x % ROWS, k1C = threadIdx.x / ROWS;      // stage C (itemA range)
     float2 Oreg[N1];
-    if (item) {
+    if (itemB) {
 #pragma unroll
         for (int k = 0; k < N1; ++k) Oreg[k] = Oz[(size_t)(cy + y0 + r) * d.Nox + cx + j + N2 * k];
     }
     const int msrc = (z == 0) ? 0 : m;
-    for (int p = 0; p < d.P; ++p) {
-        const size_t tile = ((size_t)b * d.P + p) * d.M;
-        float2* st = a.stash + ((tile + m) * d.Z + z) * N * N + (size_t)(y0 + r) * N + j;
-        float2* row = slab + r * F::RS;
+    for (int p = un.p_lo; p < un.p_hi; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M;           // batch-wide streams (stash, far-field tiles)
+        const size_t ltile = ((size_t)un.bl * d.P + p) * d.M;      // chunk-local pass buffers G1 / G2
         if (src_mode == 0) {
-            const float2* src = a.G2 + (tile + msrc) * N * N;
-            if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
-            Slab<F>::nat([&](int, int rr, int kx) { slab[rr * F::RS + F::apos(kx)] = src[(size_t)(y0 + rr) * N + kx]; });
+            const float2* src = a.G2 + (ltile + msrc) * N * N;
+            if (p + 1 < un.p_hi) prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
+            if (itemA) {
+                float2 v[N2];
+                const float2* sp = src + (size_t)(y0 + rA) * N + k1A;
+#pragma unroll
+                for (int k2 = 0; k2 < N2; ++k2) v[k2] = sp[N1 * k2];
+                F::inv_stage2_regs(slab + rA * F::RS, k1A, v, twN);
+            }
             __syncthreads();
-            F::inverse_first(slab, ROWS, twN);
         }
-        if (item) {
+        if (itemB) {
+            float2* row = slab + r * F::RS;
+            float2* st = a.stash + ((tile + m) * d.Z + z) * N * N + (size_t)(y0 + r) * N + j;
             float2 v[N1];
             if (src_mode == 0) {
 #pragma unroll
@@ -339,7 +383,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdA
             }
 #pragma unroll
             for (int k = 0; k < N1; ++k) {
-                st[N2 * k] = v[k];
+                st_stream(st + N2 * k, v[k]);
                 v[k] = cmul(v[k], Oreg[k]);
             }
             Dft<N1, -1>::run(v);
@@ -347,9 +391,18 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_da(FwdA
             for (int k1 = 0; k1 < N1; ++k1) row[F::addr(j + N2 * k1)] = k1 ? cmul(v[k1], twN[j * k1]) : v[k1];
         }
         __syncthreads();
-        F::forward_last(slab, ROWS);
-        float2* dst = (last ? a.farT : a.G1) + (tile + m) * N * N;
-        Slab<F>::tr([&](int, int rr, int q) { dst[(size_t)q * N + y0 + rr] = slab[rr * F::RS + F::apos(q)]; });
+        if (itemA) {
+            float2 v[N2];
+            F::fwd_stage2_regs(slab + rC * F::RS, k1C, v);
+            float2* dst = (last ? a.farT + (tile + m) * N * N : a.G1 + (ltile + m) * N * N) + (size_t)k1C * N + y0 + rC;
+            if (last) {
+#pragma unroll
+                for (int k2 = 0; k2 < N2; ++k2) st_stream(dst + (size_t)N1 * k2 * N, v[k2]);
+            } else {
+#pragma unroll
+                for (int k2 = 0; k2 < N2; ++k2) dst[(size_t)N1 * k2 * N] = v[k2];
+            }
+        }
         __syncthreads();
     }
 }
@@ -367,25 +420,36 @@ template <class F> __device__ __forceinline__ void load_prop_item(const FwdArgs&
     }
 }
 
-// grid (N/ROWS, M, B): G1[kx][y] -> forward-y -> *H -> inverse-y -> G2[y][kx].  The last forward stage, the propagator multiply
-// and the first inverse stage act on the same N2 elements ky = k1 + N1*k2: fused in registers, one item (row, k1) per thread.
-template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_bc(FwdArgs a, int z) {
+// grid (N/ROWS, M*groups, chunk): G1[kx][y] -> forward-y -> *H -> inverse-y -> G2[y][kx].  Same three-stage structure as k_fwd_da:
+//   A  item (row r, j):   y = j + N2 k straight from global, forward DFT over k, twiddle                           -> smem
+//   B  item (row r, k1):  forward DFT over j -> ky = k1 + N1 k2, *H_n, inverse DFT over k2, conjugate twiddle      -> smem
+//   C  item (row rr, j):  inverse DFT over k1 -> y = j + N2 k, stored straight to the transposed tile (lanes over the slab rows)
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fwd_bc(FwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.d;
-    const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
-    const bool item = threadIdx.x < ROWS * N1;
+    const Unit un = unit_of(d);
+    const int kx0 = blockIdx.x * ROWS, m = un.m, b = un.b;
+    const bool itemA = threadIdx.x < ROWS * N2, itemB = threadIdx.x < ROWS * N1;
+    const int rA = threadIdx.x / N2, jA = threadIdx.x % N2;
     const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    const int rC = threadIdx.x % ROWS, jC = threadIdx.x / ROWS;
     float2 Hreg[N2];
-    if (item) load_prop_item<F>(a, b, kx0 + r, k1, Hreg);
-    for (int p = 0; p < d.P; ++p) {
+    if (itemB) load_prop_item<F>(a, b, kx0 + r, k1, Hreg);
+    for (int p = un.p_lo; p < un.p_hi; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-        const float2* src = a.G1 + tile * N * N;
-        if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
-        Slab<F>::nat([&](int, int rr, int y) { slab[rr * F::RS + F::addr(y)] = src[(size_t)(kx0 + rr) * N + y]; });
+        const size_t ltile = ((size_t)un.bl * d.P + p) * d.M + m;
+        const float2* src = a.G1 + ltile * N * N;
+        if (p + 1 < un.p_hi) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
+        if (itemA) {
+            float2 v[N1];
+            const float2* sp = src + (size_t)(kx0 + rA) * N + jA;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) v[k] = sp[N2 * k];
+            F::fwd_stage1_regs(slab + rA * F::RS, jA, v, twN);
+        }
         __syncthreads();
-        F::forward_first(slab, ROWS, twN);
-        if (item) {
+        if (itemB) {
             float2* row = slab + r * F::RS;
             float2* ph = a.phis ? a.phis + (tile * (d.Z - 1) + z) * N * N + (size_t)(kx0 + r) * N + k1 : nullptr;
             float2 v[N2];
@@ -394,7 +458,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_bc(FwdA
             Dft<N2, -1>::run(v);
 #pragma unroll
             for (int k2 = 0; k2 < N2; ++k2) {
-                if (ph) ph[N1 * k2] = v[k2];
+                if (ph) st_stream(ph + N1 * k2, v[k2]);
                 v[k2] = cmul(v[k2], Hreg[k2]);
             }
             Dft<N2, +1>::run(v);
@@ -402,9 +466,13 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_bc(FwdA
             for (int j = 0; j < N2; ++j) row[F::addr(j + N2 * k1)] = k1 ? cmulc(v[j], twN[j * k1]) : v[j];
         }
         __syncthreads();
-        F::inverse_last(slab, ROWS);
-        float2* dst = a.G2 + tile * N * N;
-        Slab<F>::tr([&](int, int rr, int y) { dst[(size_t)y * N + kx0 + rr] = cscale(slab[rr * F::RS + F::addr(y)], 1.0f / N); });
+        if (itemA) {
+            float2 v[N1];
+            F::inv_stage1_regs(slab + rC * F::RS, jC, v);
+            float2* dst = a.G2 + ltile * N * N + (size_t)jC * N + kx0 + rC;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) dst[(size_t)N2 * k * N] = cscale(v[k], 1.0f / N);
+        }
         __syncthreads();
     }
 }
@@ -450,22 +518,24 @@ struct BwdArgs {
     int need_obj, need_probe, need_shift, need_prop;
 };
 
-// grid (N/ROWS, M, B): farT -> forward-y -> * 2 occu G~ -> inverse-y -> G2
+// grid (N/ROWS, M*groups, chunk): farT -> forward-y -> * 2 occu G~ -> inverse-y -> G2
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_start(BwdArgs a) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.f.d;
-    const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    const Unit un = unit_of(d);
+    const int kx0 = blockIdx.x * ROWS, m = un.m, b = un.b;
     const float* G = a.G + (size_t)b * N * N;
     Slab<F>::tr([&](int, int r, int ky) { fbuf[r * (N + 1) + ky] = G[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + r, N)]; });
     __syncthreads();
     const float oc2 = 2.0f * a.f.occu[m];
     float Greg[Slab<F>::EPT];
     Slab<F>::nat([&](int i, int r, int ky) { Greg[i] = oc2 * fbuf[r * (N + 1) + ky]; });
-    for (int p = 0; p < d.P; ++p) {
+    for (int p = un.p_lo; p < un.p_hi; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const size_t ltile = ((size_t)un.bl * d.P + p) * d.M + m;
         const float2* src = a.f.farT + tile * N * N;
-        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = ld_stream(src + (size_t)(kx0 + r) * N + y); });
         __syncthreads();
         F::forward(slab, ROWS, twN);
         Slab<F>::nat([&](int i, int r, int ky) {
@@ -474,45 +544,54 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_start(B
         });
         __syncthreads();
         F::inverse(slab, ROWS, twN);
-        float2* dst = a.f.G2 + tile * N * N;
+        float2* dst = a.f.G2 + ltile * N * N;
         Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
         __syncthreads();
     }
 }
 
-// grid (N/ROWS, M, B).  out_mode: 0 = forward-x and store transposed to G1 (z>0, or z==0 with shifted probes),
+// grid (N/ROWS, M*groups, chunk).  out_mode: 0 = forward-x and store transposed to G1 (z>0, or z==0 with shifted probes),
 //                                 1 = store gpsi_0 untransformed (natural) to G1 (z==0, unshifted probes), 2 = nothing.
-// Register-fused like k_fwd_da: inverse stage over k1, gO accumulation over the probe modes, conj(O_z) multiply and the first
-// forward stage all act on the item's N1 elements x = j + N2*k.
+// Three register stages like k_fwd_da: A inverse DFT over k2 from global; B inverse DFT over k1 -> gphi_z, gO accumulation over the
+// probe modes, conj(O_z) multiply, forward DFT over k; C forward DFT over j -> transposed store.
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdArgs a, int z, int out_mode) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
-    const int y0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
+    const Unit un = unit_of(d);
+    const int y0 = blockIdx.x * ROWS, m = un.m, b = un.b;
     int cy, cx;
     roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
     const float2* Oz = a.f.O + ((size_t)obj_mode(d, b, m) * d.Z + z) * d.Noy * d.Nox;
-    const bool item = threadIdx.x < ROWS * N2;
+    const bool itemA = threadIdx.x < ROWS * N1, itemB = threadIdx.x < ROWS * N2;
+    const int rA = threadIdx.x / N1, k1A = threadIdx.x % N1;
     const int r = threadIdx.x / N2, j = threadIdx.x % N2;
+    const int rC = threadIdx.x % ROWS, k1C = threadIdx.x / ROWS;
     const size_t roi = (size_t)(cy + y0 + r) * d.Nox + cx + j;
     float2 Oreg[N1], accO[N1];
-    if (item) {
+    if (itemB) {
 #pragma unroll
         for (int k = 0; k < N1; ++k) { Oreg[k] = Oz[roi + N2 * k]; accO[k] = make_float2(0.f, 0.f); }
     }
-    for (int p = 0; p < d.P; ++p) {
+    for (int p = un.p_lo; p < un.p_hi; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-        const float2* src = a.f.G2 + tile * N * N;
+        const size_t ltile = ((size_t)un.bl * d.P + p) * d.M + m;
+        const float2* src = a.f.G2 + ltile * N * N;
         const float2* stt = a.f.stash + (tile * d.Z + z) * N * N;
-        if (p + 1 < d.P) {
+        if (p + 1 < un.p_hi) {
             prefetch_slab<N>(src + (size_t)d.M * N * N, y0);
             prefetch_slab<N>(stt + (size_t)d.M * d.Z * N * N, y0);
         }
-        Slab<F>::nat([&](int, int rr, int kx) { slab[rr * F::RS + F::apos(kx)] = src[(size_t)(y0 + rr) * N + kx]; });
+        if (itemA) {
+            float2 v[N2];
+            const float2* sp = src + (size_t)(y0 + rA) * N + k1A;
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) v[k2] = sp[N1 * k2];
+            F::inv_stage2_regs(slab + rA * F::RS, k1A, v, twN);
+        }
         __syncthreads();
-        F::inverse_first(slab, ROWS, twN);
-        float2* dst = a.f.G1 + tile * N * N;
-        if (item) {
+        float2* dst = a.f.G1 + ltile * N * N;
+        if (itemB) {
             float2* row = slab + r * F::RS;
             const float2* st = stt + (size_t)(y0 + r) * N + j;
             float2 v[N1];
@@ -522,7 +601,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
 #pragma unroll
             for (int k = 0; k < N1; ++k) {
                 const float2 gphi = cscale(v[k], 1.0f / N);
-                accO[k] = cadd(accO[k], cmulc(gphi, st[N2 * k]));          // conj(psi) * gphi
+                accO[k] = cadd(accO[k], cmulc(gphi, ld_stream(st + N2 * k)));   // conj(psi) * gphi
                 v[k] = cmulc(gphi, Oreg[k]);                                // conj(O) * gphi
             }
             if (out_mode == 0) {
@@ -536,53 +615,69 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
         }
         __syncthreads();
         if (out_mode == 0) {
-            F::forward_last(slab, ROWS);
-            Slab<F>::tr([&](int, int rr, int q) { dst[(size_t)q * N + y0 + rr] = slab[rr * F::RS + F::apos(q)]; });
+            if (itemA) {
+                float2 v[N2];
+                F::fwd_stage2_regs(slab + rC * F::RS, k1C, v);
+                float2* dp = dst + (size_t)k1C * N + y0 + rC;
+#pragma unroll
+                for (int k2 = 0; k2 < N2; ++k2) dp[(size_t)N1 * k2 * N] = v[k2];
+            }
             __syncthreads();
         }
     }
-    if (a.need_obj && item) {
+    if (a.need_obj && itemB) {
         float2* gOz = a.gO + ((size_t)obj_mode(d, b, m) * d.Z + z) * d.Noy * d.Nox + roi;
 #pragma unroll
         for (int k = 0; k < N1; ++k) red_add_f2(gOz + N2 * k, accO[k]);
     }
 }
 
-// grid (N/ROWS, M, B), z >= 1: G1 -> forward-y -> *conj(H_n) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
-// (register-fused like k_fwd_bc)
-template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdArgs a, int z) {
+// grid (N/ROWS, M*groups, chunk), z >= 1: G1 -> forward-y -> *conj(H_n) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
+// (three register stages like k_fwd_bc)
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bwd_bc(BwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
-    const int kx0 = blockIdx.x * ROWS, m = blockIdx.y, b = blockIdx.z;
-    const bool item = threadIdx.x < ROWS * N1;
+    const Unit un = unit_of(d);
+    const int kx0 = blockIdx.x * ROWS, m = un.m, b = un.b;
+    const bool itemA = threadIdx.x < ROWS * N2, itemB = threadIdx.x < ROWS * N1;
+    const int rA = threadIdx.x / N2, jA = threadIdx.x % N2;
     const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    const int rC = threadIdx.x % ROWS, jC = threadIdx.x / ROWS;
     float2 Hreg[N2];
-    if (item) load_prop_item<F>(a.f, b, kx0 + r, k1, Hreg);
+    if (itemB) load_prop_item<F>(a.f, b, kx0 + r, k1, Hreg);
     float s3[3] = {0.f, 0.f, 0.f};
     const float Kx = kgrid(kx0 + r, N, a.dx);
     const float invN2 = 1.0f / (float(N) * float(N));
-    float Kyr[N2], Kzr[N2];                                  // Ky and Kz - k0 of the item's elements (propagator gradients only)
-    if (a.need_prop) {
-#pragma unroll
-        for (int k2 = 0; k2 < N2; ++k2) {
-            const float Ky = kgrid(k1 + N1 * k2, N, a.dx);
-            const float kk = Kx * Kx + Ky * Ky;
-            Kyr[k2] = Ky;
-            Kzr[k2] = -kk / (sqrtf(a.k0 * a.k0 - kk) + a.k0);   // Kz - k0, cancellation-free
-        }
-    }
-    for (int p = 0; p < d.P; ++p) {
-        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-        const float2* src = a.f.G1 + tile * N * N;
-        if (p + 1 < d.P) prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
-        Slab<F>::nat([&](int, int rr, int y) { slab[rr * F::RS + F::addr(y)] = src[(size_t)(kx0 + rr) * N + y]; });
+    float* kyS = fbuf;                                       // Ky[ky] (propagator gradients only); Kz - k0 is formed on the fly so
+    if (a.need_prop) {                                       // that the registers can hold the Fourier stash loaded ahead of the DFT
+        for (int n = threadIdx.x; n < N; n += NT) kyS[n] = kgrid(n, N, a.dx);
         __syncthreads();
-        F::forward_first(slab, ROWS, twN);
-        if (item) {
+    }
+    for (int p = un.p_lo; p < un.p_hi; ++p) {
+        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const size_t ltile = ((size_t)un.bl * d.P + p) * d.M + m;
+        const float2* src = a.f.G1 + ltile * N * N;
+        if (p + 1 < un.p_hi) {
+            prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
+            if (a.need_prop) prefetch_slab<N>(a.f.phis + ((tile + d.M) * (d.Z - 1) + (z - 1)) * N * N, kx0);
+        }
+        if (itemA) {
+            float2 v[N1];
+            const float2* sp = src + (size_t)(kx0 + rA) * N + jA;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) v[k] = sp[N2 * k];
+            F::fwd_stage1_regs(slab + rA * F::RS, jA, v, twN);
+        }
+        __syncthreads();
+        if (itemB) {
             float2* row = slab + r * F::RS;
             const float2* ph = a.need_prop ? a.f.phis + (tile * (d.Z - 1) + (z - 1)) * N * N + (size_t)(kx0 + r) * N + k1 : nullptr;
-            float2 v[N2];
+            float2 v[N2], phi[N2];
+            if (ph) {                                                        // issued before the DFT: latency hidden behind it
+#pragma unroll
+                for (int k2 = 0; k2 < N2; ++k2) phi[k2] = ld_stream(ph + N1 * k2);
+            }
 #pragma unroll
             for (int jj = 0; jj < N2; ++jj) v[jj] = row[F::addr(jj + N2 * k1)];
             Dft<N2, -1>::run(v);
@@ -590,9 +685,11 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdA
             for (int k2 = 0; k2 < N2; ++k2) {
                 v[k2] = cmulc(v[k2], Hreg[k2]);                              // conj(H) * F2(gpsi)
                 if (ph) {
-                    const float2 phi = ph[N1 * k2];
-                    const float sv = (phi.x * v[k2].y - phi.y * v[k2].x) * invN2;   // Im(conj(Phi) * v) / N^2
-                    s3[0] += Kyr[k2] * sv; s3[1] += Kx * sv; s3[2] += Kzr[k2] * sv;
+                    const float sv = (phi[k2].x * v[k2].y - phi[k2].y * v[k2].x) * invN2;   // Im(conj(Phi) * v) / N^2
+                    const float Ky = kyS[k1 + N1 * k2];
+                    const float kk = Kx * Kx + Ky * Ky;
+                    s3[0] += Ky * sv; s3[1] += Kx * sv;
+                    s3[2] += -kk / (sqrtf(a.k0 * a.k0 - kk) + a.k0) * sv;    // Kz - k0, cancellation-free
                 }
             }
             Dft<N2, +1>::run(v);
@@ -600,9 +697,13 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdA
             for (int jj = 0; jj < N2; ++jj) row[F::addr(jj + N2 * k1)] = k1 ? cmulc(v[jj], twN[jj * k1]) : v[jj];
         }
         __syncthreads();
-        F::inverse_last(slab, ROWS);
-        float2* dst = a.f.G2 + tile * N * N;
-        Slab<F>::tr([&](int, int rr, int y) { dst[(size_t)y * N + kx0 + rr] = cscale(slab[rr * F::RS + F::addr(y)], 1.0f / N); });
+        if (itemA) {
+            float2 v[N1];
+            F::inv_stage1_regs(slab + rC * F::RS, jC, v);
+            float2* dst = a.f.G2 + ltile * N * N + (size_t)jC * N + kx0 + rC;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) dst[(size_t)N2 * k * N] = cscale(v[k], 1.0f / N);
+        }
         __syncthreads();
     }
     if (a.need_prop) {
@@ -615,14 +716,14 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_bc(BwdA
     }
 }
 
-// shifted probes: grid (N/ROWS, P, nchunk).  T = forward-y(sum_m G1[b,p,m]) / N^2 ; gPhatT += conj(w') T ;
-// shift gradients -2 pi sum kappa Im(conj(w') conj(Phat) T)
-template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(BwdArgs a, int bchunk) {
+// shifted probes: grid (N/ROWS, P, nsub), samples bl_lo..bl_hi of the chunk per CTA.  T = forward-y(sum_m G1[bl,p,m]) / N^2 ;
+// gPhatT += conj(w') T ; shift gradients -2 pi sum kappa Im(conj(w') conj(Phat) T)
+template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(BwdArgs a, int nchunk_b, int bsub) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N;
     const Dims& d = a.f.d;
     const int kx0 = blockIdx.x * ROWS, p = blockIdx.y;
-    const int b_lo = blockIdx.z * bchunk, b_hi = min(d.B, b_lo + bchunk);
+    const int b_lo = blockIdx.z * bsub, b_hi = min(nchunk_b, b_lo + bsub);
     float2 acc[Slab<F>::EPT], Ph[Slab<F>::EPT];
     float kapy[Slab<F>::EPT], kapx[Slab<F>::EPT];
     Slab<F>::nat([&](int i, int r, int ky) {
@@ -632,8 +733,9 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(B
         kapx[i] = float(shift_idx(kx0 + r, N)) / float(N);
     });
     const float invN2 = 1.0f / (float(N) * float(N));
-    for (int b = b_lo; b < b_hi; ++b) {
-        const size_t tile0 = ((size_t)b * d.P + p) * d.M;
+    for (int bl = b_lo; bl < b_hi; ++bl) {
+        const int b = d.b0 + bl;
+        const size_t tile0 = ((size_t)bl * d.P + p) * d.M;
         Slab<F>::nat([&](int, int r, int y) {
             float2 v = make_float2(0.f, 0.f);
             for (int m = 0; m < d.M; ++m) v = cadd(v, a.f.G1[(tile0 + m) * N * N + (size_t)(kx0 + r) * N + y]);
@@ -668,14 +770,16 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(B
     }
 }
 
-// unshifted probes: g_probe[p][y][x] = sum_{b,m} G1[b,p,m][y][x] (natural layout).  grid (ceil(N*N/256), P)
-__global__ void k_bwd_probe_noshift(Dims d, const float2* __restrict__ G1, float2* __restrict__ gprobe) {
+// unshifted probes: g_probe[p][y][x] (+)= sum_{bl,m} G1[bl,p,m][y][x] (natural layout) over the nb samples of one chunk; chunks run
+// one after the other on the stream, the first one stores.  grid (ceil(N*N/256), P)
+__global__ void k_bwd_probe_noshift(Dims d, int nb, int first, const float2* __restrict__ G1, float2* __restrict__ gprobe) {
     int e = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
     if (e >= d.N * d.N) return;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int b = 0; b < d.B; ++b)
+    float2* dst = gprobe + (size_t)p * d.N * d.N + e;
+    float2 acc = first ? make_float2(0.f, 0.f) : *dst;
+    for (int b = 0; b < nb; ++b)
         for (int m = 0; m < d.M; ++m) acc = cadd(acc, G1[(((size_t)b * d.P + p) * d.M + m) * d.N * d.N + e]);
-    gprobe[(size_t)p * d.N * d.N + e] = acc;
+    *dst = acc;
 }
 
 // g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O))   (polar backward, forward.py:53)

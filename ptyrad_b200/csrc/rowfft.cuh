@@ -71,6 +71,33 @@ template <int N1_, int N2_> struct RowFFT {
         for (int k = 0; k < N1; ++k) row[addr(j + N2 * k)] = v[k];
     }
 
+    // Register-fed / register-draining variants of the outer stages, for kernels that load the first stage's operands straight
+    // from global memory and store the last stage's results straight to global memory (general_kernels.cuh, stages A and C):
+    //   fwd_stage1_regs: v[k] = x[j + N2*k] in registers           -> row (as fwd_stage1 leaves it)
+    //   fwd_stage2_regs: row (as fwd_stage1 leaves it)             -> v[k2] = X[k1 + N1*k2] in registers
+    //   inv_stage2_regs: v[k2] = X[k1 + N1*k2] in registers        -> row (as inv_stage2 leaves it)
+    //   inv_stage1_regs: row (as inv_stage2 leaves it)             -> v[k] = x[j + N2*k] in registers (unnormalised)
+    PTYB_HD static void fwd_stage1_regs(float2* row, int j, float2 (&v)[N1], const float2* twN) {
+        Dft<N1, -1>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < N1; ++k1) row[addr(j + N2 * k1)] = (k1 == 0) ? v[k1] : cmul(v[k1], tw<-1>(twN, j * k1));
+    }
+    PTYB_HD static void fwd_stage2_regs(const float2* row, int k1, float2 (&v)[N2]) {
+#pragma unroll
+        for (int j = 0; j < N2; ++j) v[j] = row[addr(j + N2 * k1)];
+        Dft<N2, -1>::run(v);
+    }
+    PTYB_HD static void inv_stage2_regs(float2* row, int k1, float2 (&v)[N2], const float2* twN) {
+        Dft<N2, +1>::run(v);
+#pragma unroll
+        for (int j = 0; j < N2; ++j) row[addr(j + N2 * k1)] = (k1 == 0) ? v[j] : cmul(v[j], tw<+1>(twN, j * k1));
+    }
+    PTYB_HD static void inv_stage1_regs(const float2* row, int j, float2 (&v)[N1]) {
+#pragma unroll
+        for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[addr(j + N2 * k1)];
+        Dft<N1, +1>::run(v);
+    }
+
 #ifdef __CUDACC__
     // Block-wide drivers over `rows` rows of a slab with row stride RS.  All threads of the block must call.
     __device__ static void forward(float2* slab, int rows, const float2* twN) {

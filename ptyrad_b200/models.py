@@ -108,6 +108,8 @@ class PtychoAD(nn.Module):
             self._current_object_patches = None
             self.kernel_path = _lib.PATH_AUTO
             self.kernel_flags = 0          # experimental kernel switches (cfg.reserved[0])
+            self.kernel_chunk = 0          # general path: samples per L2-resident chunk (0 = library heuristic; cfg.reserved[2])
+            self.kernel_pmodes_per_cta = 0  # general path: probe modes looped over by one CTA (0 = heuristic; cfg.reserved[3])
 
             self._validate(init_variables)
             self.create_grids()
@@ -219,6 +221,8 @@ class PtychoAD(nn.Module):
                               self._dx_host, self._lambd_host, 1e-10, self.kernel_path)
         cfg.reserved[0] = int(self.kernel_flags)
         cfg.reserved[1] = 1 if patch_mode else 0
+        cfg.reserved[2] = int(self.kernel_chunk)
+        cfg.reserved[3] = int(self.kernel_pmodes_per_cta)
         return cfg
 
     def _roi_tensor(self, idx):

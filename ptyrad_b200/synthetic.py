@@ -67,6 +67,10 @@ CONFIGS = {
     "C4": ScanConfig("C4", N=256, scan=256, P=12, M=1, Z=16, batch=256, lr_shifts=1e-4),
     # C5: mixed-state object + Poisson loss
     "C5": ScanConfig("C5", N=192, scan=96, P=1, M=2, Z=10, batch=512, loss="poissn"),
+    # tuning stand-ins: C3 / C4 kernels shapes on a smaller scan (seconds instead of a minute of input generation); not bench lines
+    "C3s": ScanConfig("C3s", N=256, scan=64, P=8, M=1, Z=32, batch=64, kv=300.0, conv_angle=21.4,
+                      dz=10.0, defocus=-200.0, tilt_each=True, lr_shifts=1e-4, lr_tilts=1e-4),
+    "C4s": ScanConfig("C4s", N=256, scan=96, P=12, M=1, Z=16, batch=256, lr_shifts=1e-4),
     # tiny cases for parity tests (oracle finishes in well under a second)
     "T32": ScanConfig("T32", N=32, scan=6, P=2, M=2, Z=3, batch=5, lr_shifts=1e-4, step=0.6),
     "T64": ScanConfig("T64", N=64, scan=5, P=3, M=1, Z=4, batch=7, lr_shifts=1e-4),

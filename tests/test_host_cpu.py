@@ -188,6 +188,22 @@ def test_gradient_exchange_world2_gloo():
         assert all(v < 1e-6 for v in err.values()), (rank, err)
 
 
+def test_fft_index_algebra_on_host(tmp_path):
+    """The register DFT templates and the two-stage row FFT (incl. the register-fed outer stages the general kernels use) are
+    __host__ __device__: compile them for the host and check them against a double-precision DFT (no GPU needed)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "test_fft_host")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc_host", "test_fft_host.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-o", exe, src], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "ALL OK" in r.stdout
+
+
 def test_product_package_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under ptyrad_b200/ may import it (a product path through the oracle would void
     every parity claim)."""
