@@ -176,7 +176,25 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64 and cfg.N <= 128))
+    simulate = cfg.scan <= 64 and cfg.N <= 128
+    if world > 1 and simulate:
+        # the simulated measurements cost ~30 s of host time with all cores: rank 0 makes them once (torchrun pins every rank to one
+        # OpenMP thread) and the other ranks read them from a node-local file -- every rank ends up with identical inputs
+        shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp",
+                              f"ptyb200_meas_{cfg.name}_{os.environ.get('MASTER_PORT', '0')}.npy")
+        if rank == 0:
+            torch.set_num_threads(threads)
+            iv, mp, lp = make_inputs(cfg, simulate_measurements=True)
+            np.save(shared + ".tmp.npy", iv["measurements"])
+            os.replace(shared + ".tmp.npy", shared)
+        dist.barrier()
+        if rank != 0:
+            iv, mp, lp = make_inputs(cfg, measurements=np.load(shared))
+        dist.barrier()
+        if rank == 0:
+            os.remove(shared)
+    else:
+        iv, mp, lp = make_inputs(cfg, simulate_measurements=simulate)
     Ntot = iv["crop_pos"].shape[0]
     model = PtychoAD(iv, mp, device=dev, verbose=False)
     model.kernel_path = {"auto": _lib.PATH_AUTO, "general": _lib.PATH_GENERAL, "fused": _lib.PATH_FUSED}[args.path]

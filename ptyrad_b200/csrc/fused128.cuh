@@ -61,7 +61,6 @@ struct Args {
     float2* gprobe;         // (P, N, N) natural (unshifted probes)
     float* gprop;
     float* gshift;
-    float2* acc;            // (slots, Z, TILE) CTA-private gO accumulators
     float dx, k0;
     int shift, need_obj, need_probe, need_shift, need_prop, units, direct_red;
 };
@@ -359,6 +358,10 @@ struct Ptrs {                       // per-CTA base pointers into the packed obj
     size_t roi0;                    // (cy + yl)*Nox + cx + x
 };
 
+// TILT: per-sample tilt ramps multiply the propagator; PHIS: the Fourier-domain waves are kept for the tilt / thickness gradients.
+// Compile-time switches: as runtime flags inside the unrolled pointwise loops they cost a branch + convergence barrier per element
+// (BSSY/BSYNC/BRA/UMOV were 8 % of the forward's and 14 % of the adjoint's stall samples).
+template <bool TILT, bool PHIS>
 __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
@@ -376,8 +379,7 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     const size_t ostr = (size_t)8 * d.Nox;
     const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
     const int tR = g.yl * 128 + g.x;
-    const bool tilt = a.f.tvec != nullptr;
-    const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
+    const float2 eyv = TILT ? s.ey[g.ky] : make_float2(1.f, 0.f);
     float2 v[32];
     if (a.shift) {
         const float4* __restrict__ ph = reinterpret_cast<const float4*>(a.PhatF) + (size_t)p * (TILE / 2) + g.t;
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
             fft2_R_to_F(v, s.E, s.tw, g);
             if (z == d.Z - 1) break;
             const float4* __restrict__ hf = reinterpret_cast<const float4*>(a.HF) + g.t;
-            float4* __restrict__ ph = a.phisF ? reinterpret_cast<float4*>(a.phisF) + (tile * (d.Z - 1) + z) * (TILE / 2) + g.t : nullptr;
+            float4* __restrict__ ph = PHIS ? reinterpret_cast<float4*>(a.phisF) + (tile * (d.Z - 1) + z) * (TILE / 2) + g.t : nullptr;
 #pragma unroll
             for (int j0 = 0; j0 < 16; j0 += CH2) {
                 float4 h[CH2];
@@ -437,9 +439,9 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 #pragma unroll
                 for (int i = 0; i < CH2; ++i) {
                     const int u = 2 * (j0 + i);
-                    if (ph) ph[(j0 + i) * 512] = pack2(v[u], v[u + 1]);
+                    if (PHIS) ph[(j0 + i) * 512] = pack2(v[u], v[u + 1]);
                     float2 h0 = lo2(h[i]), h1 = hi2(h[i]);
-                    if (tilt) { h0 = cmul(h0, cmul(eyv, s.ex[g.kx(u)])); h1 = cmul(h1, cmul(eyv, s.ex[g.kx(u + 1)])); }
+                    if (TILT) { h0 = cmul(h0, cmul(eyv, s.ex[g.kx(u)])); h1 = cmul(h1, cmul(eyv, s.ex[g.kx(u + 1)])); }
                     v[u] = cmul(v[u], h0);
                     v[u + 1] = cmul(v[u + 1], h1);
                 }
@@ -462,8 +464,7 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 }
 
 // ---- adjoint --------------------------------------------------------------------------------------------------------
-// gO accumulation over the probe modes.  MODE 0: first mode -> store; 1: middle -> read-modify-write;
-// 2: last mode -> scatter (accumulator + own) into the dense gradient; 3: scatter own (default); 4: not wanted
+// pointwise phase after the inverse FFT.  MODE 3: scatter conj(psi_z) gphi_z into the dense gradient; 4: object gradient not wanted
 // default scatter path (one CTA per probe mode): conj(psi_z) gphi_z is staged per warp in shared memory (8 pairs = 8 x 512 B)
 // and handed to the TMA engine as bulk reductions (cp.reduce.async.bulk ... add.f32) into the packed dense gradient --
 // the SM issues no RED instructions and keeps no registers alive for them.
@@ -508,21 +509,18 @@ __device__ __forceinline__ void accum_phase(float2 (&v)[32], const float4* __res
                                             float4* __restrict__ ac, float4* __restrict__ gOz) {
 #pragma unroll
     for (int j0 = 0; j0 < 16; j0 += CH2) {
-        float4 ps[CH2], o[CH2], av[CH2];
+        float4 ps[CH2], o[CH2];
 #pragma unroll
         for (int i = 0; i < CH2; ++i) {
             o[i] = __ldg(Oz + (j0 + i) * ostr);
             if (MODE != 4) ps[i] = __ldg(st + (j0 + i) * 32);
-            if (MODE == 1 || MODE == 2) av[i] = ac[(j0 + i) * 512];
         }
 #pragma unroll
         for (int i = 0; i < CH2; ++i) {
             const int k = 2 * (j0 + i);
             if (MODE != 4) {
-                float2 c0 = cmulc(v[k], lo2(ps[i])), c1 = cmulc(v[k + 1], hi2(ps[i]));     // conj(psi) * gphi
-                if (MODE == 1 || MODE == 2) { c0 = cadd(c0, lo2(av[i])); c1 = cadd(c1, hi2(av[i])); }
-                if (MODE == 0 || MODE == 1) ac[(j0 + i) * 512] = pack2(c0, c1);
-                else red_f4(gOz + (j0 + i) * ostr, c0, c1);
+                const float2 c0 = cmulc(v[k], lo2(ps[i])), c1 = cmulc(v[k + 1], hi2(ps[i]));     // conj(psi) * gphi
+                red_f4(gOz + (j0 + i) * ostr, c0, c1);
             }
             v[k] = cmulc(v[k], lo2(o[i]));                     // gpsi_z = conj(O_z) gphi_z
             v[k + 1] = cmulc(v[k + 1], hi2(o[i]));
@@ -530,29 +528,26 @@ __device__ __forceinline__ void accum_phase(float2 (&v)[32], const float4* __res
     }
 }
 
-// ACC = false (default): one CTA per (sample, object mode, probe mode); every mode scatters its conj(psi_z) gphi_z straight
-//   into the dense (L2-resident) object gradient with red.global.add.v4.f32 -- no accumulator traffic, all units independent.
-// ACC = true: persistent CTAs over units (sample, object mode) looping over the probe modes; the sum over modes is kept in a
-//   CTA-private accumulator (plain loads/stores; slot = blockIdx.x) and scattered once per pixel and slice.
-// Per probe mode the loop runs "steps" s = Z .. 0 with ONE forward/inverse FFT call site:
+// One CTA per unit (sample, object mode, probe mode); every mode scatters its conj(psi_z) gphi_z straight into the dense (L2-resident)
+// object gradient with red.global.add.v4.f32 -- no accumulator traffic, all units independent.  (Accumulating over the probe modes
+// in a CTA-private scratch first was measured slower -- 2.1 vs 1.63 ms at C2, the 148 MB of accumulators do not stay in L2 -- and
+// was removed.)
+// Per unit the loop runs "steps" s = Z .. 0 with ONE forward/inverse FFT call site:
 //   s = Z     : (stashed) F2(psi_{Z-1} O_{Z-1}) * (2 occu G~ / N^2)     -> inverse -> gphi_{Z-1}
 //   s = z >= 1: F2(gpsi_z) * conj(H_n)/N^2 [+ propagator-gradient sums] -> inverse -> gphi_{z-1}
 //   s = 0     : F2(gpsi_0) -> probe-spectrum and shift gradients (only with shifted probes)
-template <bool ACC>
+// TILT / PROP (tilt ramps on the propagator / tilt + thickness gradient sums) are compile-time, see k_forward.
+template <bool TILT, bool PROP>
 __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem s = carve_smem(smem_raw);
     const Geo g;
     const Dims& d = a.f.d;
     const int tR = g.yl * 128 + g.x;
-    float4* accb = ACC ? reinterpret_cast<float4*>(a.acc) + (size_t)blockIdx.x * d.Z * (TILE / 2) + tR : nullptr;
-    const bool tilt = a.f.tvec != nullptr;
     const bool want_probe_fft = a.shift && (a.need_probe || a.need_shift);
     const size_t plane = (size_t)d.Noy * d.Nox;
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
-        int b, m, p_lo, p_hi;
-        if (ACC) { b = unit / d.M; m = unit % d.M; p_lo = 0; p_hi = d.P; }
-        else { p_lo = unit % d.P; p_hi = p_lo + 1; const int bm = unit / d.P; b = bm / d.M; m = bm % d.M; }
+        const int p = unit % d.P, bm = unit / d.P, b = bm / d.M, m = bm % d.M;
         const int64_t n0 = a.f.idx[b];
         int cy, cx;
         roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
@@ -563,130 +558,116 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         const float gsc = 2.0f * a.f.occu[m] * (1.0f / (128.0f * 128.0f));
         const float* __restrict__ Grow = a.G + (size_t)b * TILE + ((g.ky + 64) & 127) * 128;
         __syncthreads();
-        const float2 eyv = tilt ? s.ey[g.ky] : make_float2(1.f, 0.f);
+        const float2 eyv = TILT ? s.ey[g.ky] : make_float2(1.f, 0.f);
         const size_t ostr = (size_t)8 * d.Nox;
         const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
         float s3[3] = {0.f, 0.f, 0.f};                  // Ky S, Kx S, (Kz-k0) S
-        for (int p = p_lo; p < p_hi; ++p) {
-            const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-            const float4* stash_t = reinterpret_cast<const float4*>(a.f.stash) + tile * d.Z * (TILE / 2);
-            const int mode = !a.need_obj ? 4 : ((!ACC || d.P == 1) ? 3 : (p == 0 ? 0 : (p < d.P - 1 ? 1 : 2)));
-            float2 v[32];
-            for (int st_i = d.Z; st_i >= 0; --st_i) {
-                if (st_i == 0 && !want_probe_fft) break;
-                // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
-                const int zn = st_i == d.Z ? d.Z - 1 : st_i - 1;
-                if (st_i > 0) {
-                    l2_prefetch_tile(stash_t + (size_t)zn * (TILE / 2));
-                    l2_prefetch_roi(Oplane + (size_t)zn * plane, cy, cx, d.Nox);
-                }
-                if (st_i < d.Z) fft2_R_to_F(v, s.E, s.tw, g);
-                if (st_i == d.Z) {
-                    const float4* __restrict__ ff = reinterpret_cast<const float4*>(a.farF) + (((size_t)b * d.M + m) * d.P + p) * (TILE / 2) + g.t;
+        const size_t tile = ((size_t)b * d.P + p) * d.M + m;
+        const float4* stash_t = reinterpret_cast<const float4*>(a.f.stash) + tile * d.Z * (TILE / 2);
+        float2 v[32];
+        for (int st_i = d.Z; st_i >= 0; --st_i) {
+            if (st_i == 0 && !want_probe_fft) break;
+            // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
+            const int zn = st_i == d.Z ? d.Z - 1 : st_i - 1;
+            if (st_i > 0) {
+                l2_prefetch_tile(stash_t + (size_t)zn * (TILE / 2));
+                l2_prefetch_roi(Oplane + (size_t)zn * plane, cy, cx, d.Nox);
+            }
+            if (st_i < d.Z) fft2_R_to_F(v, s.E, s.tw, g);
+            if (st_i == d.Z) {
+                const float4* __restrict__ ff = reinterpret_cast<const float4*>(a.farF) + (((size_t)b * d.M + m) * d.P + p) * (TILE / 2) + g.t;
 #pragma unroll
-                    for (int j0 = 0; j0 < 16; j0 += CH2) {
-                        float4 f[CH2];
+                for (int j0 = 0; j0 < 16; j0 += CH2) {
+                    float4 f[CH2];
 #pragma unroll
-                        for (int i = 0; i < CH2; ++i) f[i] = __ldg(ff + (j0 + i) * 512);
+                    for (int i = 0; i < CH2; ++i) f[i] = __ldg(ff + (j0 + i) * 512);
 #pragma unroll
-                        for (int i = 0; i < CH2; ++i) {
-                            const int u = 2 * (j0 + i);
-                            v[u] = cscale(lo2(f[i]), gsc * __ldg(Grow + ((g.kx(u) + 64) & 127)));
-                            v[u + 1] = cscale(hi2(f[i]), gsc * __ldg(Grow + ((g.kx(u + 1) + 64) & 127)));
-                        }
+                    for (int i = 0; i < CH2; ++i) {
+                        const int u = 2 * (j0 + i);
+                        v[u] = cscale(lo2(f[i]), gsc * __ldg(Grow + ((g.kx(u) + 64) & 127)));
+                        v[u + 1] = cscale(hi2(f[i]), gsc * __ldg(Grow + ((g.kx(u + 1) + 64) & 127)));
                     }
-                } else if (st_i >= 1) {
-                    const float4* __restrict__ hf = reinterpret_cast<const float4*>(a.HF) + g.t;
-                    const float4* __restrict__ ph = a.need_prop ? reinterpret_cast<const float4*>(a.phisF) + (tile * (d.Z - 1) + (st_i - 1)) * (TILE / 2) + g.t : nullptr;
-                    const float Ky = a.need_prop ? kgrid(g.ky, 128, a.dx) : 0.f;
+                }
+            } else if (st_i >= 1) {
+                const float4* __restrict__ hf = reinterpret_cast<const float4*>(a.HF) + g.t;
+                const float4* __restrict__ ph = PROP ? reinterpret_cast<const float4*>(a.phisF) + (tile * (d.Z - 1) + (st_i - 1)) * (TILE / 2) + g.t : nullptr;
+                const float Ky = PROP ? kgrid(g.ky, 128, a.dx) : 0.f;
 #pragma unroll
-                    for (int j0 = 0; j0 < 16; j0 += CH2) {
-                        float4 h[CH2], phi[CH2];
+                for (int j0 = 0; j0 < 16; j0 += CH2) {
+                    float4 h[CH2], phi[CH2];
 #pragma unroll
-                        for (int i = 0; i < CH2; ++i) { h[i] = __ldg(hf + (j0 + i) * 512); if (ph) phi[i] = __ldg(ph + (j0 + i) * 512); }
+                    for (int i = 0; i < CH2; ++i) { h[i] = __ldg(hf + (j0 + i) * 512); if (PROP) phi[i] = __ldg(ph + (j0 + i) * 512); }
 #pragma unroll
-                        for (int i = 0; i < CH2; ++i) {
+                    for (int i = 0; i < CH2; ++i) {
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int u = 2 * (j0 + i) + e;
-                                float2 hh = e ? hi2(h[i]) : lo2(h[i]);
-                                if (tilt) hh = cmul(hh, cmul(eyv, s.ex[g.kx(u)]));
-                                v[u] = cmulc(v[u], hh);              // conj(H)/N^2 * F2(gpsi)
-                                if (ph) {
-                                    const float2 pz = e ? hi2(phi[i]) : lo2(phi[i]);
-                                    const float sv = pz.x * v[u].y - pz.y * v[u].x;
-                                    const float Kx = kgrid(g.kx(u), 128, a.dx);
-                                    const float k2 = Kx * Kx + Ky * Ky;
-                                    s3[0] += Ky * sv; s3[1] += Kx * sv; s3[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
-                                }
+                        for (int e = 0; e < 2; ++e) {
+                            const int u = 2 * (j0 + i) + e;
+                            float2 hh = e ? hi2(h[i]) : lo2(h[i]);
+                            if (TILT) hh = cmul(hh, cmul(eyv, s.ex[g.kx(u)]));
+                            v[u] = cmulc(v[u], hh);              // conj(H)/N^2 * F2(gpsi)
+                            if (PROP) {
+                                const float2 pz = e ? hi2(phi[i]) : lo2(phi[i]);
+                                const float sv = pz.x * v[u].y - pz.y * v[u].x;
+                                const float Kx = kgrid(g.kx(u), 128, a.dx);
+                                const float k2 = Kx * Kx + Ky * Ky;
+                                s3[0] += Ky * sv; s3[1] += Kx * sv; s3[2] += -k2 / (sqrtf(a.k0 * a.k0 - k2) + a.k0) * sv;
                             }
                         }
                     }
-                } else {
-                    // st_i == 0: v = N^2 T of gpsi_0 (shifted probes): probe-spectrum and shift gradients
-                    const float4* __restrict__ phf = reinterpret_cast<const float4*>(a.PhatF) + (size_t)p * (TILE / 2) + g.t;   // Phat / N^2
-                    float4* __restrict__ gp = reinterpret_cast<float4*>(a.gPhatF) + (size_t)p * (TILE / 2) + g.t;
-                    const float2 wyv = s.wy[g.ky];
-                    const float kapy = float((g.ky + 64) & 127) * (1.0f / 128.0f);
-                    const float invN2 = 1.0f / (128.0f * 128.0f);
-                    float r2[2] = {0.f, 0.f};
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float4 pq = __ldg(phf + j * 512);
-                        float2 cw[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int u = 2 * j + e;
-                            const float2 w = cmul(wyv, s.wx[g.kx(u)]);
-                            cw[e] = cmulc(v[u], w);                              // conj(w') * N^2 T
-                            const float2 pv = e ? hi2(pq) : lo2(pq);
-                            const float qv = cw[e].y * pv.x - cw[e].x * pv.y;    // Im(conj(w') T conj(Phat))
-                            r2[0] += kapy * qv;
-                            r2[1] += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
-                        }
-                        if (a.need_probe) red_f4(gp + j * 512, cscale(cw[0], invN2), cscale(cw[1], invN2));
-                    }
-                    if (a.need_shift) {
-                        block_sum<2>(r2, s.red);
-                        if (threadIdx.x == 0) {
-                            atomicAdd(a.gshift + 2 * n0 + 0, -6.283185307179586f * r2[0]);
-                            atomicAdd(a.gshift + 2 * n0 + 1, -6.283185307179586f * r2[1]);
-                        }
-                    }
-                    break;
                 }
-                fft2_F_to_R(v, s.E, s.tw, g);                                   // gphi_{zn}
-                {
-                    const float4* st = stash_t + (size_t)zn * (TILE / 2) + stash_index(g.t, 0);
-                    const float4* Oz = Oplane + (size_t)zn * plane + roi0;
-                    float4* gOz = a.gOpack + ((size_t)obj_mode(d, b, m) * d.Z + zn) * plane + roi0;
-                    float4* ac = ACC ? accb + (size_t)zn * (TILE / 2) : nullptr;
-                    if (ACC) {
-                        switch (mode) {
-                            case 0: accum_phase<0>(v, st, Oz, ostr, ac, gOz); break;
-                            case 1: accum_phase<1>(v, st, Oz, ostr, ac, gOz); break;
-                            case 2: accum_phase<2>(v, st, Oz, ostr, ac, gOz); break;
-                            case 3: accum_phase<3>(v, st, Oz, ostr, ac, gOz); break;
-                            default: accum_phase<4>(v, st, Oz, ostr, ac, gOz); break;
-                        }
-                    } else {
-#if F128_TMA_RED       // measured slower than LSU reds on B200 (1.85 vs 1.67 ms per C2 batch): kept for reference
-                        float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
-                        accum_phase_tma(v, st, Oz, ostr, gOz - (g.x & 31), sw, g.lane, mode == 3);
-#else
-                        if (mode == 3) accum_phase<3>(v, st, Oz, ostr, ac, gOz);
-                        else accum_phase<4>(v, st, Oz, ostr, ac, gOz);
-#endif
+            } else {
+                // st_i == 0: v = N^2 T of gpsi_0 (shifted probes): probe-spectrum and shift gradients
+                const float4* __restrict__ phf = reinterpret_cast<const float4*>(a.PhatF) + (size_t)p * (TILE / 2) + g.t;   // Phat / N^2
+                float4* __restrict__ gp = reinterpret_cast<float4*>(a.gPhatF) + (size_t)p * (TILE / 2) + g.t;
+                const float2 wyv = s.wy[g.ky];
+                const float kapy = float((g.ky + 64) & 127) * (1.0f / 128.0f);
+                const float invN2 = 1.0f / (128.0f * 128.0f);
+                float r2[2] = {0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 pq = __ldg(phf + j * 512);
+                    float2 cw[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int u = 2 * j + e;
+                        const float2 w = cmul(wyv, s.wx[g.kx(u)]);
+                        cw[e] = cmulc(v[u], w);                              // conj(w') * N^2 T
+                        const float2 pv = e ? hi2(pq) : lo2(pq);
+                        const float qv = cw[e].y * pv.x - cw[e].x * pv.y;    // Im(conj(w') T conj(Phat))
+                        r2[0] += kapy * qv;
+                        r2[1] += float((g.kx(u) + 64) & 127) * (1.0f / 128.0f) * qv;
+                    }
+                    if (a.need_probe) red_f4(gp + j * 512, cscale(cw[0], invN2), cscale(cw[1], invN2));
+                }
+                if (a.need_shift) {
+                    block_sum<2>(r2, s.red);
+                    if (threadIdx.x == 0) {
+                        atomicAdd(a.gshift + 2 * n0 + 0, -6.283185307179586f * r2[0]);
+                        atomicAdd(a.gshift + 2 * n0 + 1, -6.283185307179586f * r2[1]);
                     }
                 }
+                break;
             }
-            if (!a.shift && a.need_probe) {               // unshifted probes: g_probe += gpsi_0 (natural layout)
-                float2* gp = a.gprobe + (size_t)p * TILE + tR;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) red_f2(gp + k * 512, v[k]);
+            fft2_F_to_R(v, s.E, s.tw, g);                                   // gphi_{zn}
+            {
+                const float4* st = stash_t + (size_t)zn * (TILE / 2) + stash_index(g.t, 0);
+                const float4* Oz = Oplane + (size_t)zn * plane + roi0;
+                float4* gOz = a.gOpack + ((size_t)obj_mode(d, b, m) * d.Z + zn) * plane + roi0;
+#if F128_TMA_RED       // measured slower than LSU reds on B200 (1.85 vs 1.67 ms per C2 batch): kept for reference
+                float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
+                accum_phase_tma(v, st, Oz, ostr, gOz - (g.x & 31), sw, g.lane, a.need_obj != 0);
+#else
+                if (a.need_obj) accum_phase<3>(v, st, Oz, ostr, nullptr, gOz);
+                else accum_phase<4>(v, st, Oz, ostr, nullptr, gOz);
+#endif
             }
         }
-        if (a.need_prop) {
+        if (!a.shift && a.need_probe) {               // unshifted probes: g_probe += gpsi_0 (natural layout)
+            float2* gp = a.gprobe + (size_t)p * TILE + tR;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) red_f2(gp + k * 512, v[k]);
+        }
+        if (PROP) {
             block_sum<3>(s3, s.red);
             if (threadIdx.x == 0) {
                 atomicAdd(a.gprop + 3 * b + 0, s3[0]);
@@ -699,10 +680,8 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-constexpr int MAX_SLOTS = 148;
-
 struct Scratch {
-    float2 *HF, *PhatF, *gPhatF, *acc, *farF;
+    float2 *HF, *PhatF, *gPhatF, *farF;
     float4 *Opack, *gOpack;
     float* Ipart;
     size_t total;
@@ -712,7 +691,6 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base + o; };
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-    const bool acc_mode = (c.reserved[0] & 1) != 0;
     s.HF = (float2*)take((size_t)TILE * 8);
     s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
@@ -720,7 +698,6 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     s.gOpack = (float4*)take(obj * 16);
     s.Ipart = (float*)take((size_t)B * c.M * c.P * TILE * 4);
     s.farF = (float2*)take((size_t)B * c.M * c.P * TILE * 8);
-    s.acc = (float2*)take(acc_mode ? (size_t)MAX_SLOTS * c.Z * TILE * 8 : 0);
     s.total = off;
     return s;
 }
@@ -738,7 +715,7 @@ inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc,
     memset(&a, 0, sizeof a);
     a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.Ipart = sc.Ipart; a.farF = sc.farF; a.phisF = f.phis ? phis : nullptr;
     a.Opack = sc.Opack; a.gOpack = sc.gOpack;
-    a.gPhatF = sc.gPhatF; a.acc = sc.acc; a.shift = c.shift_probes;
+    a.gPhatF = sc.gPhatF; a.shift = c.shift_probes;
     return a;
 }
 
@@ -757,8 +734,16 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
         k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(f.PhatT, sc.PhatF, inv);
         F128_CK(cudaGetLastError()); ++*launches;
     }
-    F128_CK(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_FWD));
-    k_forward<<<dim3(c.P, c.M, B), FT, SMEM_BYTES_FWD, st>>>(a);
+    const dim3 grid(c.P, c.M, B);
+    const bool tilt = f.tvec != nullptr, phis = a.phisF != nullptr;
+#define F128_LAUNCH_FWD(T, PH)                                                                                                     \
+    do {                                                                                                                           \
+        F128_CK(cudaFuncSetAttribute(k_forward<T, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_FWD));         \
+        k_forward<T, PH><<<grid, FT, SMEM_BYTES_FWD, st>>>(a);                                                                     \
+    } while (0)
+    if (tilt) { if (phis) F128_LAUNCH_FWD(true, true); else F128_LAUNCH_FWD(true, false); }
+    else      { if (phis) F128_LAUNCH_FWD(false, true); else F128_LAUNCH_FWD(false, false); }
+#undef F128_LAUNCH_FWD
     F128_CK(cudaGetLastError()); ++*launches;
     k_dp_reduce<<<dim3(TILE / 256, B), 256, 0, st>>>(sc.Ipart, f.dp, c.M * c.P, c.eps);
     F128_CK(cudaGetLastError()); ++*launches;
@@ -774,27 +759,23 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
     a.G = bw.G; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
     a.dx = bw.dx; a.k0 = bw.k0;
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
-    const bool acc_mode = (c.reserved[0] & 1) != 0;     // experimental: accumulate over probe modes before scattering
-    a.units = acc_mode ? B * c.M : B * c.M * c.P;
-    a.direct_red = acc_mode ? 0 : 1;
+    a.units = B * c.M * c.P;
+    a.direct_red = 1;
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     if (a.need_obj) F128_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
     if (a.need_probe) {
         if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
         else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
     }
-    int dev = 0, sms = MAX_SLOTS;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (acc_mode) {
-        int grid = a.units < sms ? a.units : sms;
-        if (grid > MAX_SLOTS) grid = MAX_SLOTS;
-        F128_CK(cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));
-        k_backward<true><<<grid, FT, SMEM_BYTES_BWD, st>>>(a);
-    } else {
-        F128_CK(cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));
-        k_backward<false><<<a.units, FT, SMEM_BYTES_BWD, st>>>(a);
-    }
+    const bool tilt = bw.f.tvec != nullptr, prop = a.need_prop != 0;
+#define F128_LAUNCH_BWD(T, PR)                                                                                                     \
+    do {                                                                                                                           \
+        F128_CK(cudaFuncSetAttribute(k_backward<T, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));        \
+        k_backward<T, PR><<<a.units, FT, SMEM_BYTES_BWD, st>>>(a);                                                                 \
+    } while (0)
+    if (tilt) { if (prop) F128_LAUNCH_BWD(true, true); else F128_LAUNCH_BWD(true, false); }
+    else      { if (prop) F128_LAUNCH_BWD(false, true); else F128_LAUNCH_BWD(false, false); }
+#undef F128_LAUNCH_BWD
     F128_CK(cudaGetLastError()); ++*launches;
     if (a.need_probe && c.shift_probes) {
         k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
