@@ -229,7 +229,10 @@ template <class F> int backward_general(const ptyb200_cfg& c, int B, const Works
             int out_mode = 0;
             if (z == 0) out_mode = want_p ? (c.shift_probes ? 0 : 1) : 2;
             LAUNCH((k_bwd_da<F>), grid, st, a, z, out_mode);
-            if (z > 0) LAUNCH((k_bwd_bc<F>), grid, st, a, z);
+            if (z > 0) {
+                if (a.need_prop) LAUNCH((k_bwd_bc<F, true>), grid, st, a, z);
+                else LAUNCH((k_bwd_bc<F, false>), grid, st, a, z);
+            }
         }
         if (want_p) {                                     // gpsi_0 of this chunk is in G1
             if (c.shift_probes) {

@@ -633,8 +633,8 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
 }
 
 // grid (N/ROWS, M*groups, chunk), z >= 1: G1 -> forward-y -> *conj(H_n) [+ propagator-gradient sums vs Phi_{z-1}] -> inverse-y -> G2
-// (three register stages like k_fwd_bc)
-template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bwd_bc(BwdArgs a, int z) {
+// (three register stages like k_fwd_bc; PROP is compile-time so that the plain adjoint carries no per-element branches)
+template <class F, bool PROP> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bwd_bc(BwdArgs a, int z) {
     PTYB_SMEM_CARVE(F)
     constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
@@ -650,7 +650,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bw
     const float Kx = kgrid(kx0 + r, N, a.dx);
     const float invN2 = 1.0f / (float(N) * float(N));
     float* kyS = fbuf;                                       // Ky[ky] (propagator gradients only); Kz - k0 is formed on the fly so
-    if (a.need_prop) {                                       // that the registers can hold the Fourier stash loaded ahead of the DFT
+    if (PROP) {                                              // that the registers can hold the Fourier stash loaded ahead of the DFT
         for (int n = threadIdx.x; n < N; n += NT) kyS[n] = kgrid(n, N, a.dx);
         __syncthreads();
     }
@@ -660,7 +660,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bw
         const float2* src = a.f.G1 + ltile * N * N;
         if (p + 1 < un.p_hi) {
             prefetch_slab<N>(src + (size_t)d.M * N * N, kx0);
-            if (a.need_prop) prefetch_slab<N>(a.f.phis + ((tile + d.M) * (d.Z - 1) + (z - 1)) * N * N, kx0);
+            if (PROP) prefetch_slab<N>(a.f.phis + ((tile + d.M) * (d.Z - 1) + (z - 1)) * N * N, kx0);
         }
         if (itemA) {
             float2 v[N1];
@@ -672,9 +672,9 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bw
         __syncthreads();
         if (itemB) {
             float2* row = slab + r * F::RS;
-            const float2* ph = a.need_prop ? a.f.phis + (tile * (d.Z - 1) + (z - 1)) * N * N + (size_t)(kx0 + r) * N + k1 : nullptr;
+            const float2* ph = PROP ? a.f.phis + (tile * (d.Z - 1) + (z - 1)) * N * N + (size_t)(kx0 + r) * N + k1 : nullptr;
             float2 v[N2], phi[N2];
-            if (ph) {                                                        // issued before the DFT: latency hidden behind it
+            if (PROP) {                                                      // issued before the DFT: latency hidden behind it
 #pragma unroll
                 for (int k2 = 0; k2 < N2; ++k2) phi[k2] = ld_stream(ph + N1 * k2);
             }
@@ -684,7 +684,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bw
 #pragma unroll
             for (int k2 = 0; k2 < N2; ++k2) {
                 v[k2] = cmulc(v[k2], Hreg[k2]);                              // conj(H) * F2(gpsi)
-                if (ph) {
+                if (PROP) {
                     const float sv = (phi[k2].x * v[k2].y - phi[k2].y * v[k2].x) * invN2;   // Im(conj(Phi) * v) / N^2
                     const float Ky = kyS[k1 + N1 * k2];
                     const float kk = Kx * Kx + Ky * Ky;
@@ -706,7 +706,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_bw
         }
         __syncthreads();
     }
-    if (a.need_prop) {
+    if (PROP) {
         block_sum<3>(s3, red);
         if (threadIdx.x == 0) {
             atomicAdd(a.gprop + 3 * b + 0, s3[0]);
