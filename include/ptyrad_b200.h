@@ -113,7 +113,8 @@ int ptyb200_forward(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const
  * a forward on the same workspace with the same inputs.  G = dL/d(dp) (B,N,N).  Gradient outputs are DENSE
  * and are OVERWRITTEN (zero-filled where no pattern contributes), as the reference's .grad tensors are:
  *   g_obja,g_objp (M,Z,Noy,Nox); g_probe (P,N,N) float2; g_shifts (Ntot,2); g_tilts (1|Ntot,2); g_dz scalar.
- * Outputs whose bit is absent from need_mask may be NULL and cost nothing. */
+ * Outputs whose bit is absent from need_mask may be NULL and cost nothing.  Alignment: g_obja, g_objp, g_probe 16 bytes,
+ * g_shifts, g_tilts 8 bytes (vector stores / reductions); a misaligned pointer is refused with an error. */
 int ptyb200_backward(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const float* obja, const float* objp,
                      const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
                      const float* tilts, const float* dz, const float* occu, const float* G, void* workspace,

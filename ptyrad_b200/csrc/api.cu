@@ -356,6 +356,10 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (need_t && (!g_tilts || !c->tilt_mode)) return fail_msg("tilt gradient requested without tilts");
     if (need_dz && !g_dz) return fail_msg("g_dz is NULL");
     if (a.need_prop && !c->stash_fourier) return fail_msg("tilt/thickness gradients need cfg.stash_fourier = 1 in the forward");
+    // the kernels write gradients with 8- and 16-byte vector accesses
+    auto misaligned = [](const void* p, size_t al) { return p && (reinterpret_cast<uintptr_t>(p) & (al - 1)) != 0; };
+    if (misaligned(g_obja, 16) || misaligned(g_objp, 16) || misaligned(g_probe, 16) || misaligned(g_shifts, 8) || misaligned(g_tilts, 8))
+        return fail_msg("gradient buffers must be 16-byte aligned (g_shifts / g_tilts: 8-byte)");
     const size_t obj = (size_t)((c->reserved[1] & 1) ? B : 1) * c->M * c->Z * c->Noy * c->Nox;
     if (a.need_obj && !use_fused(*c)) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
     if (a.need_probe && c->shift_probes) CK(cudaMemsetAsync(w.gPhatT, 0, (size_t)c->P * c->N * c->N * 8, st));

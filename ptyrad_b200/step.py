@@ -12,23 +12,29 @@ are never broadcast.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from .losses import MeasurementView
+from . import _lib, engine
+from ._lib import ptr
+from .losses import CombinedLoss, MeasurementView
 
 
 class GradArena:
     def __init__(self, model):
         self.params = [p for g in model.optimizable_params for p in g["params"]]
-        n = sum(p.numel() for p in self.params)
+        # every view starts on a 256-byte boundary: the kernels write gradients with 8- and 16-byte vector accesses
+        A = 64
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + A - 1) // A * A
         dev = self.params[0].device if self.params else "cpu"
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.views, off = [], 0
-        for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view(p.shape))
-            off += p.numel()
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
         self.attach()
 
     def attach(self):
@@ -56,10 +62,114 @@ def shard_indices(indices, rank: int, world: int):
     return np.array_split(np.asarray(indices), world)[rank]
 
 
+def direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements) -> bool:
+    """The autograd-free step covers the default configuration: native loss terms only, no blur / pad / resample options,
+    gradients written once into the arena (no accumulation over batches)."""
+    if arena is None or grad_accumulation != 1 or not do_step or not torch.is_grad_enabled():
+        return False
+    if type(loss_fn) is not CombinedLoss or loss_fn.loss_params["loss_simlar"]["state"]:
+        return False
+    lp = loss_fn.loss_params
+    if not (lp["loss_single"]["state"] or lp["loss_poissn"]["state"] or lp["loss_pacbed"]["state"]):
+        return False
+    if model.obj_preblur_std or model.detector_blur_std:
+        return False
+    if measurements is None and (model.meas_padded is not None or model.meas_scale_factors is not None):
+        return False
+    if measurements is not None and not isinstance(measurements, MeasurementView):
+        return False
+    return True
+
+
+def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
+    """Forward, loss, loss gradient and adjoint through the C ABI with the gradient tensors of the arena as the kernels' output
+    buffers -- what ``model(idx)`` -> ``loss_fn`` -> ``backward()`` computes (engine.MultisliceFunction / DataLossFunction /
+    SparseLossFunction), minus the autograd graph, its ~30 small elementwise launches per step and the accumulate-into-.grad copies.
+    Returns the five loss terms as one device tensor."""
+    lib = _lib.lib()
+    st = engine._stream()
+    dev = model.opt_obja.device
+    B = idx.numel()
+    obja, objp, probe = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous(), model.opt_probe.data.contiguous()
+    tilts, dz, shifts = model.opt_obj_tilts.data.contiguous(), model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
+    Z = obja.shape[1]
+    n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
+    n_probe = model.opt_probe.requires_grad
+    n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
+    n_tilts = model.opt_obj_tilts.requires_grad and model.tilt_obj and Z > 1
+    n_dz = model.opt_slice_thickness.requires_grad and model.change_thickness and Z > 1
+    need_prop = (model.opt_obj_tilts.requires_grad and model.tilt_obj) or (model.opt_slice_thickness.requires_grad and model.change_thickness)
+    cfg = model._cfg(stash_fourier=bool(need_prop))
+    Hbase = engine.propagator(cfg, dz) if model.change_thickness else model.H
+    ws_bytes = lib.ptyb200_workspace_bytes(C.byref(cfg), B)
+    if ws_bytes == 0:
+        _lib.check(1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
+    tl = tilts if cfg.tilt_mode else None
+    sh = shifts if cfg.shift_probes else None
+    _lib.check(lib.ptyb200_forward(C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
+                                   ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws), st))
+    # losses: [single, poissn, pacbed] and [sparse] land in one (5,) tensor; simlar (slot 4) is off on this path
+    lcfg = loss_fn._lcfg
+    losses = torch.zeros(5, dtype=torch.float32, device=dev)
+    stats = torch.empty(8, dtype=torch.float64, device=dev)
+    pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
+    _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
+                                        ptr(pac), st))
+    sparse = bool(lcfg.sparse_state)
+    if sparse:
+        Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
+        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
+        _lib.check(lib.ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                              C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), st))
+    need = ((_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0) |
+            (_lib.NEED_TILTS if n_tilts else 0) | (_lib.NEED_DZ if n_dz else 0))
+    if need:
+        ones = getattr(model, "_ones3", None)                 # d(total)/d(term) = 1 for every term: total is their plain sum
+        if ones is None or ones.device != dev:
+            ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
+        G = torch.empty_like(dp)
+        _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(stats), ptr(pac),
+                                         ptr(ones), ptr(G), st))
+
+        def out(p, wanted):                                   # the arena view of a live parameter, scratch for a frozen one
+            if not wanted:
+                return None
+            return p.grad if p.requires_grad else torch.empty_like(p.data)
+
+        g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
+        _lib.check(lib.ptyb200_backward(
+            C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
+            ptr(model.omode_occu), ptr(G), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(out(model.opt_probe, n_probe)),
+            ptr(out(model.opt_probe_pos_shifts, n_shifts)), ptr(out(model.opt_obj_tilts, n_tilts)),
+            ptr(out(model.opt_slice_thickness, n_dz)), need, st))
+        if sparse and model.opt_objp.requires_grad:
+            _lib.check(lib.ptyb200_sparse_grad(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                               ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), st))
+    elif sparse and model.opt_objp.requires_grad:
+        raise RuntimeError("unreachable: objp.requires_grad implies NEED_OBJ")
+    return losses
+
+
 def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = None, world: int = 1,
-                grad_accumulation: int = 1, do_step: bool = True, measurements=None):
+                grad_accumulation: int = 1, do_step: bool = True, measurements=None, direct: bool | None = None):
     """One batch: zero grads, forward, loss, backward, (all-reduce), optimizer step.  Returns the 5 loss terms as a device
-    tensor (no host sync)."""
+    tensor (no host sync).  `direct` (default: whenever eligible) takes the autograd-free route of `_direct_grads`."""
+    if direct is None:
+        direct = direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements)
+    elif direct and not direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements):
+        raise ValueError("this configuration needs the autograd path (direct=False)")
+    if direct:
+        arena.attach()
+        arena.zero()
+        idx = model._index_tensor(indices)
+        meas = measurements if measurements is not None else MeasurementView(model.measurements, idx)
+        losses = _direct_grads(model, loss_fn, idx, meas, arena)
+        if world > 1:
+            arena.allreduce(world)
+        optimizer.step()
+        return losses
     if arena is not None:
         arena.attach()
         arena.zero()
@@ -226,6 +336,9 @@ def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint
         g = graphed.get(len(mine)) if (graphed and grad_accumulation == 1) else None
         if g is not None:
             per_batch.append(g(mine).clone())
+            continue
+        if grad_accumulation == 1 and direct_step_eligible(model, loss_fn, arena, 1, True, None):
+            per_batch.append(recon_batch(model, loss_fn, optimizer, mine, arena, world))      # autograd-free step
             continue
         dp = model(mine)
         idx = model._index_tensor(mine)

@@ -126,7 +126,7 @@ def test_general_path_chunked_batches(cfg_name, chunk, pg):
     _check(r, ref["dp"], ref["losses"], ref["grads"], f"{cfg_name}/chunk{chunk}/pg{pg}")
     assert np.array_equal(r["dp"], one["dp"])          # the forward does not depend on the cut
     for k, g in one["grads"].items():
-        assert rel(r["grads"][k], g) < (2e-6 if k in ("obja", "objp", "probe") else 5e-5), k   # only the order of the atomic sums changes
+        assert rel(r["grads"][k], g) < (2e-6 if k in ("obja", "objp", "probe") else 2e-4), k   # only the order of the atomic sums changes
 
 
 def test_general_path_unshifted_probe_chunked():
@@ -141,6 +141,48 @@ def test_general_path_unshifted_probe_chunked():
     ref = oracle_step(iv, mp, lp, idx, torch.float64)
     r = _run(iv, mp, lp, idx, path=_lib.PATH_GENERAL, chunk=3, pmodes_per_cta=1)
     _check(r, ref["dp"], ref["losses"], ref["grads"], "T64/noshift/chunk3")
+
+
+@pytest.mark.parametrize("case", ["T128", "T64+tilt+dz", "T192", "T64-frozen-probe", "T128m-pacbed"])
+def test_direct_step_matches_autograd_step(case):
+    """recon_batch's autograd-free route (kernels write straight into the gradient arena) against the autograd route
+    (PtychoAD.forward -> CombinedLoss -> backward): same losses, same gradients, same parameters after the Adam step."""
+    from dataclasses import replace
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, recon_batch, direct_step_eligible
+    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    name = case.split("+")[0].split("-")[0]
+    cfg = CONFIGS[name]
+    if "tilt" in case:
+        cfg = replace(cfg, tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4)
+    iv, mp, lp = make_inputs(cfg, seed=17)
+    if "pacbed" in case:
+        lp["loss_pacbed"]["state"] = True
+        lp["loss_single"]["state"] = True
+    idx = np.arange(cfg.batch, dtype=np.int64)
+    out = {}
+    for direct in (False, True):
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        if "frozen" in case:
+            model.opt_probe.requires_grad = False
+            model.opt_obja.requires_grad = False
+        loss_fn = CombinedLoss(lp, device="cuda")
+        opt = FusedAdam(model.optimizable_params)
+        arena = GradArena(model)
+        assert direct_step_eligible(model, loss_fn, arena, 1, True, None)
+        losses = recon_batch(model, loss_fn, opt, idx, arena, direct=direct)
+        torch.cuda.synchronize()
+        out[direct] = (losses.cpu().numpy(), {k: (None if t.grad is None else t.grad.detach().cpu().numpy().copy()) for k, t in model.optimizable_tensors.items()},
+                       {k: t.detach().cpu().numpy().copy() for k, t in model.optimizable_tensors.items()})
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-6, atol=1e-9)
+    for k, g in out[False][1].items():
+        if g is None:
+            assert out[True][1][k] is None, k
+        else:
+            assert rel(out[True][1][k], g) < (2e-6 if k in ("obja", "objp", "probe") else 2e-4), k   # run-to-run atomics noise
+    for k, v in out[False][2].items():
+        assert rel(out[True][2][k], v) < 1e-6, k
 
 
 def test_tilt_and_thickness_gradients():
