@@ -568,11 +568,11 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
     const int r = threadIdx.x / N2, j = threadIdx.x % N2;
     const int rC = threadIdx.x % ROWS, k1C = threadIdx.x / ROWS;
     const size_t roi = (size_t)(cy + y0 + r) * d.Nox + cx + j;
-    float2 Oreg[N1], accO[N1];
-    if (itemB) {
+    // register budget of stage B (128): accO + the stash values requested ahead of the DFT + the DFT's own array; O_z is re-read
+    // per probe mode instead of being cached in registers -- its 32 KB slab stays in L1 because the streaming tiles bypass L1 (ld.cg)
+    float2 accO[N1];
 #pragma unroll
-        for (int k = 0; k < N1; ++k) { Oreg[k] = Oz[roi + N2 * k]; accO[k] = make_float2(0.f, 0.f); }
-    }
+    for (int k = 0; k < N1; ++k) accO[k] = make_float2(0.f, 0.f);
     for (int p = un.p_lo; p < un.p_hi; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const size_t ltile = ((size_t)un.bl * d.P + p) * d.M + m;
@@ -586,14 +586,19 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
             float2 v[N2];
             const float2* sp = src + (size_t)(y0 + rA) * N + k1A;
 #pragma unroll
-            for (int k2 = 0; k2 < N2; ++k2) v[k2] = sp[N1 * k2];
+            for (int k2 = 0; k2 < N2; ++k2) v[k2] = __ldcg(sp + N1 * k2);
             F::inv_stage2_regs(slab + rA * F::RS, k1A, v, twN);
+        }
+        float2 psi[N1];
+        if (itemB) {                                           // requested ahead of the barrier and the DFT: latency hidden
+            const float2* st = stt + (size_t)(y0 + r) * N + j;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) psi[k] = __ldcg(st + N2 * k);
         }
         __syncthreads();
         float2* dst = a.f.G1 + ltile * N * N;
         if (itemB) {
             float2* row = slab + r * F::RS;
-            const float2* st = stt + (size_t)(y0 + r) * N + j;
             float2 v[N1];
 #pragma unroll
             for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[F::addr(j + N2 * k1)];
@@ -601,8 +606,8 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
 #pragma unroll
             for (int k = 0; k < N1; ++k) {
                 const float2 gphi = cscale(v[k], 1.0f / N);
-                accO[k] = cadd(accO[k], cmulc(gphi, ld_stream(st + N2 * k)));   // conj(psi) * gphi
-                v[k] = cmulc(gphi, Oreg[k]);                                // conj(O) * gphi
+                accO[k] = cadd(accO[k], cmulc(gphi, psi[k]));               // conj(psi) * gphi
+                v[k] = cmulc(gphi, __ldg(Oz + roi + N2 * k));               // conj(O) * gphi
             }
             if (out_mode == 0) {
                 Dft<N1, -1>::run(v);
@@ -833,7 +838,15 @@ struct LossK {
     float s_w, s_p, p_w, p_p, p_eps, b_w, b_p;
 };
 
-__device__ __forceinline__ float powp(float x, float p) { return p == 0.5f ? sqrtf(x) : (p == 1.0f ? x : powf(x, p)); }
+// x^p with the exponents the loss terms actually use evaluated exactly-rounded and cheaply (dp_pow = 0.5 and 1 and their
+// derivative exponents -0.5 and 0; powf costs ~10x more and is kept for everything else)
+__device__ __forceinline__ float powp(float x, float p) {
+    if (p == 0.5f) return sqrtf(x);
+    if (p == 1.0f) return x;
+    if (p == -0.5f) return 1.0f / sqrtf(x);
+    if (p == 0.0f) return 1.0f;
+    return powf(x, p);
+}
 
 // stats: [0] sum (I^p-M^p)^2  [1] sum M^p  [2] sum (M^q log(I^q+e) - I^q)  [3] sum M^q  [4] sum M^r  [5] sum (Ibar^r - Mbar^r)^2
 // grid (chunks, B): block (c, b) handles a contiguous chunk of pattern b
