@@ -1,4 +1,4 @@
-// General multislice path: every 2-D FFT is two row passes over 16-row slabs held in shared memory, each
+// General multislice path: every 2-D FFT is two row passes over ROWS-row slabs (8 rows) held in shared memory, each
 // pass writing its result transposed, with the pointwise physics fused into the passes:
 //
 //   forward, per slice z      DA: (inverse-x) -> psi_z -> stash, *O_z (ROI gather), forward-x  -> G1 (transposed)
@@ -9,7 +9,7 @@
 //                                   registers, one red.global per pixel), gpsi = conj(O_z) gphi, forward-x -> G1
 //                             BC^H: forward-y, *conj(H_n) [+ tilt/thickness sums], inverse-y     -> G2
 //
-// A CTA owns (sample, object mode, probe-mode group, 16-row slab) and loops over the probe modes of its group, so the O_z ROI,
+// A CTA owns (sample, object mode, probe-mode group, ROWS-row slab) and loops over the probe modes of its group, so the O_z ROI,
 // the propagator values and the object-gradient accumulators live in registers across the loop.
 // The host can run the slice sequence on CHUNKS of the batch (api.cu: gen_plan; default one chunk): the pass buffers G1/G2 hold only
 // the chunk's tiles.
@@ -20,15 +20,18 @@
 
 namespace ptyb {
 
-constexpr int ROWS = 16;   // slab height (rows per CTA)
-constexpr int NT = 256;    // threads per CTA
+#ifndef PTYB_ROWS
+#define PTYB_ROWS 8      // 8-row slabs, 128-thread CTAs, 4 (6 for N <= 192) CTAs per SM: finer barriers; measured +3-4 % over 16 rows x 256 threads
+#endif
+constexpr int ROWS = PTYB_ROWS;        // slab height (rows per CTA)
+constexpr int NT = 16 * PTYB_ROWS;     // threads per CTA (one register-stage work item per thread at N = 256)
 #ifndef GEN_MINB
-#define GEN_MINB 2       // minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (256 * GEN_MINB))
+#define GEN_MINB (2 * 16 / PTYB_ROWS)   // minimum resident CTAs per SM requested from the compiler (register cap 128 per thread)
 #endif
 // the kernels with one cached table (k_fwd_da, k_fwd_bc, k_bwd_bc) fit 3 CTAs per SM (80 registers) without spilling up to N = 192
 // (measured: C5 +14 %); at N = 256 the 80-register build spills and is slower than 2 CTAs per SM (C4 -3 %, C3 -13 %)
 #ifndef GEN_MINB_LIGHT
-#define GEN_MINB_LIGHT(F) ((F::N) <= 192 ? 3 : 2)
+#define GEN_MINB_LIGHT(F) (((F::N) <= 192 ? 3 : 2) * 16 / PTYB_ROWS)
 #endif
 
 struct Dims {
@@ -230,7 +233,7 @@ template <class F> struct Slab {
             f(i, e / N, e % N);
         }
     }
-    // transposed ownership: lanes run across the 16 rows (coalesced for arrays indexed [q][row])
+    // transposed ownership: lanes run across the ROWS rows (coalesced for arrays indexed [q][row])
     template <class Fn> __device__ __forceinline__ static void tr(Fn f) {
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -329,7 +332,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_init_shift(
 //   A  item (row r, k1):  X[k1 + N1 k2] straight from global (128-byte segments), inverse DFT over k2, twiddle        -> smem
 //   B  item (row r, j):   inverse DFT over k1 -> psi_z[x = j + N2 k] -> stash, *O_z, forward DFT over k, twiddle     -> smem
 //   C  item (row rr, k1): forward DFT over j -> frequency q = k1 + N1 k2, stored straight to the transposed tile: the lanes run
-//      over the 16 rows of the slab, so each store instruction writes 128-byte segments and the odd row stride keeps the
+//      over the ROWS rows of the slab, so each store instruction writes 8*ROWS-byte segments and the odd row stride keeps the
 //      shared-memory reads conflict free.
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fwd_da(FwdArgs a, int z, int src_mode, int last) {
     PTYB_SMEM_CARVE(F)
