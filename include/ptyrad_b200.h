@@ -144,6 +144,13 @@ int ptyb200_sparse_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, cons
                         const int64_t* idx, int32_t B, const float* occu, const double* Ssum, const float* upstream,
                         const int32_t* cover, float* g_objp, ptyb200_stream s);
 
+/* 5x5 Gaussian blur with reflect padding over the last two dims of `planes` (H,W) float32 planes: what torchvision's
+ * gaussian_blur(kernel_size=5, sigma) computes for the object pre-blur (models.py:275-284), the detector blur (models.py:379-380)
+ * and loss_simlar (losses.py:125,134).  transpose = 1 applies the adjoint operator (the backward pass).  `tmp` is caller-owned
+ * scratch of the same size; in, tmp and out must be distinct. */
+int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t planes, int32_t H, int32_t W, float sigma,
+                           int32_t transpose, ptyb200_stream s);
+
 /* optimizer.step() for torch.optim.Adam defaults (reconstruction.py:759; built at reconstruction.py:285-368):
  * one launch over up to 8 tensors with per-tensor learning rates.  The host arrays of pointers / lrs / numels are read
  * during the call; step_counter is one device int64 that the call increments before use (bias correction), so no

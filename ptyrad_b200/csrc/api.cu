@@ -4,6 +4,7 @@
 #include "general_kernels.cuh"
 #include "fused128.cuh"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -83,7 +84,7 @@ GenPlan gen_plan(const ptyb200_cfg& c, int B) {
     g.chunk = chunk; g.pg = pg; g.groups = (c.P + pg - 1) / pg;
     return g;
 }
-constexpr int kMinCtas = 296;      // 148 SMs x 2 resident CTAs
+constexpr int kProbeCtas = 4 * 148 * 4;   // probe pass: ~4 waves of 148 SMs x 4 resident CTAs, so that no CTA loops over more than B/7 samples
 
 Workspace carve(const ptyb200_cfg& c, int B, void* base) {
     Workspace w;
@@ -237,7 +238,7 @@ template <class F> int backward_general(const ptyb200_cfg& c, int B, const Works
         if (want_p) {                                     // gpsi_0 of this chunk is in G1
             if (c.shift_probes) {
                 int per = nb * c.P;
-                int nsub = (kMinCtas + per - 1) / per;
+                int nsub = (kProbeCtas + per - 1) / per;
                 if (nsub > nbc) nsub = nbc;
                 if (nsub < 1) nsub = 1;
                 int bsub = (nbc + nsub - 1) / nsub;
@@ -443,6 +444,30 @@ int ptyb200_sparse_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const 
     size_t n = (size_t)c->M * c->Z * c->Noy * c->Nox;
     k_sparse_grad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, lc->sparse_weight, lc->sparse_order, objp, occu, Ssum, upstream, cover, g_objp);
     CKL();
+    return 0;
+}
+
+int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t planes, int32_t H, int32_t W, float sigma,
+                           int32_t transpose, ptyb200_stream s) {
+    if (!in || !tmp || !out) return fail_msg("NULL argument");
+    if (planes < 1 || H < 3 || W < 3) return fail_msg("gaussian_blur5 needs planes >= 1 and H, W >= 3 (reflect padding of 2)");
+    if (!(sigma > 0.f)) return fail_msg("sigma must be positive");
+    if (in == out || in == tmp || tmp == out) return fail_msg("in, tmp and out must be distinct buffers");
+    Blur5 b;
+    double sum = 0, k[5];
+    for (int i = 0; i < 5; ++i) { const double t = (i - 2) / (double)sigma; k[i] = exp(-0.5 * t * t); sum += k[i]; }
+    for (int i = 0; i < 5; ++i) b.k[i] = (float)(k[i] / sum);
+    const long long total = (long long)planes * H * W;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    cudaStream_t st = (cudaStream_t)s;
+    // forward: x pass then y pass (as torchvision's separable kernel); the adjoint applies the transposed factors in reverse order
+    if (!transpose) {
+        k_blur5<0, false><<<grid, 256, 0, st>>>(b, in, tmp, total, H, W); CKL();
+        k_blur5<1, false><<<grid, 256, 0, st>>>(b, tmp, out, total, H, W); CKL();
+    } else {
+        k_blur5<1, true><<<grid, 256, 0, st>>>(b, in, tmp, total, H, W); CKL();
+        k_blur5<0, true><<<grid, 256, 0, st>>>(b, tmp, out, total, H, W); CKL();
+    }
     return 0;
 }
 

@@ -983,6 +983,39 @@ __global__ void k_sparse_grad(Dims d, float weight, float order, const float* __
 
 
 // ------------------------------------------------------------------------------------------------
+// 5-tap Gaussian blur with reflect padding along one axis, and its adjoint (torchvision gaussian_blur(kernel_size=5), used by
+// models.py:275-284 (object pre-blur), models.py:379-380 (detector blur) and losses.py:125,134).
+//   forward:  out[n] = sum_m W[n][m] in[m],   adjoint:  out[m] = sum_n W[n][m] in[n],   W[n][m] = sum_i k_i [refl(n+i) == m]
+// refl(t) = -t (t < 0), 2(S-1)-t (t > S-1): every non-zero W[n][m] has |n-m| <= 2, so both directions are 5-point gathers.
+// ------------------------------------------------------------------------------------------------
+struct Blur5 { float k[5]; };
+__device__ __forceinline__ int refl_idx(int t, int S) { return t < 0 ? -t : (t > S - 1 ? 2 * (S - 1) - t : t); }
+__device__ __forceinline__ float blur_w(const Blur5& b, int n, int m, int S) {       // W[n][m]
+    float w = 0.f;
+#pragma unroll
+    for (int i = -2; i <= 2; ++i) w += (refl_idx(n + i, S) == m) ? b.k[i + 2] : 0.f;
+    return w;
+}
+// AXIS 0: along W (contiguous), 1: along H.  grid: ceil(planes*H*W / 256)
+template <int AXIS, bool ADJ> __global__ void k_blur5(Blur5 b, const float* __restrict__ in, float* __restrict__ out, long long total, int H, int W) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int x = int(e % W), y = int((e / W) % H);
+    const int S = AXIS == 0 ? W : H, c = AXIS == 0 ? x : y;
+    const long long stride = AXIS == 0 ? 1 : W;
+    const float* base = in + (e - (long long)c * stride);
+    float acc = 0.f;
+#pragma unroll
+    for (int dlt = -2; dlt <= 2; ++dlt) {
+        const int o = c + dlt;
+        if (o < 0 || o >= S) continue;
+        const float w = ADJ ? blur_w(b, o, c, S) : blur_w(b, c, o, S);
+        acc += w * base[(long long)o * stride];
+    }
+    out[e] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused multi-tensor Adam (torch.optim.Adam semantics: no amsgrad, no weight decay, no maximize), reconstruction.py:759
 // ------------------------------------------------------------------------------------------------
 struct AdamTensors {

@@ -187,3 +187,28 @@ class SparseLossFunction(torch.autograd.Function):
         _lib.check(_lib.lib().ptyb200_sparse_grad(C.byref(cfg), C.byref(ctx.lcfg), ptr(objp), ptr(crop_pos), ptr(idx), idx.numel(),
                                                   ptr(occu), ptr(Ssum), ptr(up), ptr(cover), ptr(g), _stream()))
         return g, None, None, None, None, None
+
+
+class GaussianBlur5Function(torch.autograd.Function):
+    """5x5 Gaussian blur, reflect padding, last two dims (torchvision gaussian_blur(kernel_size=5); models.py:275-284,379-380,
+    losses.py:125,134); backward = the adjoint kernel."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, sigma):
+        _require_cuda(x)
+        x = x.contiguous()
+        ctx.sigma = float(sigma)
+        return _blur5(x, ctx.sigma, 0)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        return _blur5(g.contiguous().float(), ctx.sigma, 1), None
+
+
+def _blur5(x, sigma, transpose):
+    H, W = x.shape[-2], x.shape[-1]
+    out, tmp = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib().ptyb200_gaussian_blur5(ptr(x), ptr(tmp), ptr(out), x.numel() // (H * W), H, W, float(sigma), transpose, _stream()))
+    return out

@@ -330,8 +330,11 @@ class PtychoAD(nn.Module):
 
 def gaussian_blur5(x, sigma):
     """5x5 Gaussian, reflect padding, on the last two dims (what torchvision's gaussian_blur(kernel_size=5) computes;
-    reference models.py:275-284,379-380).  Written as separable shifted sums rather than conv2d: cuDNN convolutions default to
-    TF32 (1e-3 errors in the gradient), elementwise float32 arithmetic does not.  Off the default path."""
+    reference models.py:275-284,379-380).  CUDA float32 tensors go through the native blur / adjoint-blur kernels
+    (ptyb200_gaussian_blur5); anything else (the CPU helper getters, float64 checks) uses separable shifted sums -- not conv2d:
+    cuDNN convolutions default to TF32 (1e-3 errors in the gradient).  Off the default path."""
+    if x.is_cuda and x.dtype == torch.float32:
+        return engine.GaussianBlur5Function.apply(x, float(sigma))       # native kernels: blur and its adjoint
     t = torch.arange(-2, 3, dtype=x.dtype, device=x.device)
     k = torch.exp(-0.5 * (t / sigma) ** 2)
     k = k / k.sum()

@@ -546,3 +546,24 @@ def test_graphed_step_with_streamed_measurements_and_prefetch():
         torch.cuda.synchronize()
         res.append(torch.stack(ls).cpu().numpy())
     np.testing.assert_allclose(res[1], res[0], rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape,sigma", [((3, 2, 50, 37), 1.0), ((4, 64, 64), 0.6), ((2, 5, 9), 2.0), ((1, 3, 3), 1.0)])
+def test_native_gaussian_blur_and_adjoint(shape, sigma):
+    """ptyb200_gaussian_blur5 (object pre-blur / detector blur / loss_simlar, models.py:275-284,379-380) against the separable
+    reflect-padded 5-tap blur in float64 and its autograd adjoint; plus the dot-product identity <A x, y> == <x, A^T y>."""
+    from ptyrad_b200.models import gaussian_blur5
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(shape, generator=g, dtype=torch.float64)
+    y = torch.randn(shape, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    ref = gaussian_blur5(xr, sigma)                      # float64 on the CPU: the tensor-op formulation
+    ref.backward(y)
+    xc = x.float().cuda().requires_grad_(True)
+    out = gaussian_blur5(xc, sigma)                      # float32 on CUDA: the native kernels
+    out.backward(y.float().cuda())
+    assert rel(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-6
+    assert rel(xc.grad.cpu().numpy(), xr.grad.numpy()) < 1e-6
+    lhs = float((out.detach().double().cpu() * y).sum())
+    rhs = float((x * xc.grad.double().cpu()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
