@@ -51,6 +51,58 @@ def test_workspace_query_and_errors_without_gpu(built):
         engine.make_cfg(100, 1, 1, 1, 200, 200, 10, 0, 0, 0, 0.1, 0.02)
 
 
+def test_general_path_cut_changes_the_workspace_and_entry_points_refuse_bad_arguments(built):
+    """cfg.reserved[2] (samples per chunk) sizes the pass buffers of the general path; the blur and backward entry points validate
+    their arguments before touching the device (no GPU needed)."""
+    import ctypes as C
+    from ptyrad_b200 import engine
+    lib = built.lib()
+    cfg = engine.make_cfg(256, 12, 1, 16, 1186, 1186, 65536, 1, 0, 0, 0.1494, 0.0418)
+    whole = lib.ptyb200_workspace_bytes(C.byref(cfg), 256)
+    cfg.reserved[2] = 4
+    cut = lib.ptyb200_workspace_bytes(C.byref(cfg), 256)
+    tile = 12 * 256 * 256 * 8
+    assert whole - cut == 2 * (256 - 4) * tile                 # G1 and G2 shrink from the batch to one chunk
+    assert lib.ptyb200_gaussian_blur5(None, None, None, 1, 8, 8, 1.0, 0, None) != 0
+    assert b"NULL" in lib.ptyb200_last_error()
+    one = C.c_void_p(16); two = C.c_void_p(32); three = C.c_void_p(48)
+    assert lib.ptyb200_gaussian_blur5(one, two, three, 1, 2, 8, 1.0, 0, None) != 0      # H < 3: reflect padding of 2 impossible
+    assert lib.ptyb200_gaussian_blur5(one, two, three, 1, 8, 8, 0.0, 0, None) != 0      # sigma must be positive
+    assert lib.ptyb200_gaussian_blur5(one, one, three, 1, 8, 8, 1.0, 0, None) != 0      # aliasing
+    assert b"distinct" in lib.ptyb200_last_error()
+
+
+def test_grad_arena_layout_and_direct_step_eligibility():
+    """GradArena: every .grad is a 256-byte-aligned view into one flat buffer (the kernels write gradients with 8/16-byte vector
+    accesses), frozen tensors get grad=None; the autograd-free step is chosen only for configurations it covers."""
+    from ptyrad_b200 import CombinedLoss
+    from ptyrad_b200.step import GradArena, direct_step_eligible
+    from ptyrad_b200.synthetic import default_loss_params
+    m, iv, mp, lp = _model(tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4, lr_shifts=1e-4)
+    arena = GradArena(m)
+    base = arena.flat.data_ptr()
+    seen = 0
+    for p, v in zip(arena.params, arena.views):
+        assert (v.data_ptr() - base) % 256 == 0 and v.shape == p.shape
+        assert p.grad is not None and p.grad.data_ptr() == v.data_ptr()
+        seen += p.numel()
+    assert seen <= arena.flat.numel() < seen + 64 * len(arena.params) + 64
+    m.opt_probe.requires_grad = False
+    arena.attach()
+    assert m.opt_probe.grad is None and m.opt_obja.grad is not None
+    loss = CombinedLoss(lp, device="cpu")
+    assert direct_step_eligible(m, loss, arena, 1, True, None)
+    assert not direct_step_eligible(m, loss, None, 1, True, None)            # needs the arena as the kernels' output buffers
+    assert not direct_step_eligible(m, loss, arena, 2, True, None)           # gradient accumulation adds: autograd path
+    simlar = default_loss_params("single"); simlar["loss_simlar"]["state"] = True
+    assert not direct_step_eligible(m, CombinedLoss(simlar, device="cpu"), arena, 1, True, None)
+    m.detector_blur_std = 1.0
+    assert not direct_step_eligible(m, loss, arena, 1, True, None)
+    m.detector_blur_std = None
+    with torch.no_grad():
+        assert not direct_step_eligible(m, loss, arena, 1, True, None)
+
+
 def _model(name="T32", **kw):
     from dataclasses import replace
     from ptyrad_b200 import PtychoAD
