@@ -28,8 +28,8 @@ constexpr int NT = 16 * PTYB_ROWS;     // threads per CTA (one register-stage wo
 #ifndef GEN_MINB
 #define GEN_MINB (2 * 16 / PTYB_ROWS)   // minimum resident CTAs per SM requested from the compiler (register cap 128 per thread)
 #endif
-// the kernels with one cached table (k_fwd_da, k_fwd_bc, k_bwd_bc) fit 3 CTAs per SM (80 registers) without spilling up to N = 192
-// (measured: C5 +14 %); at N = 256 the 80-register build spills and is slower than 2 CTAs per SM (C4 -3 %, C3 -13 %)
+// the kernels with one cached table (k_fwd_da, k_fwd_bc, k_bwd_bc) run at 80 registers (768 threads per SM instead of 512) without
+// spilling up to N = 192 (measured: C5 +14 %); at N = 256 the 80-register build spills and is slower (C4 -3 %, C3 -13 %)
 #ifndef GEN_MINB_LIGHT
 #define GEN_MINB_LIGHT(F) (((F::N) <= 192 ? 3 : 2) * 16 / PTYB_ROWS)
 #endif
