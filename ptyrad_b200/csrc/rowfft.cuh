@@ -8,7 +8,8 @@
 //   stage 2 item (row, k1<N1): v[j] = x[j + N2*k1], DFT<N2> over j -> k2, written back at k2 + N2*k1   (= X[k1 + N1*k2])
 // so no item ever writes a location another item of the same stage reads, and one barrier between the
 // stages is all that is needed.  Rows are padded by one element per N2 group (addr()) which makes the
-// stride-N2 accesses of the frequency-ordered phases bank-conflict free for 64-bit words.
+// stride-N2 accesses of the frequency-ordered phases bank-conflict free for 64-bit words; the row stride RS
+// takes care of the accesses that run across the rows of a slab.
 //
 // The item functions are __host__ __device__: tests/csrc_host/test_fft_host.cu runs them on the CPU.
 #pragma once
@@ -19,7 +20,12 @@ namespace ptyb {
 template <int N1_, int N2_> struct RowFFT {
     static constexpr int N1 = N1_, N2 = N2_, N = N1_ * N2_;
     static constexpr int ROW_ELEMS = N + N1;                                  // N + N/N2 padding elements
-    static constexpr int RS = (ROW_ELEMS % 2) ? ROW_ELEMS : ROW_ELEMS + 1;    // odd row stride (transposed reads)
+#ifndef PTYB_RS_MOD16
+#define PTYB_RS_MOD16 2
+#endif
+    // row stride == 2 (mod 16) elements, i.e. 4 banks: the transposed accesses (lanes over the 8 rows of a slab, the two
+    // half-warp halves on neighbouring work items, which sit 2 banks apart) are then conflict free for 64-bit words
+    static constexpr int RS = (ROW_ELEMS + 15 - PTYB_RS_MOD16) / 16 * 16 + PTYB_RS_MOD16;
 
     PTYB_HD static int addr(int n) { return n + n / N2; }
     PTYB_HD static int pos(int q) { return (q / N1) + N2 * (q % N1); }        // where frequency q sits after fwd
