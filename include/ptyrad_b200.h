@@ -47,7 +47,7 @@ typedef struct ptyb200_cfg {
     int32_t tilt_mode;     /* 0: propagator shared by all positions; 1: one global tilt (1,2); 2: per-position (Ntot,2) */
     int32_t stash_fourier; /* 1: keep the Fourier-domain waves so tilt / thickness gradients can be formed */
     int32_t path;          /* PTYB200_PATH_* */
-    int32_t reserved[5];   /* [0] bit 0: adjoint accumulates over probe modes before scattering (experimental);
+    int32_t reserved[5];   /* [0] unused (was an experimental adjoint variant, removed);
                               [1] bit 0: PATCH MODE -- obja/objp (and their gradients) are per-sample ROI stacks (B,M,Z,N,N),
                                   e.g. pre-blurred patches (models.py:275-284); needs Noy == Nox == N, crop_pos is ignored;
                               [2] general path: samples per chunk (the slice sequence runs chunk by chunk so that the pass buffers

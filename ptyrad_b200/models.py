@@ -107,7 +107,7 @@ class PtychoAD(nn.Module):
             self.loss_iters, self.iter_times, self.dz_iters, self.avg_tilt_iters = [], [], [], []
             self._current_object_patches = None
             self.kernel_path = _lib.PATH_AUTO
-            self.kernel_flags = 0          # experimental kernel switches (cfg.reserved[0])
+            self.kernel_flags = 0          # cfg.reserved[0]: reserved for kernel experiments (no switch defined at present)
             self.kernel_chunk = 0          # general path: samples per L2-resident chunk (0 = library heuristic; cfg.reserved[2])
             self.kernel_pmodes_per_cta = 0  # general path: probe modes looped over by one CTA (0 = heuristic; cfg.reserved[3])
 
