@@ -725,45 +725,61 @@ template <class F, bool PROP> __global__ void __launch_bounds__(NT, GEN_MINB_LIG
 }
 
 // shifted probes: grid (N/ROWS, P, nsub), samples bl_lo..bl_hi of the chunk per CTA.  T = forward-y(sum_m G1[bl,p,m]) / N^2 ;
-// gPhatT += conj(w') T ; shift gradients -2 pi sum kappa Im(conj(w') conj(Phat) T)
+// gPhatT += conj(w') T ; shift gradients -2 pi sum kappa Im(conj(w') conj(Phat) T).
+// Two register stages per sample: A item (row r, j): y = j + N2 k straight from global (summed over the object modes), forward DFT
+// over k, twiddle -> smem;  B item (row r, k1): forward DFT over j -> ky = k1 + N1 k2, and all the pointwise work on those N2
+// frequencies in registers (the accumulators of the probe-spectrum gradient stay in registers across the samples).
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(BwdArgs a, int nchunk_b, int bsub) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
     const int kx0 = blockIdx.x * ROWS, p = blockIdx.y;
     const int b_lo = blockIdx.z * bsub, b_hi = min(nchunk_b, b_lo + bsub);
-    float2 acc[Slab<F>::EPT], Ph[Slab<F>::EPT];
-    float kapy[Slab<F>::EPT], kapx[Slab<F>::EPT];
-    Slab<F>::nat([&](int i, int r, int ky) {
-        acc[i] = make_float2(0.f, 0.f);
-        Ph[i] = a.f.PhatT[((size_t)p * N + kx0 + r) * N + ky];
-        kapy[i] = float(shift_idx(ky, N)) / float(N);
-        kapx[i] = float(shift_idx(kx0 + r, N)) / float(N);
-    });
+    const bool itemA = threadIdx.x < ROWS * N2, itemB = threadIdx.x < ROWS * N1;
+    const int rA = threadIdx.x / N2, jA = threadIdx.x % N2;
+    const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    float2 acc[N2], Ph[N2];
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) {
+        acc[k2] = make_float2(0.f, 0.f);
+        Ph[k2] = itemB ? a.f.PhatT[((size_t)p * N + kx0 + r) * N + k1 + N1 * k2] : make_float2(0.f, 0.f);
+    }
+    const float kapx = float(shift_idx(kx0 + r, N)) / float(N);
     const float invN2 = 1.0f / (float(N) * float(N));
     for (int bl = b_lo; bl < b_hi; ++bl) {
         const int b = d.b0 + bl;
         const size_t tile0 = ((size_t)bl * d.P + p) * d.M;
-        Slab<F>::nat([&](int, int r, int y) {
-            float2 v = make_float2(0.f, 0.f);
-            for (int m = 0; m < d.M; ++m) v = cadd(v, a.f.G1[(tile0 + m) * N * N + (size_t)(kx0 + r) * N + y]);
-            slab[r * F::RS + F::addr(y)] = v;
-        });
+        if (itemA) {
+            float2 v[N1];
+            const float2* sp = a.f.G1 + tile0 * N * N + (size_t)(kx0 + rA) * N + jA;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) v[k] = __ldcg(sp + N2 * k);
+            for (int m = 1; m < d.M; ++m) {
+#pragma unroll
+                for (int k = 0; k < N1; ++k) v[k] = cadd(v[k], __ldcg(sp + (size_t)m * N * N + N2 * k));
+            }
+            F::fwd_stage1_regs(slab + rA * F::RS, jA, v, twN);
+        }
         __syncthreads();
-        F::forward(slab, ROWS, twN);
-        const float2* wy = a.f.wvec + ((size_t)b * 2 + 0) * N;
-        const float2* wx = a.f.wvec + ((size_t)b * 2 + 1) * N;
         float s2[2] = {0.f, 0.f};
-        Slab<F>::nat([&](int i, int r, int ky) {
-            float2 T = cscale(slab[r * F::RS + F::apos(ky)], invN2);
-            float2 w = cmul(wy[ky], wx[kx0 + r]);
-            float2 cwT = cmulc(T, w);                                    // conj(w') * T
-            acc[i] = cadd(acc[i], cwT);
-            float q = cwT.y * Ph[i].x - cwT.x * Ph[i].y;                 // Im(conj(w') T conj(Phat))
-            s2[0] += kapy[i] * q; s2[1] += kapx[i] * q;
-        });
+        if (itemB) {
+            const float2* wy = a.f.wvec + ((size_t)b * 2 + 0) * N;
+            const float2 wxv = a.f.wvec[((size_t)b * 2 + 1) * N + kx0 + r];
+            float2 v[N2];
+            F::fwd_stage2_regs(slab + r * F::RS, k1, v);
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) {
+                const int ky = k1 + N1 * k2;
+                const float2 T = cscale(v[k2], invN2);
+                const float2 cwT = cmulc(T, cmul(wy[ky], wxv));              // conj(w') * T
+                acc[k2] = cadd(acc[k2], cwT);
+                const float q = cwT.y * Ph[k2].x - cwT.x * Ph[k2].y;         // Im(conj(w') T conj(Phat))
+                s2[0] += float(shift_idx(ky, N)) / float(N) * q;
+                s2[1] += kapx * q;
+            }
+        }
         if (a.need_shift) {
-            block_sum<2>(s2, red);
+            block_sum<2>(s2, red);                                          // its barriers also order the slab reuse
             if (threadIdx.x == 0) {
                 int64_t n0 = a.f.idx[b];
                 atomicAdd(a.gshift + 2 * n0 + 0, -6.283185307179586f * s2[0]);
@@ -772,9 +788,10 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_probe(B
         }
         __syncthreads();
     }
-    if (a.need_probe) {
-        float2* dst = a.gPhatT + (size_t)p * N * N;
-        Slab<F>::nat([&](int i, int r, int ky) { red_add_f2(dst + (size_t)(kx0 + r) * N + ky, acc[i]); });
+    if (a.need_probe && itemB) {
+        float2* dst = a.gPhatT + ((size_t)p * N + kx0 + r) * N + k1;
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) red_add_f2(dst + N1 * k2, acc[k2]);
     }
 }
 
