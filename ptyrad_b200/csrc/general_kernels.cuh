@@ -309,20 +309,37 @@ struct FwdArgs {
 // psi0 half-shifted: G2[b,p,0][y][kx] = (1/N) * inverse-y( PhatT[p][kx][ky] * wy[ky] * wx[kx] ).  grid (N/ROWS, groups, chunk)
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_init_shift(FwdArgs a) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const int kx0 = blockIdx.x * ROWS, bl = blockIdx.z, b = a.d.b0 + bl;
     const int p_lo = blockIdx.y * a.d.pg, p_hi = min(a.d.P, p_lo + a.d.pg);
-    const float2* wy = a.wvec + ((size_t)b * 2 + 0) * N;
-    const float2* wx = a.wvec + ((size_t)b * 2 + 1) * N;
-    float2 wreg[Slab<F>::EPT];
-    Slab<F>::nat([&](int i, int r, int ky) { wreg[i] = cmul(wy[ky], wx[kx0 + r]); });
+    // two register stages: A item (row r, k1): Phat[kx][k1 + N1 k2] * w' straight from global, inverse DFT over k2 -> smem;
+    //                      C item (row rr, j): inverse DFT over k1 -> y = j + N2 k, stored straight to the transposed tile
+    const bool itemA = threadIdx.x < ROWS * N1, itemC = threadIdx.x < ROWS * N2;
+    const int rA = threadIdx.x / N1, k1A = threadIdx.x % N1;
+    const int rC = threadIdx.x % ROWS, jC = threadIdx.x / ROWS;
+    float2 wreg[N2];
+    if (itemA) {
+        const float2* wy = a.wvec + ((size_t)b * 2 + 0) * N;
+        const float2 wxv = a.wvec[((size_t)b * 2 + 1) * N + kx0 + rA];
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) wreg[k2] = cmul(wy[k1A + N1 * k2], wxv);
+    }
     for (int p = p_lo; p < p_hi; ++p) {
-        const float2* src = a.PhatT + (size_t)p * N * N;
-        Slab<F>::nat([&](int i, int r, int ky) { slab[r * F::RS + F::apos(ky)] = cmul(src[(size_t)(kx0 + r) * N + ky], wreg[i]); });
+        if (itemA) {
+            const float2* sp = a.PhatT + (size_t)p * N * N + (size_t)(kx0 + rA) * N + k1A;
+            float2 v[N2];
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) v[k2] = cmul(sp[N1 * k2], wreg[k2]);
+            F::inv_stage2_regs(slab + rA * F::RS, k1A, v, twN);
+        }
         __syncthreads();
-        F::inverse(slab, ROWS, twN);
-        float2* dst = a.G2 + ((size_t)bl * a.d.P + p) * a.d.M * N * N;   // m = 0 slot
-        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        if (itemC) {
+            float2 v[N1];
+            F::inv_stage1_regs(slab + rC * F::RS, jC, v);
+            float2* dst = a.G2 + ((size_t)bl * a.d.P + p) * a.d.M * N * N + (size_t)jC * N + kx0 + rC;   // m = 0 slot
+#pragma unroll
+            for (int k = 0; k < N1; ++k) dst[(size_t)N2 * k * N] = cscale(v[k], 1.0f / N);
+        }
         __syncthreads();
     }
 }
@@ -483,28 +500,45 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fw
 // grid (N/ROWS, B): dp[b][sh(ky)][sh(kx)] = eps + sum_{m,p} occu_m |forward-y(farT)|^2 / N^2
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_final(FwdArgs a) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.d;
     const int kx0 = blockIdx.x * ROWS, b = blockIdx.y;
-    float acc[Slab<F>::EPT];
+    // two register stages per tile: A item (row r, j): y = j + N2 k straight from global, forward DFT over k -> smem;
+    // B item (row r, k1): forward DFT over j -> ky = k1 + N1 k2, |.|^2 accumulated in registers over the modes
+    const bool itemA = threadIdx.x < ROWS * N2, itemB = threadIdx.x < ROWS * N1;
+    const int rA = threadIdx.x / N2, jA = threadIdx.x % N2;
+    const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    float acc[N2];
 #pragma unroll
-    for (int i = 0; i < Slab<F>::EPT; ++i) acc[i] = 0.f;
+    for (int k2 = 0; k2 < N2; ++k2) acc[k2] = 0.f;
     for (int m = 0; m < d.M; ++m) {
         const float oc = a.occu[m];
         for (int p = 0; p < d.P; ++p) {
-            const float2* src = a.farT + (((size_t)b * d.P + p) * d.M + m) * N * N;
-            Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = src[(size_t)(kx0 + r) * N + y]; });
+            if (itemA) {
+                const float2* sp = a.farT + (((size_t)b * d.P + p) * d.M + m) * N * N + (size_t)(kx0 + rA) * N + jA;
+                float2 v[N1];
+#pragma unroll
+                for (int k = 0; k < N1; ++k) v[k] = sp[N2 * k];
+                F::fwd_stage1_regs(slab + rA * F::RS, jA, v, twN);
+            }
             __syncthreads();
-            F::forward(slab, ROWS, twN);
-            Slab<F>::nat([&](int i, int r, int ky) { acc[i] += oc * cabs2(slab[r * F::RS + F::apos(ky)]); });
+            if (itemB) {
+                float2 v[N2];
+                F::fwd_stage2_regs(slab + r * F::RS, k1, v);
+#pragma unroll
+                for (int k2 = 0; k2 < N2; ++k2) acc[k2] += oc * cabs2(v[k2]);
+            }
             __syncthreads();
         }
     }
     const float inv = 1.0f / (float(N) * float(N));
-    Slab<F>::nat([&](int i, int r, int ky) { fbuf[r * (N + 1) + ky] = acc[i] * inv + a.eps; });
+    if (itemB) {
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) fbuf[r * (N + 1) + k1 + N1 * k2] = acc[k2] * inv + a.eps;
+    }
     __syncthreads();
     float* dp = a.dp + (size_t)b * N * N;
-    Slab<F>::tr([&](int, int r, int ky) { dp[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + r, N)] = fbuf[r * (N + 1) + ky]; });
+    Slab<F>::tr([&](int, int rr, int ky) { dp[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + rr, N)] = fbuf[rr * (N + 1) + ky]; });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -524,31 +558,49 @@ struct BwdArgs {
 // grid (N/ROWS, M*groups, chunk): farT -> forward-y -> * 2 occu G~ -> inverse-y -> G2
 template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_start(BwdArgs a) {
     PTYB_SMEM_CARVE(F)
-    constexpr int N = F::N;
+    constexpr int N = F::N, N1 = F::N1, N2 = F::N2;
     const Dims& d = a.f.d;
     const Unit un = unit_of(d);
     const int kx0 = blockIdx.x * ROWS, m = un.m, b = un.b;
+    // three register stages like k_fwd_bc, with 2 occu_m dL/dI (fftshifted) in the place of the propagator
+    const bool itemA = threadIdx.x < ROWS * N2, itemB = threadIdx.x < ROWS * N1;
+    const int rA = threadIdx.x / N2, jA = threadIdx.x % N2;
+    const int r = threadIdx.x / N1, k1 = threadIdx.x % N1;
+    const int rC = threadIdx.x % ROWS, jC = threadIdx.x / ROWS;
     const float* G = a.G + (size_t)b * N * N;
-    Slab<F>::tr([&](int, int r, int ky) { fbuf[r * (N + 1) + ky] = G[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + r, N)]; });
+    Slab<F>::tr([&](int, int rr, int ky) { fbuf[rr * (N + 1) + ky] = G[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + rr, N)]; });
     __syncthreads();
     const float oc2 = 2.0f * a.f.occu[m];
-    float Greg[Slab<F>::EPT];
-    Slab<F>::nat([&](int i, int r, int ky) { Greg[i] = oc2 * fbuf[r * (N + 1) + ky]; });
+    float Greg[N2];
+#pragma unroll
+    for (int k2 = 0; k2 < N2; ++k2) Greg[k2] = itemB ? oc2 * fbuf[r * (N + 1) + k1 + N1 * k2] : 0.f;
     for (int p = un.p_lo; p < un.p_hi; ++p) {
         const size_t tile = ((size_t)b * d.P + p) * d.M + m;
         const size_t ltile = ((size_t)un.bl * d.P + p) * d.M + m;
-        const float2* src = a.f.farT + tile * N * N;
-        Slab<F>::nat([&](int, int r, int y) { slab[r * F::RS + F::addr(y)] = ld_stream(src + (size_t)(kx0 + r) * N + y); });
+        if (itemA) {
+            const float2* sp = a.f.farT + tile * N * N + (size_t)(kx0 + rA) * N + jA;
+            float2 v[N1];
+#pragma unroll
+            for (int k = 0; k < N1; ++k) v[k] = ld_stream(sp + N2 * k);
+            F::fwd_stage1_regs(slab + rA * F::RS, jA, v, twN);
+        }
         __syncthreads();
-        F::forward(slab, ROWS, twN);
-        Slab<F>::nat([&](int i, int r, int ky) {
-            float2 v = slab[r * F::RS + F::apos(ky)];
-            slab[r * F::RS + F::apos(ky)] = cscale(v, Greg[i]);
-        });
+        if (itemB) {
+            float2* row = slab + r * F::RS;
+            float2 v[N2];
+            F::fwd_stage2_regs(row, k1, v);
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) v[k2] = cscale(v[k2], Greg[k2]);
+            F::inv_stage2_regs(row, k1, v, twN);
+        }
         __syncthreads();
-        F::inverse(slab, ROWS, twN);
-        float2* dst = a.f.G2 + ltile * N * N;
-        Slab<F>::tr([&](int, int r, int y) { dst[(size_t)y * N + kx0 + r] = cscale(slab[r * F::RS + F::addr(y)], 1.0f / N); });
+        if (itemA) {
+            float2 v[N1];
+            F::inv_stage1_regs(slab + rC * F::RS, jC, v);
+            float2* dst = a.f.G2 + ltile * N * N + (size_t)jC * N + kx0 + rC;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) dst[(size_t)N2 * k * N] = cscale(v[k], 1.0f / N);
+        }
         __syncthreads();
     }
 }
