@@ -100,7 +100,7 @@ def cpu_reference_rate(cfg, iv, mp, lp, batch_cpu, steps, warmup, threads):
     """The oracle port of the reference's torch path, timed on the host cores (test infrastructure used as the baseline only)."""
     import torch
     from oracle.ptycho_torch import OracleTrainer
-    from ptyrad_b200.synthetic import random_batches
+    from workloads import random_batches
     tr = OracleTrainer(iv, mp, lp, threads=threads)
     batches = random_batches(iv["crop_pos"].shape[0], batch_cpu, seed=99)
     times = []
@@ -132,7 +132,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    from ptyrad_b200.synthetic import CONFIGS, make_inputs, random_batches
+    from workloads import CONFIGS, make_inputs, random_batches
     cfg = CONFIGS[args.config]
     B = args.batch or cfg.batch
     threads = os.cpu_count() or 1

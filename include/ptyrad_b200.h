@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PTYB200_ABI_VERSION 1
+#define PTYB200_ABI_VERSION 2
 
 /* cudaStream_t without pulling in the CUDA headers */
 typedef void* ptyb200_stream;
@@ -47,7 +47,7 @@ typedef struct ptyb200_cfg {
     int32_t tilt_mode;     /* 0: propagator shared by all positions; 1: one global tilt (1,2); 2: per-position (Ntot,2) */
     int32_t stash_fourier; /* 1: keep the Fourier-domain waves so tilt / thickness gradients can be formed */
     int32_t path;          /* PTYB200_PATH_* */
-    int32_t reserved[5];   /* [0] unused (was an experimental adjoint variant, removed);
+    int32_t reserved[5];   /* [0] unused;
                               [1] bit 0: PATCH MODE -- obja/objp (and their gradients) are per-sample ROI stacks (B,M,Z,N,N),
                                   e.g. pre-blurred patches (models.py:275-284); needs Noy == Nox == N, crop_pos is ignored;
                               [2] general path: samples per chunk (the slice sequence runs chunk by chunk so that the pass buffers
@@ -66,6 +66,18 @@ typedef struct ptyb200_loss_cfg {
     int32_t pacbed_state;  float pacbed_weight;  float pacbed_pow;                   /* losses.py:77-89  */
     int32_t sparse_state;  float sparse_weight;  float sparse_order;                 /* losses.py:91-104 */
 } ptyb200_loss_cfg;
+
+/* How the loss sees the measured patterns (PtychoAD.get_measurements, models.py:384-416).  NULL = rows of the stored (Ntot,N,N)
+ * array as they are.  Otherwise: rows are (Hs,Ws); if Hp/Wp > 0 each row is pasted into the background canvas `meas_padded`
+ * (Hp,Wp) at [h1:h2, w1:w2] ("on-the-fly" padding, models.py:401-405); if a scale factor differs from 1 the result is resampled
+ * bilinearly (torch interpolate(mode='bilinear', scale_factor=...), align_corners = False) and divided by scale_y*scale_x
+ * (models.py:407-409).  The final size must equal cfg.N.  Evaluated inside the loss kernels; nothing is materialised. */
+typedef struct ptyb200_meas_cfg {
+    int32_t Hs, Ws;          /* stored pattern size */
+    int32_t Hp, Wp;          /* padded canvas size, 0 = no padding */
+    int32_t h1, h2, w1, w2;  /* paste window */
+    float   scale_y, scale_x;/* resample factors, 0 or 1 = none */
+} ptyb200_meas_cfg;
 
 int         ptyb200_abi_version(void);
 const char* ptyb200_last_error(void);
@@ -126,12 +138,18 @@ int ptyb200_backward(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, cons
  * (Ntot,N,N) measurement array; rows idx[b] are read in place (no gathered copy; models.py:399). */
 int ptyb200_loss_forward(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
                          const int64_t* idx, int32_t B, float* losses3, double* stats, float* pacbed_scratch /* 2*N*N */,
+                         const ptyb200_meas_cfg* mcfg /* NULL: plain */, const float* meas_padded /* (Hp,Wp) or NULL */,
                          ptyb200_stream s);
+
+/* PtychoAD.get_measurements(indices) as a tensor (models.py:384-416): out (B,N,N) = the padded / resampled rows idx. */
+int ptyb200_gather_measurements(const ptyb200_cfg* cfg, const ptyb200_meas_cfg* mcfg, const float* meas_all, const float* meas_padded,
+                                const int64_t* idx, int32_t B, float* out, ptyb200_stream s);
 
 /* G = sum_t upstream[t] * d(loss_t)/d(dp), t over {single, poissn, pacbed}; upstream = 3 device floats. */
 int ptyb200_loss_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
                       const int64_t* idx, int32_t B, const double* stats, const float* pacbed_scratch,
-                      const float* upstream3, float* G_out, ptyb200_stream s);
+                      const float* upstream3, float* G_out, const ptyb200_meas_cfg* mcfg, const float* meas_padded,
+                      ptyb200_stream s);
 
 /* loss_sparse (losses.py:91-104) evaluated on the ROIs without materialising the patches:
  * loss = weight * sum_m occu_m * (mean_{b,z,y,x} |phi_patch|^n)^(1/n);  Ssum (M doubles) kept for the gradient. */
@@ -153,11 +171,12 @@ int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t plan
 
 /* optimizer.step() for torch.optim.Adam defaults (reconstruction.py:759; built at reconstruction.py:285-368):
  * one launch over up to 8 tensors with per-tensor learning rates.  The host arrays of pointers / lrs / numels are read
- * during the call; step_counter is one device int64 that the call increments before use (bias correction), so no
- * host synchronisation is needed. */
+ * during the call.  steps[i] is tensor i's OWN step counter, one device float32 scalar (torch.optim.Adam's state['step']): the call
+ * advances each by one before use (per-tensor bias correction, as torch does for tensors that join late through start_iter,
+ * reconstruction.py:783-790), so no host synchronisation is needed. */
 int ptyb200_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
-                      float* const* exp_avg_sq, const float* lrs, const int64_t* numels, float beta1, float beta2, float eps,
-                      int64_t* step_counter, ptyb200_stream s);
+                      float* const* exp_avg_sq, float* const* steps, const float* lrs, const int64_t* numels, float beta1,
+                      float beta2, float eps, ptyb200_stream s);
 
 #ifdef __cplusplus
 }

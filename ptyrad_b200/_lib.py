@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PTYB_LIB") or os.path.join(_HERE, "lib", "libptyrad_b200.so")   # PTYB_LIB: kernel-variant experiments
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NEED_OBJ, NEED_PROBE, NEED_SHIFTS, NEED_TILTS, NEED_DZ = 1, 2, 4, 8, 16
 PATH_AUTO, PATH_GENERAL, PATH_FUSED = 0, 1, 2
@@ -36,6 +36,14 @@ class LossCfg(C.Structure):
     ]
 
 
+class MeasCfg(C.Structure):
+    _fields_ = [
+        ("Hs", C.c_int32), ("Ws", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32),
+        ("h1", C.c_int32), ("h2", C.c_int32), ("w1", C.c_int32), ("w2", C.c_int32),
+        ("scale_y", C.c_float), ("scale_x", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "ptyb200_abi_version": (C.c_int, []),
@@ -48,12 +56,13 @@ _SIGNATURES = {
     "ptyb200_gather_patches": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ptyb200_forward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 12),
     "ptyb200_backward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 17 + [C.c_uint32, _P]),
-    "ptyb200_loss_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
-    "ptyb200_loss_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    "ptyb200_loss_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, C.POINTER(MeasCfg), _P, _P]),
+    "ptyb200_loss_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(MeasCfg), _P, _P]),
+    "ptyb200_gather_measurements": (C.c_int, [C.POINTER(Cfg), C.POINTER(MeasCfg), _P, _P, _P, C.c_int32, _P, _P]),
     "ptyb200_sparse_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ptyb200_sparse_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ptyb200_gaussian_blur5": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
-    "ptyb200_adam_step": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "ptyb200_adam_step": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <string>
 
 using namespace ptyb;
@@ -15,7 +17,7 @@ using namespace ptyb;
 namespace {
 
 thread_local std::string g_err;
-long long g_launches = 0;          // kernels launched by this library (bench.py reports it as gpu_launches)
+std::atomic<long long> g_launches{0};   // kernels launched by this library (bench.py reports it as gpu_launches)
 
 // optional per-section device timing (bench.py roofline): event pairs around the multislice forward / adjoint sections
 constexpr int kMaxEv = 256;
@@ -25,8 +27,12 @@ struct Timing {
     int n[2] = {0, 0};
     bool created = false;
 } g_tm;
+std::mutex g_tm_mu;
 void tm_mark(int section, int which, cudaStream_t st) {
     if (!g_tm.on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;   // no events inside a graph capture
+    std::lock_guard<std::mutex> lk(g_tm_mu);
     if (!g_tm.created) {
         for (int s = 0; s < 2; ++s) for (int i = 0; i < kMaxEv; ++i) { cudaEventCreate(&g_tm.ev[s][i][0]); cudaEventCreate(&g_tm.ev[s][i][1]); }
         g_tm.created = true;
@@ -72,12 +78,15 @@ bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && 
 struct GenPlan { int chunk, pg, groups; };
 GenPlan gen_plan(const ptyb200_cfg& c, int B) {
     GenPlan g;
+    // the environment is read ONCE per process: a change between ptyb200_workspace_bytes and the launch must not move the cut
+    static const int env_chunk = [] { const char* e = getenv("PTYB200_GEN_CHUNK"); return e ? atoi(e) : 0; }();
+    static const int env_pg = [] { const char* e = getenv("PTYB200_GEN_PG"); return e ? atoi(e) : 0; }();
     int chunk = B, pg = c.P;
-    if (const char* e = getenv("PTYB200_GEN_CHUNK")) { if (atoi(e) > 0) chunk = atoi(e); }
+    if (env_chunk > 0) chunk = env_chunk;
     if (c.reserved[2] > 0) chunk = c.reserved[2];
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
-    if (const char* e = getenv("PTYB200_GEN_PG")) { if (atoi(e) > 0) pg = atoi(e); }
+    if (env_pg > 0) pg = env_pg;
     if (c.reserved[3] > 0) pg = c.reserved[3];
     if (pg < 1) pg = 1;
     if (pg > c.P) pg = c.P;
@@ -175,7 +184,7 @@ template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace
                                     const float* objp, const float* probe, const float* shifts, const float* Hbase,
                                     const float* tilts, const float* dz, cudaStream_t st) {
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-    if (!use_fused(c)) {                       // the fused path builds its own packed copy of the complex object
+    if (!use_fused(c) || F128_OASYNC) {        // (the pre-cp.async fused variant builds its own packed copy of the complex object)
         k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
         CKL();
     }
@@ -256,7 +265,38 @@ template <class F> int backward_general(const ptyb200_cfg& c, int B, const Works
     return 0;
 }
 
-__global__ void k_increment(long long* c) { c[0] += 1; }
+// kernel-side view of the measurements from the ABI's description; returns an error text or null
+const char* make_meas_view(const ptyb200_cfg& c, const ptyb200_meas_cfg* m, const float* meas_all, const float* padded, const void* a1,
+                           const void* a2, MeasView* out) {
+    MeasView v;
+    memset(&v, 0, sizeof v);
+    v.meas = meas_all;
+    v.Hs = v.Ws = c.N;
+    v.ry = v.rx = v.scale = 1.f;
+    if (m) {
+        if (m->Hs < 1 || m->Ws < 1) return "meas_cfg: stored pattern size must be positive";
+        v.Hs = m->Hs; v.Ws = m->Ws;
+        int H = v.Hs, W = v.Ws;
+        if (m->Hp > 0 || m->Wp > 0) {
+            if (!padded) return "meas_cfg: padded canvas size given but meas_padded is NULL";
+            if (m->h1 < 0 || m->w1 < 0 || m->h2 > m->Hp || m->w2 > m->Wp || m->h2 - m->h1 != m->Hs || m->w2 - m->w1 != m->Ws)
+                return "meas_cfg: paste window [h1:h2, w1:w2] must lie inside the canvas and match the stored pattern size";
+            v.padded = padded; v.Hp = m->Hp; v.Wp = m->Wp; v.h1 = m->h1; v.h2 = m->h2; v.w1 = m->w1; v.w2 = m->w2;
+            H = v.Hp; W = v.Wp;
+        }
+        const bool rs = (m->scale_y > 0.f && m->scale_y != 1.f) || (m->scale_x > 0.f && m->scale_x != 1.f);
+        if (rs) {
+            const float sy = m->scale_y > 0.f ? m->scale_y : 1.f, sx = m->scale_x > 0.f ? m->scale_x : 1.f;
+            v.resample = 1; v.ry = 1.f / sy; v.rx = 1.f / sx; v.scale = 1.f / (sy * sx);
+            H = (int)floor((double)H * (double)sy); W = (int)floor((double)W * (double)sx);
+        }
+        if (H != c.N || W != c.N) return "meas_cfg: padded / resampled pattern size does not equal cfg.N";
+    }
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    v.vec = (!v.padded && !v.resample && al16(meas_all) && al16(a1) && al16(a2) && (c.N * c.N) % 4 == 0) ? 1 : 0;
+    *out = v;
+    return nullptr;
+}
 
 LossK make_lossk(const ptyb200_loss_cfg& l) {
     LossK k;
@@ -271,9 +311,10 @@ LossK make_lossk(const ptyb200_loss_cfg& l) {
 extern "C" {
 
 int ptyb200_abi_version(void) { return PTYB200_ABI_VERSION; }
-long long ptyb200_launch_count(void) { return g_launches; }
-void ptyb200_timing_enable(int on) { g_tm.on = on != 0; g_tm.n[0] = g_tm.n[1] = 0; }
+long long ptyb200_launch_count(void) { return g_launches.load(); }
+void ptyb200_timing_enable(int on) { std::lock_guard<std::mutex> lk(g_tm_mu); g_tm.on = on != 0; g_tm.n[0] = g_tm.n[1] = 0; }
 int ptyb200_timing_read(double* ms_forward, double* ms_backward, int* n_forward, int* n_backward) {
+    std::lock_guard<std::mutex> lk(g_tm_mu);
     double acc[2] = {0, 0};
     for (int s = 0; s < 2; ++s)
         for (int i = 0; i < g_tm.n[s]; ++i) {
@@ -388,16 +429,31 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     return 0;
 }
 
+int ptyb200_gather_measurements(const ptyb200_cfg* c, const ptyb200_meas_cfg* mcfg, const float* meas_all, const float* meas_padded,
+                                const int64_t* idx, int32_t B, float* out, ptyb200_stream s) {
+    if (!c || !meas_all || !idx || !out || B < 1) return fail_msg("NULL argument");
+    MeasView mv;
+    if (const char* e = make_meas_view(*c, mcfg, meas_all, meas_padded, out, out, &mv)) return fail_msg(e);
+    mv.vec = 0;
+    unsigned chunks = (unsigned)((c->N * c->N + 256 * 8 - 1) / (256 * 8));
+    k_meas_gather<<<dim3(chunks, B), 256, 0, (cudaStream_t)s>>>(mv, idx, c->N, out);
+    CKL();
+    return 0;
+}
+
 int ptyb200_loss_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
-                         const int64_t* idx, int32_t B, float* losses3, double* stats, float* pac, ptyb200_stream s) {
+                         const int64_t* idx, int32_t B, float* losses3, double* stats, float* pac,
+                         const ptyb200_meas_cfg* mcfg, const float* meas_padded, ptyb200_stream s) {
     if (!c || !lc || !dp || !meas_all || !idx || !losses3 || !stats) return fail_msg("NULL argument");
     if (lc->pacbed_state && !pac) return fail_msg("pacbed needs pacbed_scratch");
     cudaStream_t st = (cudaStream_t)s;
     LossK k = make_lossk(*lc);
+    MeasView mv;
+    if (const char* e = make_meas_view(*c, mcfg, meas_all, meas_padded, dp, dp, &mv)) return fail_msg(e);
     CK(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
     if (k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
     unsigned chunks = (unsigned)((c->N * c->N + 256 * 16 - 1) / (256 * 16));
-    k_loss_partial<<<dim3(chunks, B), 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac);
+    k_loss_partial<<<dim3(chunks, B), 256, 0, st>>>(k, dp, mv, idx, B, c->N, stats, pac);
     CKL();
     k_loss_final<<<1, 256, 0, st>>>(k, B, c->N, stats, pac, losses3);
     CKL();
@@ -406,12 +462,14 @@ int ptyb200_loss_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const
 
 int ptyb200_loss_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
                       const int64_t* idx, int32_t B, const double* stats, const float* pac, const float* upstream3,
-                      float* G_out, ptyb200_stream s) {
+                      float* G_out, const ptyb200_meas_cfg* mcfg, const float* meas_padded, ptyb200_stream s) {
     if (!c || !lc || !dp || !meas_all || !idx || !stats || !upstream3 || !G_out) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     LossK k = make_lossk(*lc);
+    MeasView mv;
+    if (const char* e = make_meas_view(*c, mcfg, meas_all, meas_padded, dp, G_out, &mv)) return fail_msg(e);
     unsigned chunks = (unsigned)((c->N * c->N + 256 * 8 - 1) / (256 * 8));
-    k_loss_grad<<<dim3(chunks, B), 256, 0, st>>>(k, dp, meas_all, idx, B, c->N, stats, pac, upstream3, G_out);
+    k_loss_grad<<<dim3(chunks, B), 256, 0, st>>>(k, dp, mv, idx, B, c->N, stats, pac, upstream3, G_out);
     CKL();
     return 0;
 }
@@ -472,25 +530,26 @@ int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t plan
 }
 
 int ptyb200_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
-                      float* const* exp_avg_sq, const float* lrs, const int64_t* numels, float beta1, float beta2, float eps,
-                      int64_t* step_counter, ptyb200_stream s) {
+                      float* const* exp_avg_sq, float* const* steps, const float* lrs, const int64_t* numels, float beta1, float beta2,
+                      float eps, ptyb200_stream s) {
     if (count < 1 || count > 8) return fail_msg("adam_step handles 1..8 tensors per call");
-    if (!params || !grads || !exp_avg || !exp_avg_sq || !lrs || !numels || !step_counter) return fail_msg("NULL argument");
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !steps || !lrs || !numels) return fail_msg("NULL argument");
     AdamTensors a;
     long long nmax = 0;
     for (int i = 0; i < count; ++i) {
         a.p[i] = params[i]; a.g[i] = grads[i]; a.m[i] = exp_avg[i]; a.v[i] = exp_avg_sq[i];
-        a.lr[i] = lrs[i]; a.n[i] = numels[i];
+        a.step[i] = steps[i]; a.lr[i] = lrs[i]; a.n[i] = numels[i];
+        if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || !steps[i]) return fail_msg("NULL tensor pointer");
         if (numels[i] > nmax) nmax = numels[i];
     }
     a.count = count; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
     cudaStream_t st = (cudaStream_t)s;
-    k_increment<<<1, 1, 0, st>>>((long long*)step_counter);
+    k_adam_advance<<<1, 32, 0, st>>>(a);
     CKL();
     unsigned bx = (unsigned)((nmax + 1023) / 1024);
     if (bx > 148 * 8) bx = 148 * 8;
     if (bx < 1) bx = 1;
-    k_adam<<<dim3(bx, count), 256, 0, st>>>(a, (const long long*)step_counter);
+    k_adam<<<dim3(bx, count), 256, 0, st>>>(a);
     CKL();
     return 0;
 }

@@ -22,27 +22,25 @@
 // Forward: grid (P, M, B), one wave per CTA; psi_z is stashed per slice through per-warp shared-memory staging blocks and
 // TMA bulk stores (cp.async.bulk), the far-field spectrum is kept for the adjoint.  Adjoint: one CTA per (sample, object
 // mode, probe mode); conj(psi_z) gphi_z is scattered straight into the packed, L2-resident dense object gradient with
-// red.global.add.v4.f32 (an accumulate-over-modes variant is kept behind cfg.reserved[0] & 1).  Every buffer this path owns
-// uses 16-byte "pair" layouts so that a thread's two consecutive elements are one 128-bit access.
+// red.global.add.v4.f32.  Every buffer this path owns uses 16-byte "pair" layouts so that a thread's two consecutive elements
+// are one 128-bit access.
 #pragma once
 #include "general_kernels.cuh"
 #include "../../include/ptyrad_b200.h"
+#include <atomic>
 #include <string>
 #include <cstring>
 
 namespace ptyb {
 namespace fused128 {
 
-#ifndef F128_TMA_RED
-#define F128_TMA_RED 0
-#endif
 constexpr int FN = 128;
 constexpr int FT = 512;                 // threads per CTA
 constexpr int CH = 528;                 // elements per chunk region (512 used by E1, 16 rows x 33 by E2)
 constexpr int E_ELEMS = 32 * CH;        // 16896 float2 = 135168 B
 constexpr int TILE = FN * FN;           // 16384
 // exchange buffer + twiddle/ramp tables + reduction scratch (+ 16 per-warp 4 KB TMA staging blocks where used)
-constexpr size_t SMEM_BYTES_BWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + (F128_TMA_RED ? 16 * 4096 : 0);
+constexpr size_t SMEM_BYTES_BWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float);
 constexpr size_t SMEM_BYTES_FWD = sizeof(float2) * (E_ELEMS + 128 + 4 * 128) + 128 * sizeof(float) + 16 * 4096;   // + stash staging
 
 struct Args {
@@ -56,13 +54,12 @@ struct Args {
     float2* phisF;          // (B,P,M,Z-1,TILE) layout F or null
     // adjoint only
     const float* G;
-    float2* gO;
     float2* gPhatF;         // (P, TILE) layout F
     float2* gprobe;         // (P, N, N) natural (unshifted probes)
     float* gprop;
     float* gshift;
     float dx, k0;
-    int shift, need_obj, need_probe, need_shift, need_prop, units, direct_red;
+    int shift, need_obj, need_probe, need_shift, need_prop, units;
 };
 
 struct Geo {
@@ -137,7 +134,11 @@ __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const fl
     Dft<32, -1>::run(v);
 }
 
-__device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const float2* tw, const Geo& g) {
+// `pre` runs between the last shared-memory read and the last register DFT: from there on the 32 slots this thread has just read
+// (E[r*CH + yl*128 + x]) belong to it alone until the next forward FFT's first barrier, which is where the kernels park the
+// asynchronous copy of the next slice's object ROI (prefetch_roi_to_E).
+template <class Pre>
+__device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const float2* tw, const Geo& g, Pre pre) {
     Dft<32, +1>::run(v);
     // no CTA barrier here: this warp only writes its OWN two chunks, whose only foreign readers are the layout-R reads at
     // the end of an earlier inverse FFT, and a forward FFT (two CTA barriers) always runs between two inverse FFTs
@@ -184,6 +185,7 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const fl
 #pragma unroll
         for (int r = 0; r < 32; ++r) v[r] = p[r * CH];
     }
+    pre();
     Dft<32, +1>::run(v);
 }
 
@@ -195,7 +197,7 @@ struct Smem {
     float2* wx;
     float2* ey;
     float2* ex;
-    float* fl;      // 64 KB: per-warp TMA staging blocks (16 warps x 4 KB)
+    float* fl;      // forward only, 64 KB: per-warp TMA staging blocks of the stash stores (16 warps x 4 KB)
     float* red;     // 128 floats (block_sum scratch)
 };
 __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
@@ -204,7 +206,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
     s.tw = s.E + E_ELEMS;
     s.wy = s.tw + 128; s.wx = s.wy + 128; s.ey = s.wx + 128; s.ex = s.ey + 128;
     s.red = reinterpret_cast<float*>(s.ex + 128);     // 128 floats of block_sum scratch
-    s.fl = s.red + 128;                               // adjoint only (the forward launches with SMEM_BYTES_FWD)
+    s.fl = s.red + 128;                               // forward only (SMEM_BYTES_FWD); the adjoint launches without it
     return s;
 }
 
@@ -327,9 +329,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -340,6 +339,27 @@ __device__ __forceinline__ int stash_index(int t, int j) { return (((t >> 5) * 1
 __device__ __forceinline__ float2 lo2(float4 q) { return make_float2(q.x, q.y); }
 __device__ __forceinline__ float2 hi2(float4 q) { return make_float2(q.z, q.w); }
 __device__ __forceinline__ float4 pack2(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+
+// F128_OASYNC 1: the object ROI of the NEXT pointwise phase is copied global -> shared memory asynchronously (cp.async, no
+// registers) while the last register DFT of the inverse FFT runs, into the 32 exchange-buffer slots the thread has just read.
+#ifndef F128_OASYNC
+#define F128_OASYNC 1
+#endif
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// O_z ROI -> this thread's own slots of E: slot k holds O_z[cy + yl + 4k][cx + x]  (Oz points at row cy + yl, column cx + x)
+__device__ __forceinline__ void prefetch_roi_to_E(float2* E, const Geo& g, const float2* __restrict__ Oz, int Nox) {
+    const uint32_t s0 = smem_u32(E + g.yl * 128 + g.x);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) cp_async8(s0 + k * (CH * 8), Oz + (size_t)(4 * k) * Nox);
+    cp_async_commit();
+}
 
 #ifndef F128_CHK
 #define F128_CHK 4
@@ -371,13 +391,17 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     int cy, cx;
     roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
     const size_t plane = (size_t)d.Noy * d.Nox;
+#if F128_OASYNC
+    const float2* Oroi = a.f.O + (size_t)obj_mode(d, b, m) * d.Z * plane + (size_t)(cy + g.yl) * d.Nox + cx + g.x;   // slice 0, this thread's first row
+#else
     const float4* Oplane = a.Opack + (size_t)obj_mode(d, b, m) * d.Z * plane;
     l2_prefetch_roi(Oplane, cy, cx, d.Nox);
+    const size_t ostr = (size_t)8 * d.Nox;
+    const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+#endif
     load_tables(s, a, b);
     __syncthreads();
     const size_t tile = ((size_t)b * d.P + p) * d.M + m;
-    const size_t ostr = (size_t)8 * d.Nox;
-    const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
     const int tR = g.yl * 128 + g.x;
     const float2 eyv = TILT ? s.ey[g.ky] : make_float2(1.f, 0.f);
     float2 v[32];
@@ -395,11 +419,19 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __ldg(pr + k * 512);
     }
+#if F128_OASYNC
+    if (!a.shift) prefetch_roi_to_E(s.E, g, Oroi, d.Nox);        // no inverse FFT precedes slice 0: fetch its ROI now
+#endif
     for (int z = a.shift ? -1 : 0; z < d.Z; ++z) {
         if (z >= 0) {
             float4* st = reinterpret_cast<float4*>(a.f.stash) + (tile * d.Z + z) * (TILE / 2);
+#if F128_OASYNC
+            cp_async_wait_all();                                  // O_z sits in this thread's own slots of E
+            const float2* __restrict__ Os = s.E + tR;
+#else
             const float4* __restrict__ Oz = Oplane + (size_t)z * plane + roi0;
             if (z + 1 < d.Z) l2_prefetch_roi(Oplane + (size_t)(z + 1) * plane, cy, cx, d.Nox);
+#endif
             // psi_z -> stash through a per-warp 4 KB staging block and one TMA bulk store per half (8 pairs): the stores
             // leave the LSU path, so the FFT's shared-memory traffic is not queued behind a 128 KB store burst
             float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
@@ -407,6 +439,15 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
             for (int h = 0; h < 2; ++h) {
                 if (g.lane == 0) bulk_wait_read0();
                 __syncwarp();
+#if F128_OASYNC
+#pragma unroll
+                for (int j = h * 8; j < h * 8 + 8; ++j) {
+                    const int k = 2 * j;
+                    sw[(j - h * 8) * 32] = pack2(v[k], v[k + 1]);
+                    v[k] = cmul(v[k], Os[k * CH]);
+                    v[k + 1] = cmul(v[k + 1], Os[(k + 1) * CH]);
+                }
+#else
 #pragma unroll
                 for (int j0 = 0; j0 < 8; j0 += CH2) {
                     float4 o[CH2];
@@ -420,6 +461,7 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
                         v[k + 1] = cmul(v[k + 1], hi2(o[i]));
                     }
                 }
+#endif
                 fence_async_smem();
                 __syncwarp();
                 if (g.lane == 0) {
@@ -447,7 +489,14 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
                 }
             }
         }
-        fft2_F_to_R(v, s.E, s.tw, g);
+#if F128_OASYNC
+        {
+            const float2* On = Oroi + (size_t)(z + 1) * plane;    // the ROI the pointwise phase after this inverse FFT multiplies
+            fft2_F_to_R(v, s.E, s.tw, g, [&] { prefetch_roi_to_E(s.E, g, On, d.Nox); });
+        }
+#else
+        fft2_F_to_R(v, s.E, s.tw, g, [] {});
+#endif
     }
     // far field: partial intensity of this (object mode, probe mode) in layout F (k_dp_reduce sums modes and fftshifts) and
     // the spectrum itself for the adjoint
@@ -464,49 +513,42 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 }
 
 // ---- adjoint --------------------------------------------------------------------------------------------------------
-// pointwise phase after the inverse FFT.  MODE 3: scatter conj(psi_z) gphi_z into the dense gradient; 4: object gradient not wanted
-// default scatter path (one CTA per probe mode): conj(psi_z) gphi_z is staged per warp in shared memory (8 pairs = 8 x 512 B)
-// and handed to the TMA engine as bulk reductions (cp.reduce.async.bulk ... add.f32) into the packed dense gradient --
-// the SM issues no RED instructions and keeps no registers alive for them.
-__device__ __forceinline__ void accum_phase_tma(float2 (&v)[32], const float4* __restrict__ st, const float4* __restrict__ Oz, size_t ostr,
-                                                float4* gOz_warp /* lane-0 address of pair 0 */, float4* sw, int lane, bool want) {
+// pointwise phase after the inverse FFT.  MODE 3: scatter conj(psi_z) gphi_z into the dense gradient with vector reds (handing the
+// same data to the TMA engine as cp.reduce.async.bulk from staged shared memory was measured slower: 1.85 vs 1.67 ms per C2 batch);
+// MODE 4: object gradient not wanted.
+#if F128_OASYNC
+#ifndef F128_CHS
+#define F128_CHS 8
+#endif
+// O_z comes from this thread's own slots of E (prefetched during the inverse FFT); only the stash streams through registers
+template <int MODE>
+__device__ __forceinline__ void accum_phase_E(float2 (&v)[32], const float4* __restrict__ st, const float2* __restrict__ Os, size_t ostr,
+                                              float4* __restrict__ gOz) {
+    constexpr int CS = F128_CHS;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        if (want) {
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
+    for (int j0 = 0; j0 < 16; j0 += CS) {
+        float4 ps[CS];
+        if (MODE != 4) {
+#pragma unroll
+            for (int i = 0; i < CS; ++i) ps[i] = __ldg(st + (j0 + i) * 32);
         }
 #pragma unroll
-        for (int j0 = 0; j0 < 8; j0 += CHA) {
-            float4 ps[CHA], o[CHA];
-#pragma unroll
-            for (int i = 0; i < CHA; ++i) {
-                o[i] = __ldg(Oz + (h * 8 + j0 + i) * ostr);
-                if (want) ps[i] = __ldg(st + (h * 8 + j0 + i) * 32);
+        for (int i = 0; i < CS; ++i) {
+            const int k = 2 * (j0 + i);
+            if (MODE != 4) {
+                const float2 c0 = cmulc(v[k], lo2(ps[i])), c1 = cmulc(v[k + 1], hi2(ps[i]));     // conj(psi) * gphi
+                red_f4(gOz + (j0 + i) * ostr, c0, c1);
             }
-#pragma unroll
-            for (int i = 0; i < CHA; ++i) {
-                const int k = 2 * (h * 8 + j0 + i);
-                if (want) sw[(j0 + i) * 32] = pack2(cmulc(v[k], lo2(ps[i])), cmulc(v[k + 1], hi2(ps[i])));     // conj(psi) * gphi
-                v[k] = cmulc(v[k], lo2(o[i]));                     // gpsi_z = conj(O_z) gphi_z
-                v[k + 1] = cmulc(v[k + 1], hi2(o[i]));
-            }
-        }
-        if (want) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) bulk_reduce_add_f32(gOz_warp + (size_t)(h * 8 + jj) * ostr, sw - lane + jj * 32, 512);
-                bulk_commit();
-            }
+            v[k] = cmulc(v[k], Os[k * CH]);                        // gpsi_z = conj(O_z) gphi_z
+            v[k + 1] = cmulc(v[k + 1], Os[(k + 1) * CH]);
         }
     }
 }
+#endif
 
 template <int MODE>
 __device__ __forceinline__ void accum_phase(float2 (&v)[32], const float4* __restrict__ st, const float4* __restrict__ Oz, size_t ostr,
-                                            float4* __restrict__ ac, float4* __restrict__ gOz) {
+                                            float4* __restrict__ gOz) {
 #pragma unroll
     for (int j0 = 0; j0 < 16; j0 += CH2) {
         float4 ps[CH2], o[CH2];
@@ -551,7 +593,11 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         const int64_t n0 = a.f.idx[b];
         int cy, cx;
         roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
+#if F128_OASYNC
+        const float2* Oroi = a.f.O + (size_t)obj_mode(d, b, m) * d.Z * plane + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
+#else
         const float4* Oplane = a.Opack + (size_t)obj_mode(d, b, m) * d.Z * plane;
+#endif
         __syncthreads();
         load_tables(s, a, b);
         // dL/dI in layout F, scaled 2 occu_m G~ / N^2, is gathered from global memory in the (single) start phase per mode
@@ -571,7 +617,9 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
             const int zn = st_i == d.Z ? d.Z - 1 : st_i - 1;
             if (st_i > 0) {
                 l2_prefetch_tile(stash_t + (size_t)zn * (TILE / 2));
+#if !F128_OASYNC
                 l2_prefetch_roi(Oplane + (size_t)zn * plane, cy, cx, d.Nox);
+#endif
             }
             if (st_i < d.Z) fft2_R_to_F(v, s.E, s.tw, g);
             if (st_i == d.Z) {
@@ -648,17 +696,20 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
                 }
                 break;
             }
-            fft2_F_to_R(v, s.E, s.tw, g);                                   // gphi_{zn}
             {
                 const float4* st = stash_t + (size_t)zn * (TILE / 2) + stash_index(g.t, 0);
-                const float4* Oz = Oplane + (size_t)zn * plane + roi0;
                 float4* gOz = a.gOpack + ((size_t)obj_mode(d, b, m) * d.Z + zn) * plane + roi0;
-#if F128_TMA_RED       // measured slower than LSU reds on B200 (1.85 vs 1.67 ms per C2 batch): kept for reference
-                float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
-                accum_phase_tma(v, st, Oz, ostr, gOz - (g.x & 31), sw, g.lane, a.need_obj != 0);
+#if F128_OASYNC
+                const float2* On = Oroi + (size_t)zn * plane;
+                fft2_F_to_R(v, s.E, s.tw, g, [&] { prefetch_roi_to_E(s.E, g, On, d.Nox); });     // gphi_{zn}
+                cp_async_wait_all();
+                if (a.need_obj) accum_phase_E<3>(v, st, s.E + tR, ostr, gOz);
+                else accum_phase_E<4>(v, st, s.E + tR, ostr, gOz);
 #else
-                if (a.need_obj) accum_phase<3>(v, st, Oz, ostr, nullptr, gOz);
-                else accum_phase<4>(v, st, Oz, ostr, nullptr, gOz);
+                fft2_F_to_R(v, s.E, s.tw, g, [] {});                            // gphi_{zn}
+                const float4* Oz = Oplane + (size_t)zn * plane + roi0;
+                if (a.need_obj) accum_phase<3>(v, st, Oz, ostr, gOz);
+                else accum_phase<4>(v, st, Oz, ostr, gOz);
 #endif
             }
         }
@@ -676,7 +727,6 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
             }
         }
     }
-    if (g.lane == 0) bulk_wait_all();       // staging blocks must outlive the TMA reads; reductions complete before exit
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
@@ -694,7 +744,7 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     s.HF = (float2*)take((size_t)TILE * 8);
     s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
-    s.Opack = (float4*)take(obj * 16);
+    s.Opack = (float4*)take(F128_OASYNC ? 0 : obj * 16);
     s.gOpack = (float4*)take(obj * 16);
     s.Ipart = (float*)take((size_t)B * c.M * c.P * TILE * 4);
     s.farF = (float2*)take((size_t)B * c.M * c.P * TILE * 8);
@@ -721,13 +771,15 @@ inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc,
 
 // f.HT = transposed propagator [kx][ky]; f.PhatT = probe spectrum [kx][ky] (both made by setup_common)
 inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, const float* objp, unsigned char* scratch, cudaStream_t st,
-                   std::string& err, long long* launches) {
+                   std::string& err, std::atomic<long long>* launches) {
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, f, sc, f.phis);
     const float inv = 1.0f / (128.0f * 128.0f);
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
+#if !F128_OASYNC
     k_obj_polar_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, sc.Opack, c.Noy, c.Nox, obj);
     F128_CK(cudaGetLastError()); ++*launches;
+#endif
     k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
     F128_CK(cudaGetLastError()); ++*launches;
     if (c.shift_probes) {
@@ -753,14 +805,13 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
 // adjoint incl. the polar backward of the object gradient; the caller zeroes gPhatT / gprop / gshift and runs the
 // probe-spectrum inverse FFT
 inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float* obja, const float* objp, float* g_obja, float* g_objp,
-                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, long long* launches) {
+                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches) {
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, bw.f, sc, bw.f.phis);
     a.G = bw.G; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
     a.dx = bw.dx; a.k0 = bw.k0;
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
     a.units = B * c.M * c.P;
-    a.direct_red = 1;
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     if (a.need_obj) F128_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
     if (a.need_probe) {

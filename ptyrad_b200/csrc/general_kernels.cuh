@@ -920,19 +920,69 @@ __device__ __forceinline__ float powp(float x, float p) {
     return powf(x, p);
 }
 
+// Measured pattern of sample b as the loss sees it (models.py:384-416): row idx[b] of the stored (Ntot,Hs,Ws) array, optionally
+// pasted into a padded background canvas (Hp,Wp) at [h1:h2, w1:w2] ("on-the-fly" padding, models.py:401-405) and optionally
+// resampled bilinearly by fixed scale factors and divided by their product (models.py:407-409; the arithmetic follows ATen's
+// upsample_bilinear2d with align_corners = false and a given scale_factor: src = (dst + 0.5) / scale - 0.5, clamped at 0).
+// Evaluated on the fly inside the loss kernels: no gathered / padded / resampled copy is ever materialised.
+struct MeasView {
+    const float* meas;      // (Ntot,Hs,Ws)
+    const float* padded;    // (Hp,Wp) or null
+    int Hs, Ws, Hp, Wp, h1, w1, h2, w2;
+    int resample;           // 0: output pixel = source pixel
+    int vec;                // 1: plain layout and 16-byte aligned rows -> 128-bit reads
+    float ry, rx;           // source pixels per output pixel (1 / scale_factor)
+    float scale;            // 1 / prod(scale_factor)
+};
+__device__ __forceinline__ float meas_src(const MeasView& v, const float* __restrict__ Mrow, int y, int x) {
+    if (!v.padded) return Mrow[(size_t)y * v.Ws + x];
+    if (y >= v.h1 && y < v.h2 && x >= v.w1 && x < v.w2) return Mrow[(size_t)(y - v.h1) * v.Ws + (x - v.w1)];
+    return v.padded[(size_t)y * v.Wp + x];
+}
+__device__ __forceinline__ float meas_at(const MeasView& v, const float* __restrict__ Mrow, int Y, int X) {
+    if (!v.resample) return meas_src(v, Mrow, Y, X);
+    const int H = v.padded ? v.Hp : v.Hs, W = v.padded ? v.Wp : v.Ws;
+    const float sy = fmaxf(v.ry * (float(Y) + 0.5f) - 0.5f, 0.f), sx = fmaxf(v.rx * (float(X) + 0.5f) - 0.5f, 0.f);
+    const int y0 = min(int(sy), H - 1), x0 = min(int(sx), W - 1);
+    const int yp = y0 < H - 1 ? 1 : 0, xp = x0 < W - 1 ? 1 : 0;
+    const float ly = sy - float(y0), lx = sx - float(x0), hy = 1.f - ly, hx = 1.f - lx;
+    const float val = hy * (hx * meas_src(v, Mrow, y0, x0) + lx * meas_src(v, Mrow, y0, x0 + xp)) +
+                      ly * (hx * meas_src(v, Mrow, y0 + yp, x0) + lx * meas_src(v, Mrow, y0 + yp, x0 + xp));
+    return val * v.scale;
+}
+__device__ __forceinline__ bool meas_plain(const MeasView& v) { return v.vec != 0; }
+
+// the transformed patterns as a tensor (PtychoAD.get_measurements(indices), models.py:384-416).  grid (chunks, B)
+__global__ void k_meas_gather(MeasView mv, const int64_t* __restrict__ idx, int N, float* __restrict__ out) {
+    const int NN = N * N, b = blockIdx.y;
+    const float* __restrict__ M_ = mv.meas + (size_t)idx[b] * mv.Hs * mv.Ws;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x)
+        out[(size_t)b * NN + pix] = meas_at(mv, M_, pix / N, pix % N);
+}
+
 // stats: [0] sum (I^p-M^p)^2  [1] sum M^p  [2] sum (M^q log(I^q+e) - I^q)  [3] sum M^q  [4] sum M^r  [5] sum (Ibar^r - Mbar^r)^2
 // grid (chunks, B): block (c, b) handles a contiguous chunk of pattern b
-__global__ void k_loss_partial(LossK k, const float* __restrict__ dp, const float* __restrict__ meas, const int64_t* __restrict__ idx,
+__global__ void k_loss_partial(LossK k, const float* __restrict__ dp, MeasView mv, const int64_t* __restrict__ idx,
                                int B, int N, double* stats, float* pac) {
     const int NN = N * N, b = blockIdx.y;
     const float* __restrict__ I_ = dp + (size_t)b * NN;
-    const float* __restrict__ M_ = meas + (size_t)idx[b] * NN;
+    const float* __restrict__ M_ = mv.meas + (size_t)idx[b] * mv.Hs * mv.Ws;
     float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x) {
-        const float I = I_[pix], Mv = M_[pix];
+    auto term = [&](int pix, float I, float Mv) {
         if (k.s_on) { float mp = powp(Mv, k.s_p), df = powp(I, k.s_p) - mp; a0 += df * df; a1 += mp; }
         if (k.p_on) { float mq = powp(Mv, k.p_p), iq = powp(I, k.p_p); a2 += mq * logf(iq + k.p_eps) - iq; a3 += mq; }
         if (k.b_on) { a4 += powp(Mv, k.b_p); atomicAdd(pac + pix, I); atomicAdd(pac + NN + pix, Mv); }
+    };
+    if (meas_plain(mv)) {                                     // 128-bit reads of both streams (N*N is a multiple of 4)
+        const float4* __restrict__ I4 = reinterpret_cast<const float4*>(I_);
+        const float4* __restrict__ M4 = reinterpret_cast<const float4*>(M_);
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NN / 4; q += gridDim.x * blockDim.x) {
+            const float4 i4 = I4[q], m4 = __ldg(M4 + q);
+            term(4 * q, i4.x, m4.x); term(4 * q + 1, i4.y, m4.y); term(4 * q + 2, i4.z, m4.z); term(4 * q + 3, i4.w, m4.w);
+        }
+    } else {
+        for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x)
+            term(pix, I_[pix], meas_at(mv, M_, pix / N, pix % N));
     }
     __shared__ float red[5 * 32];
     float v[5] = {a0, a1, a2, a3, a4};
@@ -968,7 +1018,7 @@ __global__ void k_loss_final(LossK k, int B, int N, double* stats, const float* 
     }
 }
 
-__global__ void k_loss_grad(LossK k, const float* __restrict__ dp, const float* __restrict__ meas, const int64_t* __restrict__ idx,
+__global__ void k_loss_grad(LossK k, const float* __restrict__ dp, MeasView mv, const int64_t* __restrict__ idx,
                             int B, int N, const double* __restrict__ stats, const float* __restrict__ pac,
                             const float* __restrict__ up, float* __restrict__ G) {
     const int NN = N * N, b = blockIdx.y;
@@ -978,21 +1028,31 @@ __global__ void k_loss_grad(LossK k, const float* __restrict__ dp, const float* 
     if (k.p_on) cp = float(-up[1] * k.p_w * k.p_p / (nel * (stats[3] / nel)));
     if (k.b_on) cb = float(up[2] * k.b_w * k.b_p / (nel * sqrt(stats[5] / NN) * (stats[4] / nel)));
     const float* __restrict__ I_ = dp + (size_t)b * NN;
-    const float* __restrict__ M_ = meas + (size_t)idx[b] * NN;
+    const float* __restrict__ M_ = mv.meas + (size_t)idx[b] * mv.Hs * mv.Ws;
     float* __restrict__ G_ = G + (size_t)b * NN;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x) {
-        const float I = I_[pix];
+    auto grad = [&](int pix, float I, float Mv) {
         float g = 0.f;
-        if (k.s_on || k.p_on) {
-            const float Mv = M_[pix];
-            if (k.s_on) g += cs * (powp(I, k.s_p) - powp(Mv, k.s_p)) * powp(I, k.s_p - 1.0f);
-            if (k.p_on) g += cp * (powp(Mv, k.p_p) / (powp(I, k.p_p) + k.p_eps) - 1.0f) * powp(I, k.p_p - 1.0f);
-        }
+        if (k.s_on) g += cs * (powp(I, k.s_p) - powp(Mv, k.s_p)) * powp(I, k.s_p - 1.0f);
+        if (k.p_on) g += cp * (powp(Mv, k.p_p) / (powp(I, k.p_p) + k.p_eps) - 1.0f) * powp(I, k.p_p - 1.0f);
         if (k.b_on) {
             const float ib = pac[pix] / B, mb = pac[NN + pix] / B;
             g += cb * (powp(ib, k.b_p) - powp(mb, k.b_p)) * powp(ib, k.b_p - 1.0f);
         }
-        G_[pix] = g;
+        return g;
+    };
+    const bool need_m = k.s_on || k.p_on;
+    if (meas_plain(mv)) {
+        const float4* __restrict__ I4 = reinterpret_cast<const float4*>(I_);
+        const float4* __restrict__ M4 = reinterpret_cast<const float4*>(M_);
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NN / 4; q += gridDim.x * blockDim.x) {
+            const float4 i4 = I4[q];
+            const float4 m4 = need_m ? __ldg(M4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(G_)[q] = make_float4(grad(4 * q, i4.x, m4.x), grad(4 * q + 1, i4.y, m4.y), grad(4 * q + 2, i4.z, m4.z),
+                                                           grad(4 * q + 3, i4.w, m4.w));
+        }
+    } else {
+        for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x)
+            G_[pix] = grad(pix, I_[pix], need_m ? meas_at(mv, M_, pix / N, pix % N) : 0.f);
     }
 }
 
@@ -1092,16 +1152,21 @@ struct AdamTensors {
     const float* g[8];
     float* m[8];
     float* v[8];
+    float* step[8];         // per-tensor step counters (device float32 scalars: torch.optim.Adam's state['step'])
     float lr[8];
     long long n[8];
     int count;
     float beta1, beta2, eps;
 };
-// step: device int64 counter (already incremented for this step)
-__global__ void k_adam(AdamTensors a, const long long* __restrict__ step) {
+__global__ void k_adam_advance(AdamTensors a) {
+    if (threadIdx.x < a.count) a.step[threadIdx.x][0] += 1.0f;
+}
+// every tensor carries its OWN step (torch.optim.Adam keeps one per parameter: a tensor whose start_iter comes later starts its
+// bias correction at 1); the counters were already advanced for this step by k_adam_advance
+__global__ void k_adam(AdamTensors a) {
     const int ti = blockIdx.y;
     if (ti >= a.count) return;
-    const double t = (double)step[0];
+    const double t = (double)a.step[ti][0];
     const float bc1 = float(1.0 - pow((double)a.beta1, t));
     const float bc2s = float(sqrt(1.0 - pow((double)a.beta2, t)));
     const float step_size = a.lr[ti] / bc1;

@@ -46,6 +46,19 @@ def make_loss_cfg(lp: dict) -> LossCfg:
     return l
 
 
+def mref(mcfg):
+    """ctypes reference to an optional MeasCfg (None -> NULL)."""
+    return None if mcfg is None else C.byref(mcfg)
+
+
+def gather_measurements(cfg: Cfg, mcfg, meas_all, padded, idx):
+    """Rows idx of the measurements with the on-the-fly pad / resample applied, as a (B,N,N) tensor (models.py:384-416)."""
+    _require_cuda(meas_all, idx)
+    out = torch.empty((idx.numel(), cfg.N, cfg.N), dtype=torch.float32, device=meas_all.device)
+    _lib.check(_lib.lib().ptyb200_gather_measurements(C.byref(cfg), mref(mcfg), ptr(meas_all), ptr(padded), ptr(idx), idx.numel(), ptr(out), _stream()))
+    return out
+
+
 def propagator(cfg: Cfg, dz: torch.Tensor) -> torch.Tensor:
     """exp(i*dz*Kz) (N,N) complex64, evaluated in float64 on the device (models.py:222-223,341,355)."""
     _require_cuda(dz)
@@ -134,7 +147,7 @@ class DataLossFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, dp, meas_all, idx, cfg, lcfg):
+    def forward(ctx, dp, meas_all, idx, cfg, lcfg, mcfg=None, padded=None):
         _require_cuda(dp, meas_all, idx)
         dp = dp.contiguous()
         B = dp.shape[0]
@@ -143,9 +156,9 @@ class DataLossFunction(torch.autograd.Function):
         stats = torch.empty(8, dtype=torch.float64, device=dev)
         pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
         _lib.check(_lib.lib().ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas_all), ptr(idx), B,
-                                                   ptr(losses3), ptr(stats), ptr(pac), _stream()))
+                                                   ptr(losses3), ptr(stats), ptr(pac), mref(mcfg), ptr(padded), _stream()))
         ctx.save_for_backward(dp, meas_all, idx, stats)
-        ctx.pac, ctx.cfg, ctx.lcfg = pac, cfg, lcfg
+        ctx.pac, ctx.cfg, ctx.lcfg, ctx.mcfg, ctx.padded = pac, cfg, lcfg, mcfg, padded
         return losses3
 
     @staticmethod
@@ -155,8 +168,8 @@ class DataLossFunction(torch.autograd.Function):
         G = torch.empty_like(dp)
         up = up.contiguous().float()
         _lib.check(_lib.lib().ptyb200_loss_grad(C.byref(ctx.cfg), C.byref(ctx.lcfg), ptr(dp), ptr(meas_all), ptr(idx), dp.shape[0],
-                                                ptr(stats), ptr(ctx.pac), ptr(up), ptr(G), _stream()))
-        return G, None, None, None, None
+                                                ptr(stats), ptr(ctx.pac), ptr(up), ptr(G), mref(ctx.mcfg), ptr(ctx.padded), _stream()))
+        return G, None, None, None, None, None, None
 
 
 class SparseLossFunction(torch.autograd.Function):

@@ -20,7 +20,11 @@ class CombinedLoss(torch.nn.Module):
         super().__init__()
         self.device = device
         self.loss_params = loss_params
-        self._lcfg = engine.make_loss_cfg(loss_params)
+
+    def lcfg(self):
+        """Kernel-side view of `loss_params`, rebuilt on every call: the reference reads the dict live (losses.py:41-47), so a
+        caller that edits weights / states between iterations (hypertune, notebooks) is honoured."""
+        return engine.make_loss_cfg(self.loss_params)
 
     # data terms -------------------------------------------------------------------------------------
     def _data_losses(self, model_DP, measured_DP):
@@ -29,13 +33,14 @@ class CombinedLoss(torch.nn.Module):
             z = torch.zeros((), dtype=torch.float32, device=model_DP.device)
             return z, z.clone(), z.clone()
         B, N = model_DP.shape[0], model_DP.shape[-1]
+        mcfg = padded = None
         if isinstance(measured_DP, MeasurementView):
-            meas_all, idx = measured_DP.all, measured_DP.idx
+            meas_all, idx, mcfg, padded = measured_DP.all, measured_DP.idx, measured_DP.mcfg, measured_DP.padded
         else:
             meas_all = measured_DP.contiguous().float()
             idx = torch.arange(B, dtype=torch.int64, device=model_DP.device)
         cfg = engine.make_cfg(N, 1, 1, 1, N, N, meas_all.shape[0], 0, 0, 0, 1.0, 1.0)
-        l3 = engine.DataLossFunction.apply(model_DP, meas_all, idx, cfg, self._lcfg)
+        l3 = engine.DataLossFunction.apply(model_DP, meas_all, idx, cfg, self.lcfg(), mcfg, padded)
         return l3[0], l3[1], l3[2]
 
     def get_loss_single(self, model_DP, measured_DP):
@@ -54,7 +59,7 @@ class CombinedLoss(torch.nn.Module):
             return torch.zeros((), dtype=torch.float32, device=omode_occu.device)
         if isinstance(objp_patches, LazyPatches):
             m = objp_patches.model
-            return engine.SparseLossFunction.apply(m.opt_objp, m.crop_pos, objp_patches.idx, omode_occu, m._cfg(False), self._lcfg)
+            return engine.SparseLossFunction.apply(m.opt_objp, m.crop_pos, objp_patches.idx, omode_occu, m._cfg(False), self.lcfg())
         n = sp["ln_order"]
         return sp["weight"] * (objp_patches.abs().pow(n).mean(dim=(0, 2, 3, 4)).pow(1.0 / n) * omode_occu).sum()
 
@@ -84,9 +89,12 @@ class CombinedLoss(torch.nn.Module):
 
 
 class MeasurementView:
-    """(all measurements, batch indices) pair: lets the native loss read rows ``idx`` of the (Ntot,N,N) array in place
-    instead of a gathered copy.  ``PtychoAD.get_measurements`` keeps returning a real tensor for compatibility; the fast
-    step (``ptyrad_b200.step.recon_batch``) passes this view."""
+    """(all measurements, batch indices) pair: lets the native loss read rows ``idx`` of the stored (Ntot,H,W) array in place
+    instead of a gathered copy.  With `model` given, the model's "on-the-fly" padding / bilinear resampling options
+    (models.py:392-409) travel along and are evaluated INSIDE the loss kernels (nothing is materialised).
+    ``PtychoAD.get_measurements`` keeps returning a real tensor for compatibility; the fast step
+    (``ptyrad_b200.step.recon_batch``) passes this view."""
 
-    def __init__(self, all_meas, idx):
+    def __init__(self, all_meas, idx, model=None):
         self.all, self.idx = all_meas, idx
+        self.mcfg, self.padded = (None, None) if model is None else model._meas_cfg(all_meas)

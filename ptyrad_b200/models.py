@@ -68,6 +68,8 @@ class PtychoAD(nn.Module):
             if init_variables.get("on_the_fly_meas_padded", None) is not None:
                 self.meas_padded = torch.tensor(init_variables["on_the_fly_meas_padded"], dtype=torch.float32, device=device)
                 self.meas_padded_idx = torch.tensor(init_variables["on_the_fly_meas_padded_idx"], dtype=torch.int32, device=device)
+                self._meas_pad_idx = tuple(int(v) for v in init_variables["on_the_fly_meas_padded_idx"])   # host copy: no sync per batch
+                self.meas_padded = self.meas_padded.contiguous()
             else:
                 self.meas_padded = None
             self.meas_scale_factors = init_variables.get("on_the_fly_meas_scale_factors", None)
@@ -285,21 +287,37 @@ class PtychoAD(nn.Module):
             psi = torch.fft.ifft2(H[None] * torch.fft.fft2(psi))
         return out
 
+    def _meas_cfg(self, meas_all=None):
+        """(MeasCfg, padded canvas) describing the on-the-fly pad / resample of the measurements for the kernels, or (None, None)
+        when the stored patterns are used as they are (models.py:392-409)."""
+        sf = self.meas_scale_factors
+        resample = sf is not None and any(f != 1 for f in sf)
+        if self.meas_padded is None and not resample:
+            return None, None
+        meas_all = self.measurements if meas_all is None else meas_all
+        m = _lib.MeasCfg()
+        m.Hs, m.Ws = int(meas_all.shape[-2]), int(meas_all.shape[-1])
+        padded = None
+        if self.meas_padded is not None:
+            padded = self.meas_padded
+            m.Hp, m.Wp = int(padded.shape[-2]), int(padded.shape[-1])
+            m.h1, m.h2, m.w1, m.w2 = self._meas_pad_idx
+        if resample:
+            m.scale_y, m.scale_x = float(sf[0]), float(sf[1])
+        return m, padded
+
     def get_measurements(self, indices=None):
-        """measurements[indices] with the optional on-the-fly pad / bilinear resample (models.py:384-416)."""
+        """measurements[indices] with the optional on-the-fly pad / bilinear resample (models.py:384-416); without indices the
+        stored array is returned as is, like the reference does (models.py:411-414)."""
         if indices is None:
             return self.measurements
         idx = self._index_tensor(indices)
-        meas = self.measurements[idx]
-        if self.meas_padded is not None:
-            h1, h2, w1, w2 = [int(v) for v in self.meas_padded_idx]
-            canvas = self.meas_padded.expand(meas.shape[0], -1, -1).clone()
-            canvas[..., h1:h2, w1:w2] = meas
-            meas = canvas
-        sf = self.meas_scale_factors
-        if sf is not None and any(f != 1 for f in sf):
-            meas = torch.nn.functional.interpolate(meas[None], scale_factor=tuple(sf), mode="bilinear")[0] / math.prod(sf)
-        return meas
+        mcfg, padded = self._meas_cfg()
+        if mcfg is None:
+            return self.measurements[idx]
+        N = self.opt_probe.shape[1]
+        cfg = engine.make_cfg(N, 1, 1, 1, N, N, self.measurements.shape[0], 0, 0, 0, 1.0, 1.0)
+        return engine.gather_measurements(cfg, mcfg, self.measurements, padded, idx)
 
     def clear_cache(self):
         self._current_object_patches = None

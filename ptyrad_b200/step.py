@@ -51,20 +51,31 @@ class GradArena:
         self.flat.zero_()
 
     def allreduce(self, world: int, group=None):
+        """Mean over the ranks of every gradient: ONE collective on the flat buffer.  NCCL averages inside the reduction
+        (ReduceOp.AVG: no separate scaling launch after the last adjoint CTA); gloo (CPU tests) has no AVG, so sum then scale."""
         if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / world)
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.mul_(1.0 / world)
 
 
 def shard_indices(indices, rank: int, world: int):
     """Rank `rank`'s slice of one global batch: contiguous split, sizes differing by at most one
     (accelerate's split_batches=True dispatch, utils/common.py:61-65, reconstruction.py:134-137)."""
-    return np.array_split(np.asarray(indices), world)[rank]
+    indices = np.asarray(indices)
+    if len(indices) < world:
+        # np.array_split would hand some rank an empty shard: that rank would fail its kernel-configuration check while the others
+        # block in the all-reduce.  Every rank sees the same global batch, so every rank raises here.
+        raise ValueError(f"a global batch of {len(indices)} positions cannot be split over {world} ranks")
+    return np.array_split(indices, world)[rank]
 
 
 def direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements) -> bool:
-    """The autograd-free step covers the default configuration: native loss terms only, no blur / pad / resample options,
-    gradients written once into the arena (no accumulation over batches)."""
+    """The autograd-free step covers: native loss terms (single / poissn / pacbed / sparse), detector blur, on-the-fly measurement
+    pad / resample; gradients written once into the arena (no accumulation over batches).  Object pre-blur and loss_simlar take
+    the autograd route."""
     if arena is None or grad_accumulation != 1 or not do_step or not torch.is_grad_enabled():
         return False
     if type(loss_fn) is not CombinedLoss or loss_fn.loss_params["loss_simlar"]["state"]:
@@ -72,9 +83,7 @@ def direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, meas
     lp = loss_fn.loss_params
     if not (lp["loss_single"]["state"] or lp["loss_poissn"]["state"] or lp["loss_pacbed"]["state"]):
         return False
-    if model.obj_preblur_std or model.detector_blur_std:
-        return False
-    if measurements is None and (model.meas_padded is not None or model.meas_scale_factors is not None):
+    if model.obj_preblur_std:
         return False
     if measurements is not None and not isinstance(measurements, MeasurementView):
         return False
@@ -110,13 +119,16 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
     sh = shifts if cfg.shift_probes else None
     _lib.check(lib.ptyb200_forward(C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
                                    ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws), st))
+    blur = model.detector_blur_std
+    if blur:                                                  # detector blur (models.py:379-380): native 5x5 kernel on the intensities
+        dp = engine._blur5(dp, float(blur), 0)
     # losses: [single, poissn, pacbed] and [sparse] land in one (5,) tensor; simlar (slot 4) is off on this path
-    lcfg = loss_fn._lcfg
+    lcfg = loss_fn.lcfg()
     losses = torch.zeros(5, dtype=torch.float32, device=dev)
     stats = torch.empty(8, dtype=torch.float64, device=dev)
     pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
     _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
-                                        ptr(pac), st))
+                                        ptr(pac), engine.mref(meas.mcfg), ptr(meas.padded), st))
     sparse = bool(lcfg.sparse_state)
     if sparse:
         Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
@@ -131,7 +143,9 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
             ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
         G = torch.empty_like(dp)
         _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(stats), ptr(pac),
-                                         ptr(ones), ptr(G), st))
+                                         ptr(ones), ptr(G), engine.mref(meas.mcfg), ptr(meas.padded), st))
+        if blur:
+            G = engine._blur5(G, float(blur), 1)              # adjoint of the blur
 
         def out(p, wanted):                                   # the arena view of a live parameter, scratch for a frozen one
             if not wanted:
@@ -153,9 +167,15 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
 
 
 def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = None, world: int = 1,
-                grad_accumulation: int = 1, do_step: bool = True, measurements=None, direct: bool | None = None):
-    """One batch: zero grads, forward, loss, backward, (all-reduce), optimizer step.  Returns the 5 loss terms as a device
-    tensor (no host sync).  `direct` (default: whenever eligible) takes the autograd-free route of `_direct_grads`."""
+                grad_accumulation: int = 1, do_step: bool = True, measurements=None, direct: bool | None = None,
+                first_of_group: bool = True):
+    """One batch: (zero grads), forward, loss, backward, (all-reduce), optimizer step.  Returns the 5 loss terms as a device
+    tensor (no host sync).  `direct` (default: whenever eligible) takes the autograd-free route of `_direct_grads`.
+
+    Gradient accumulation (reconstruction.py:750-760): pass `grad_accumulation` = group size, `first_of_group` = True only for the
+    first batch of a group (gradients are zeroed there and nowhere else) and `do_step` = True only for the last one."""
+    if world > 1 and arena is None:
+        raise RuntimeError("multi-GPU steps need a GradArena (the gradient exchange is one all-reduce over its flat buffer)")
     if direct is None:
         direct = direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements)
     elif direct and not direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements):
@@ -164,7 +184,7 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         arena.attach()
         arena.zero()
         idx = model._index_tensor(indices)
-        meas = measurements if measurements is not None else MeasurementView(model.measurements, idx)
+        meas = measurements if measurements is not None else MeasurementView(model.measurements, idx, model)
         losses = _direct_grads(model, loss_fn, idx, meas, arena)
         if world > 1:
             arena.allreduce(world)
@@ -172,56 +192,63 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         return losses
     if arena is not None:
         arena.attach()
-        arena.zero()
-    else:
+        if first_of_group:
+            arena.zero()
+    elif first_of_group:
         optimizer.zero_grad()
     dp = model(indices)
     idx = model._index_tensor(indices)
     if measurements is not None:
         meas = measurements
-    elif model.meas_padded is None and model.meas_scale_factors is None:
-        meas = MeasurementView(model.measurements, idx)          # read rows in place, no gathered copy
+    elif type(loss_fn) is CombinedLoss:
+        meas = MeasurementView(model.measurements, idx, model)   # read rows in place (pad / resample inside the loss kernels)
     else:
-        meas = model.get_measurements(idx)
+        meas = model.get_measurements(idx)                       # a foreign loss (e.g. the reference's) gets a real tensor
     total, losses = loss_fn(dp, meas, model._current_object_patches, model.omode_occu)
     (total / grad_accumulation if grad_accumulation != 1 else total).backward()
-    if world > 1:
-        if arena is None:
-            raise RuntimeError("multi-GPU steps need a GradArena")
-        arena.allreduce(world)
     if do_step:
+        if world > 1:
+            arena.allreduce(world)
         optimizer.step()
     model.clear_cache()
     return torch.stack([l.detach().reshape(()) for l in losses])
 
 
 class GraphedStep:
-    """`recon_batch` captured once into a CUDA graph and replayed per batch (sync-free, launch-free step).
+    """`recon_batch` captured into a CUDA graph and replayed per batch (sync-free, launch-free step).
 
     At the reference's default batch size (32) the per-batch work on a B200 is a few tens of microseconds while ~40 kernel
     launches plus autograd bookkeeping cost ~1 ms of host time; replaying a graph removes that.  One instance handles one batch
     size (``make_batches`` yields at most two distinct sizes).  The scan indices are the only per-step input: they are copied
     into a static device buffer.  Parameter storage must stay put between replays; constraints that rebind ``opt_*.data``
     (constraints.py:38-224) are handled by ``_rebind`` (values are copied back into the captured storage).
+
+    A captured graph bakes in WHICH tensors are trainable (the adjoint's need mask, the arena views the kernels write, the
+    optimiser's tensor list), while the reference re-evaluates ``requires_grad`` every iteration (``start_iter``,
+    reconstruction.py:783-790).  Graphs are therefore keyed by the requires_grad signature: a signature seen for the first time
+    is captured on the spot, later ones replay.  Capturing runs the step a few times; parameters AND optimiser state are
+    snapshotted before and restored afterwards, so building (or re-capturing) a GraphedStep mid-run, or after
+    ``optimizer.load_state_dict`` (reconstruction.py:356-364), leaves the Adam moments and step counters exactly as they were.
     """
 
     def __init__(self, model, loss_fn, optimizer, arena: GradArena, batch_size: int, grad_accumulation: int = 1, warmup: int = 2,
                  world: int = 1, stream_measurements: bool = False):
-        if model.meas_padded is not None or model.meas_scale_factors is not None:
-            raise NotImplementedError("GraphedStep reads the measurements in place; on-the-fly pad/resample is not captured")
+        if grad_accumulation != 1:
+            raise ValueError("GraphedStep captures a whole step (zero, forward, adjoint, exchange, optimizer): use the eager "
+                             "recon_batch / recon_step for gradient accumulation")
         self.model, self.loss_fn, self.opt, self.arena = model, loss_fn, optimizer, arena
         self.B = int(batch_size)
+        self.world, self.warmup = world, warmup
         dev = model.opt_obja.device
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.params = list(model.optimizable_tensors.values())
         # stream_measurements: this batch's patterns are copied into `self.meas` before every replay (dataset in host memory)
         self.meas = None
-        mv = None
+        self._mv = None
         if stream_measurements:
-            N = model.opt_probe.shape[1]
-            self.meas = torch.zeros((self.B, N, N), dtype=torch.float32, device=dev)
-            mv = MeasurementView(self.meas, torch.arange(self.B, device=dev))
-            self._mv = mv            # the captured graph reads these buffers by address: keep them alive with the graph
+            Nm = model.measurements.shape[-1]
+            self.meas = torch.zeros((self.B, Nm, Nm), dtype=torch.float32, device=dev)
+            self._mv = MeasurementView(self.meas, torch.arange(self.B, device=dev), model)   # read by address: lives with the graphs
             # double buffering for `prefetch`: the next batch is copied host -> device on a side stream while this one runs
             self._next_meas = torch.zeros_like(self.meas)
             self._next_idx = torch.zeros_like(self.idx)
@@ -229,35 +256,64 @@ class GraphedStep:
             self._copy_done = torch.cuda.Event()
             self._consumed = torch.cuda.Event()
             self._consumed.record(torch.cuda.current_stream(dev))
-        # warm-up and capture must not change the model: snapshot parameters and optimizer state, restore afterwards
-        # (a fresh optimizer is assumed: its state is zeroed again after the capture)
+        self._graphs = {}
+        self._ptrs = [p.data_ptr() for p in self.params]
+        self._store = [p.data for p in self.params]
+        self._capture(self.signature())
+
+    def signature(self):
+        return tuple(bool(p.requires_grad) for p in self.params)
+
+    # -- optimiser state: values are saved and written back INTO the same tensors (the graphs hold their addresses)
+    def _snapshot_opt(self):
+        snap = {}
+        for group in self.opt.param_groups:
+            for p in group["params"]:
+                st = self.opt.state.get(p)
+                snap[p] = None if not st else {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return snap
+
+    def _restore_opt(self, snap):
+        with torch.no_grad():
+            for p, old in snap.items():
+                st = self.opt.state.get(p)
+                if not st:
+                    continue
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is None or k not in old:
+                            v.zero_()                     # created by the warm-up steps: back to its initial value
+                        elif v.data_ptr() != old[k].data_ptr():
+                            v.copy_(old[k])
+                    elif old is not None and k in old:
+                        st[k] = old[k]
+
+    def _capture(self, sig):
+        model, dev = self.model, self.idx.device
+        self._rebind()
         snap_p = [p.detach().clone() for p in self.params]
+        snap_o = self._snapshot_opt()
+        run = lambda: recon_batch(model, self.loss_fn, self.opt, self.idx, self.arena, self.world, measurements=self._mv)
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
-            for i in range(warmup):
-                recon_batch(model, loss_fn, optimizer, self.idx, arena, world, grad_accumulation, measurements=mv)
+            for i in range(self.warmup):
+                run()
         torch.cuda.current_stream(dev).wait_stream(stream)
         torch.cuda.synchronize(dev)
-        self._restore(snap_p, zero_opt=True)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.losses = recon_batch(model, loss_fn, optimizer, self.idx, arena, world, grad_accumulation, measurements=mv)
-        self._restore(snap_p, zero_opt=True)
-        self._ptrs = [p.data_ptr() for p in self.params]
-        self._store = [p.data for p in self.params]
+        # the warm-up may have created optimiser state; restore values before capture so that nothing captured depends on them
+        self._restore(snap_p, snap_o)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            losses = run()
+        self._restore(snap_p, snap_o)
+        self._graphs[sig] = (graph, losses)
 
-    def _restore(self, snap_p, zero_opt):
+    def _restore(self, snap_p, snap_o):
         with torch.no_grad():
             for p, s in zip(self.params, snap_p):
                 p.data.copy_(s)
-            if zero_opt:
-                for st in self.opt.state.values():
-                    for v in st.values():
-                        if torch.is_tensor(v):
-                            v.zero_()
-                if hasattr(self.opt, "_step_dev") and self.opt._step_dev is not None:
-                    self.opt._step_dev.zero_()
+        self._restore_opt(snap_o)
 
     def _rebind(self):
         for i, p in enumerate(self.params):
@@ -265,6 +321,19 @@ class GraphedStep:
                 with torch.no_grad():
                     self._store[i].copy_(p.data)
                 p.data = self._store[i]
+
+    def _replay(self):
+        sig = self.signature()
+        if sig not in self._graphs:
+            self._capture(sig)                            # first time this set of trainable tensors is seen (start_iter)
+        graph, losses = self._graphs[sig]
+        self.arena.attach()
+        graph.replay()
+        return losses
+
+    @property
+    def losses(self):
+        return self._graphs[self.signature()][1]
 
     def prefetch(self, indices, measurements):
         """Start the host -> device copy of the NEXT batch (pinned tensors) on a side stream; pair with `step_prefetched`."""
@@ -282,8 +351,7 @@ class GraphedStep:
         self.idx.copy_(self._next_idx, non_blocking=True)
         self.meas.copy_(self._next_meas, non_blocking=True)
         self._consumed.record(cur)
-        self.graph.replay()
-        return self.losses
+        return self._replay()
 
     def __call__(self, indices, measurements=None):
         self._rebind()
@@ -294,8 +362,7 @@ class GraphedStep:
         if indices.numel() != self.B:
             raise ValueError(f"this graph was captured for batch size {self.B}, got {indices.numel()}")
         self.idx.copy_(indices, non_blocking=True)
-        self.graph.replay()
-        return self.losses
+        return self._replay()
 
 
 def toggle_grad_requires(model, niter: int):
@@ -322,6 +389,8 @@ def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
+    if world > 1 and arena is None:
+        raise RuntimeError("multi-GPU iterations need a GradArena (the gradient exchange is one all-reduce over its flat buffer)")
     toggle_grad_requires(model, niter)
     if arena is not None:
         arena.attach()
@@ -342,10 +411,7 @@ def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint
             continue
         dp = model(mine)
         idx = model._index_tensor(mine)
-        if model.meas_padded is None and model.meas_scale_factors is None:
-            meas = MeasurementView(model.measurements, idx)
-        else:
-            meas = model.get_measurements(idx)
+        meas = MeasurementView(model.measurements, idx, model) if type(loss_fn) is CombinedLoss else model.get_measurements(idx)
         total, losses = loss_fn(dp, meas, model._current_object_patches, model.omode_occu)
         (total / grad_accumulation).backward()
         if last_of_group:

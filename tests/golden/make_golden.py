@@ -4,7 +4,7 @@ Run in the build container only (needs /root/reference, which does not exist on 
 
     python tests/golden/make_golden.py
 
-For every case it builds synthetic inputs (ptyrad_b200.synthetic), instantiates the reference's own
+For every case it builds synthetic inputs (workloads), instantiates the reference's own
 ``ptyrad.models.PtychoAD`` and ``ptyrad.losses.CombinedLoss`` on the CPU in float32, runs
 forward -> get_measurements -> loss -> backward (the sequence of reconstruction.py:792-806,753) and stores
 inputs, intensities, the five loss terms and the dense gradients in ``tests/golden/<case>.npz``.
@@ -25,7 +25,7 @@ sys.path.insert(0, "/root/reference/src")
 from ptyrad.models import PtychoAD          # noqa: E402  (reference, unmodified)
 from ptyrad.losses import CombinedLoss      # noqa: E402
 
-from ptyrad_b200.synthetic import CONFIGS, ScanConfig, make_inputs, default_loss_params  # noqa: E402
+from workloads import CONFIGS, ScanConfig, make_inputs, default_loss_params  # noqa: E402
 
 BASE = ScanConfig("G", N=32, scan=4, P=2, M=2, Z=3, batch=5, step=0.6, lr_shifts=1e-4)
 
@@ -50,6 +50,10 @@ def cases():
         "g_dz_only": (replace(BASE, M=1, lr_dz=1e-4), lp_single, {}),
         "g_simlar": (BASE, lp_sim, {}),
         "g_n48": (replace(BASE, N=48, scan=3, M=1, P=2, Z=2, batch=4), lp_single, {}),
+        # depth: 8 slices = 15 chained FFT pairs per wave (the C2 depth), shifts + per-position tilts optimised
+        "g_z8": (replace(BASE, M=1, P=3, Z=8, tilt_each=True, lr_tilts=1e-4), lp_single, {}),
+        # depth: 16 slices, two object modes, Poisson + sparse (the C4 / C5 depth)
+        "g_z16_poissn": (replace(BASE, P=2, M=2, Z=16, batch=3), lp_poissn, {}),
     }
     return out
 
@@ -92,7 +96,10 @@ def run_reference(iv, mp, lp, idx, dtype):
 
 
 def main():
+    only = sys.argv[1:]                       # optional: names of the cases to (re)generate
     for name, (cfg, lp, extra) in cases().items():
+        if only and name not in only:
+            continue
         iv, mp, _ = make_inputs(cfg, seed=1234)
         if "global_tilt" in extra:
             iv["obj_tilts"] = np.array([extra["global_tilt"]], np.float32)

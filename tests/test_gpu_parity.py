@@ -81,7 +81,7 @@ def test_roi_gather_bit_exact(name):
 @pytest.mark.parametrize("cfg_name", ["T32", "T48", "T64", "T128", "T128m", "T192", "T256"])
 def test_oracle_f64_synthetic(cfg_name):
     from oracle.ptycho_torch import oracle_step
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     iv, mp, lp = make_inputs(cfg_name, seed=11)
     cfg = CONFIGS[cfg_name]
     rng = np.random.default_rng(5)
@@ -91,12 +91,62 @@ def test_oracle_f64_synthetic(cfg_name):
     _check(r, ref["dp"], ref["losses"], ref["grads"], cfg_name)
 
 
+@pytest.mark.parametrize("route", ["autograd", "direct"])
+@pytest.mark.parametrize("cfg_name", ["C2d", "C3d", "C4d", "C5d"])
+def test_baseline_configs_at_depth(cfg_name, route):
+    """BASELINE.json configs C2..C5 at their OWN depth -- same N, probe modes, object modes, slices (C3: 32 slices = 63 chained
+    FFTs, per-position tilts + sub-pixel shifts optimised; C4: 12 modes x 16 slices; C5: 192^2, two object modes, Poisson) -- on a
+    3x3 / 4x4 scan so that the float64 oracle (forward.py:53-79 + autograd) takes seconds.  Both routes a user can take: the
+    PtychoAD / CombinedLoss / backward() surface and the autograd-free recon_batch(direct=True)."""
+    from oracle.ptycho_torch import oracle_step
+    from workloads import make_inputs, CONFIGS
+    cfg = CONFIGS[cfg_name]
+    iv, mp, lp = make_inputs(cfg, seed=41)
+    rng = np.random.default_rng(9)
+    idx = np.sort(rng.choice(cfg.scan ** 2, cfg.batch, replace=False)).astype(np.int64)
+    ref = oracle_step(iv, mp, lp, idx, torch.float64)
+    if route == "autograd":
+        r = _run(iv, mp, lp, idx)
+    else:
+        from ptyrad_b200 import PtychoAD, CombinedLoss
+        from ptyrad_b200.step import GradArena, recon_batch
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        arena = GradArena(model)
+
+        class NoStep:                                       # keep the gradients: the arena is what the kernels wrote
+            def step(self):
+                pass
+        losses = recon_batch(model, loss_fn, NoStep(), idx, arena, direct=True)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            dp = model(idx)
+        r = dict(dp=dp.cpu().numpy(), losses=losses.cpu().numpy(),
+                 grads={k: t.grad.detach().cpu().numpy() for k, t in model.optimizable_tensors.items() if t.grad is not None})
+    _check(r, ref["dp"], ref["losses"], ref["grads"], f"{cfg_name}/{route}")
+    MARGINS.append((cfg_name, route, rel(r["dp"], ref["dp"]), {k: rel(r["grads"][k], g) for k, g in ref["grads"].items()}))
+
+
+MARGINS = []
+
+
+def test_depth_margins_table():
+    """Not a check: writes the margins of the depth cases to gpurun_out/depth_margins.json (summarised under profiles/)."""
+    import json, os
+    rows = [dict(cfg=n, route=r, dp=e, grads=g) for n, r, e, g in MARGINS]
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump(rows, open(os.path.join(out, "depth_margins.json"), "w"), indent=1)
+    for row in rows:
+        print("MARGIN", row)
+
+
 @pytest.mark.parametrize("cfg_name", ["T128", "T128m"])
 def test_general_path_matches_auto_path(cfg_name):
     """N = 128 has two implementations (fused on-chip and general row/column passes): both must agree with the oracle."""
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import _lib
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     iv, mp, lp = make_inputs(cfg_name, seed=12)
     cfg = CONFIGS[cfg_name]
     idx = np.arange(cfg.batch, dtype=np.int64)
@@ -113,7 +163,7 @@ def test_general_path_chunked_batches(cfg_name, chunk, pg):
     from dataclasses import replace
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import _lib
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     cfg = CONFIGS[cfg_name]
     if cfg_name == "T64":
         cfg = replace(cfg, tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4)
@@ -134,7 +184,7 @@ def test_general_path_unshifted_probe_chunked():
     from dataclasses import replace
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import _lib
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     cfg = replace(CONFIGS["T64"], lr_shifts=0.0)
     iv, mp, lp = make_inputs(cfg, seed=14)
     idx = np.arange(cfg.batch, dtype=np.int64)
@@ -151,7 +201,7 @@ def test_direct_step_matches_autograd_step(case):
     from ptyrad_b200 import PtychoAD, CombinedLoss
     from ptyrad_b200.optim import FusedAdam
     from ptyrad_b200.step import GradArena, recon_batch, direct_step_eligible
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     name = case.split("+")[0].split("-")[0]
     cfg = CONFIGS[name]
     if "tilt" in case:
@@ -189,7 +239,7 @@ def test_tilt_and_thickness_gradients():
     """Cases 1 / 2A / 3 of get_propagators (models.py:339-360) on a 64^2 problem against the float64 oracle."""
     from dataclasses import replace
     from oracle.ptycho_torch import oracle_step
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     base = CONFIGS["T64"]
     for label, cfg in (("each+dz", replace(base, tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4)),
                        ("each", replace(base, tilt_each=True, lr_tilts=1e-4)),
@@ -208,7 +258,7 @@ def test_fused128_variants(label):
     from dataclasses import replace
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import _lib
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS, default_loss_params
+    from workloads import make_inputs, CONFIGS, default_loss_params
     base = CONFIGS["T128"]
     lp_over = None
     if label == "tilt_each+dz":
@@ -237,7 +287,7 @@ def test_fused128_variants(label):
 
 
 def test_frozen_parameters_cost_nothing_and_get_no_grad():
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T64", seed=2)
     from ptyrad_b200 import PtychoAD, CombinedLoss
     model = PtychoAD(iv, mp, device="cuda", verbose=False)
@@ -254,7 +304,7 @@ def test_frozen_parameters_cost_nothing_and_get_no_grad():
 def test_energy_conservation_full_size():
     """Size-independent property at the benchmark shape (C2): with a unit-amplitude object and norm='ortho',
     sum(dp) == sum|probe|^2 for every pattern (forward.py:77)."""
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     from ptyrad_b200 import PtychoAD
     iv, mp, lp = make_inputs("C2", seed=1, simulate_measurements=False)
     iv["obj"] = np.exp(1j * np.angle(iv["obj"])).astype(np.complex64)
@@ -270,7 +320,7 @@ def test_energy_conservation_full_size():
 
 def test_adjoint_dot_product_full_size():
     """<J dx, G> == <dx, J^T G> at the C2 shape with the CUDA forward (finite difference) and CUDA adjoint."""
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     from ptyrad_b200 import PtychoAD
     iv, mp, lp = make_inputs("C2", seed=4, simulate_measurements=False)
     model = PtychoAD(iv, mp, device="cuda", verbose=False)
@@ -318,7 +368,7 @@ def test_graphed_step_matches_eager_step():
     from ptyrad_b200 import PtychoAD, CombinedLoss
     from ptyrad_b200.optim import FusedAdam
     from ptyrad_b200.step import GradArena, GraphedStep, recon_batch
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T64", seed=8)
     batches = [np.arange(0, 7), np.arange(7, 14), np.arange(14, 21)]
     out = []
@@ -346,7 +396,7 @@ def test_several_forwards_before_one_backward():
     backward once: every forward must keep its own saved state (workspace in the autograd ctx)."""
     from oracle.ptycho_torch import OracleModel, loss_terms
     from ptyrad_b200 import PtychoAD, CombinedLoss
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T64", seed=13)
     batches = [np.arange(0, 6), np.arange(6, 13), np.arange(13, 18)]
     model = PtychoAD(iv, mp, device="cuda", verbose=False)
@@ -378,7 +428,7 @@ def test_ten_adam_steps_track_the_oracle(cfg_name):
     from ptyrad_b200 import PtychoAD, CombinedLoss
     from ptyrad_b200.optim import FusedAdam
     from ptyrad_b200.step import GradArena, recon_batch
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     iv, mp, lp = make_inputs(cfg_name, seed=17)
     n = CONFIGS[cfg_name].scan ** 2
     rng = np.random.default_rng(3)
@@ -408,7 +458,7 @@ def test_grad_accumulation_and_frozen_start_iter():
     """Two accumulated half-batches == the reference's loss/grad_accumulation semantics (reconstruction.py:750-760)."""
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import PtychoAD, CombinedLoss
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T64", seed=19)
     model = PtychoAD(iv, mp, device="cuda", verbose=False)
     loss_fn = CombinedLoss(lp, device="cuda")
@@ -429,7 +479,7 @@ def test_recon_step_iterations_with_start_iter_and_constraint():
     from oracle.ptycho_torch import OracleModel, loss_terms
     from ptyrad_b200 import PtychoAD, CombinedLoss
     from ptyrad_b200.step import GradArena, recon_step
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T64", seed=23)
     mp = copy.deepcopy(mp)
     mp["update_params"]["probe"]["start_iter"] = 2
@@ -482,7 +532,7 @@ def test_object_preblur_and_detector_blur(cfg_name):
     import copy
     from oracle.ptycho_torch import OracleModel, loss_terms, _gauss5
     from ptyrad_b200 import PtychoAD, CombinedLoss
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     iv, mp, lp = make_inputs(cfg_name, seed=29)
     mp = copy.deepcopy(mp)
     mp["obj_preblur_std"], mp["detector_blur_std"] = 1.0, 0.8
@@ -520,7 +570,7 @@ def test_graphed_step_with_streamed_measurements_and_prefetch():
     from ptyrad_b200 import PtychoAD, CombinedLoss
     from ptyrad_b200.optim import FusedAdam
     from ptyrad_b200.step import GradArena, GraphedStep, recon_batch
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T64", seed=37)
     batches = [np.arange(0, 8), np.arange(8, 16), np.arange(16, 24), np.arange(3, 11)]
     res = []
@@ -567,3 +617,199 @@ def test_native_gaussian_blur_and_adjoint(shape, sigma):
     lhs = float((out.detach().double().cpu() * y).sum())
     rhs = float((x * xc.grad.double().cpu()).sum())
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+
+
+def _otf_inputs(cfg_name="T64", seed=43, pad=True, scale=None):
+    """T-case whose measurements are stored SMALLER than the model's pattern size and padded / resampled on the fly
+    (the PSO demo does 120 -> 256 by padding: demo/params/PSO_reconstruct.yml).  Returns (iv for our model, iv for the oracle with the
+    transformed measurements materialised by the reference's own tensor expressions, mp, lp)."""
+    import copy
+    from workloads import make_inputs
+    iv, mp, lp = make_inputs(cfg_name, seed=seed)
+    N = iv["probe"].shape[-1]
+    full = torch.as_tensor(iv["measurements"]).repeat(1, 2, 2)      # enough pixels for the down-sampling cases
+    s = scale or (1.0, 1.0)
+    Hp, Wp = int(round(N / s[0])), int(round(N / s[1]))            # size before resampling
+    if pad:
+        h1, w1 = Hp // 5, Wp // 4
+        Hs, Ws = Hp - 2 * h1, Wp - 2 * w1
+        stored = full[:, :Hs, :Ws].contiguous()
+        bg = 0.05 * torch.rand((Hp, Wp), generator=torch.Generator().manual_seed(1))
+        idxs = [h1, h1 + Hs, w1, w1 + Ws]
+    else:
+        stored, bg, idxs = full[:, :Hp, :Wp].contiguous(), None, None
+    # the reference's expressions (models.py:399-409), on the CPU, for every position
+    m = stored
+    if pad:
+        canvas = torch.zeros((m.shape[0], Hp, Wp)) + bg
+        canvas[..., idxs[0]:idxs[1], idxs[2]:idxs[3]] = m
+        m = canvas
+    if scale is not None:
+        m = torch.nn.functional.interpolate(m[None], scale_factor=tuple(scale), mode="bilinear")[0] / (scale[0] * scale[1])
+    assert m.shape[-2:] == (N, N), m.shape
+    iv_o = dict(iv); iv_o["measurements"] = m.numpy()
+    iv_n = dict(iv); iv_n["measurements"] = stored.numpy()
+    if pad:
+        iv_n["on_the_fly_meas_padded"] = bg.numpy()
+        iv_n["on_the_fly_meas_padded_idx"] = idxs
+    if scale is not None:
+        iv_n["on_the_fly_meas_scale_factors"] = list(scale)
+    return iv_n, iv_o, copy.deepcopy(mp), lp
+
+
+@pytest.mark.parametrize("pad,scale", [(True, None), (False, (2.0, 2.0)), (True, (2.0, 2.0)), (True, (0.5, 0.5)), (False, (1.6, 1.6))])
+def test_on_the_fly_measurement_pad_and_resample(pad, scale):
+    """models.py:392-409 natively: the loss kernels evaluate the padded / bilinearly resampled pattern per pixel.  (i) the tensor
+    form get_measurements(indices) equals the reference's torch expressions; (ii) losses + gradients of the autograd route, the
+    autograd-free route and the CUDA-graph route equal the float64 oracle fed with the materialised patterns; also with the
+    detector blur on (the PSO demo's options)."""
+    from oracle.ptycho_torch import OracleModel, loss_terms, _gauss5
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch, direct_step_eligible
+    iv_n, iv_o, mp, lp = _otf_inputs(pad=pad, scale=scale)
+    mp["detector_blur_std"] = 1.0
+    idx = np.array([0, 3, 4, 8, 15, 21, 24], dtype=np.int64)
+    model = PtychoAD(iv_n, mp, device="cuda", verbose=False)
+    got = model.get_measurements(idx).cpu().numpy()
+    np.testing.assert_allclose(got, iv_o["measurements"][idx], rtol=2e-6, atol=1e-8)
+    assert model.get_measurements().shape == iv_n["measurements"].shape          # no indices: stored array, untransformed (models.py:411-414)
+    # float64 oracle with the blur applied to the intensities
+    om = OracleModel(iv_o, mp, torch.float64)
+    dp, (a, p) = om.forward(idx)
+    dp = _gauss5(dp, 1.0)
+    otot, oterms = loss_terms(dp, om.meas[torch.as_tensor(idx)], p, om.occu, lp, obja_patches=a)
+    otot.backward()
+    ref_g = {k: t.grad.numpy() for k, t in om.params().items() if om.lr[k] != 0}
+    ref_l = np.array([float(t.detach()) for t in oterms])
+    # autograd route (PtychoAD / CombinedLoss / backward)
+    r = _run(iv_n, mp, lp, idx)
+    _check(r, dp.detach().numpy(), ref_l, ref_g, "otf/autograd")
+    # autograd-free and graphed routes
+    for graphed in (False, True):
+        model = PtychoAD(iv_n, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        arena = GradArena(model)
+        assert direct_step_eligible(model, loss_fn, arena, 1, True, None)
+
+        class NoStep(FusedAdam):
+            def step(self, closure=None):
+                pass
+        opt = NoStep(model.optimizable_params)
+        if graphed:
+            losses = GraphedStep(model, loss_fn, opt, arena, len(idx))(idx).clone()
+        else:
+            losses = recon_batch(model, loss_fn, opt, idx, arena, direct=True)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(losses.cpu().numpy(), ref_l, rtol=TOL_LOSS, atol=1e-9)
+        for k, g in ref_g.items():
+            e = rel(model.optimizable_tensors[k].grad.cpu().numpy(), g)
+            assert e < TOL_G[k], f"otf/{'graph' if graphed else 'direct'}: grad {k} {e:.2e}"
+
+
+def test_fused_adam_per_tensor_step_with_staggered_start():
+    """A tensor that joins at a later iteration (start_iter, reconstruction.py:783-790) starts ITS bias correction at step 1, as
+    torch.optim.Adam's per-parameter state['step'] does; load_state_dict round-trips the counters."""
+    from ptyrad_b200.optim import FusedAdam
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pa = [torch.randn(s, device="cuda", generator=g).requires_grad_(True) for s in [(3, 40, 50), (2, 16, 16, 2), (30, 2)]]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    lrs = [5e-4, 1e-4, 1e-3]
+    oa = torch.optim.Adam([dict(params=[p], lr=lr) for p, lr in zip(pa, lrs)])
+    ob = FusedAdam([dict(params=[p], lr=lr) for p, lr in zip(pb, lrs)])
+    start = [1, 4, 2]
+    for it in range(1, 7):
+        for i, (p, q) in enumerate(zip(pa, pb)):
+            if it >= start[i]:
+                gr = torch.randn(p.shape, device="cuda", generator=g)
+                p.grad, q.grad = gr.clone(), gr.clone()
+            else:
+                p.grad = q.grad = None
+        oa.step(); ob.step()
+        if it == 4:                                                     # checkpoint / resume in the middle
+            sd = ob.state_dict()
+            ob = FusedAdam([dict(params=[p], lr=lr) for p, lr in zip(pb, lrs)])
+            ob.load_state_dict(sd)
+    for p, q in zip(pa, pb):
+        torch.testing.assert_close(q, p, rtol=3e-6, atol=1e-7)
+    assert [float(ob.state[q]["step"]) for q in pb] == [6.0, 3.0, 5.0]
+    # a state dict written by torch.optim.Adam (step may live on the CPU) is accepted
+    oc = FusedAdam([dict(params=[p], lr=lr) for p, lr in zip(pb, lrs)])
+    oc.load_state_dict(oa.state_dict())
+    for q in pb:
+        q.grad = torch.ones_like(q)
+    oc.step()
+    assert float(oc.state[pb[1]]["step"]) == 4.0
+
+
+def test_graphed_step_keeps_optimizer_state_and_follows_start_iter():
+    """(i) a GraphedStep built in the middle of a run (or after optimizer.load_state_dict) must not touch the Adam moments / step
+    counters; (ii) requires_grad toggled by start_iter between iterations selects / captures the matching graph: a tensor with
+    start_iter = 2 is NOT updated in iteration 1.  Reference: eager recon_step on a twin model."""
+    import copy
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch, recon_step
+    from workloads import make_inputs
+    iv, mp, lp = make_inputs("T64", seed=61)
+    mp = copy.deepcopy(mp)
+    mp["update_params"]["probe"]["start_iter"] = 2
+    mp["update_params"]["probe_pos_shifts"]["start_iter"] = 3
+    batches = [np.arange(0, 8), np.arange(8, 16), np.arange(16, 24)]
+    out = []
+    for graphed in (False, True):
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        opt = FusedAdam(model.optimizable_params)
+        arena = GradArena(model)
+        hist = []
+        # iteration 1 always eager (so that the optimizer has state when the graph is built)
+        hist.append(recon_step(batches, 1, model, opt, loss_fn, None, 1, verbose=False, arena=arena))
+        probe_after_1 = model.opt_probe.detach().clone()
+        gs = None
+        if graphed:
+            before = {k: v.clone() for k, v in opt.state[model.opt_objp].items()}
+            from ptyrad_b200.step import toggle_grad_requires
+            toggle_grad_requires(model, 2)
+            gs = {8: GraphedStep(model, loss_fn, opt, arena, 8)}
+            after = opt.state[model.opt_objp]
+            for k in before:
+                assert torch.equal(before[k], after[k]), f"GraphedStep construction changed optimizer state '{k}'"
+            assert float(after["step"]) == 3.0
+        for it in (2, 3, 4):
+            hist.append(recon_step(batches, 1, model, opt, loss_fn, None, it, verbose=False, arena=arena, graphed=gs))
+        torch.cuda.synchronize()
+        if graphed:
+            assert len(gs[8]._graphs) == 2                    # iteration 2 (probe joins) and iterations 3-4 (shifts join)
+        out.append((hist, {k: v.detach().cpu().numpy() for k, v in model.optimizable_tensors.items()}, probe_after_1.cpu().numpy(),
+                    {k: float(opt.state[p]["step"]) for k, p in model.optimizable_tensors.items() if p in opt.state}))
+    assert np.array_equal(out[0][2], np.stack([iv["probe"].real, iv["probe"].imag], -1))      # probe frozen in iteration 1
+    assert out[0][3] == out[1][3] == {"obja": 12.0, "objp": 12.0, "probe": 9.0, "probe_pos_shifts": 6.0}
+    for it in range(4):
+        for k in lp:
+            np.testing.assert_allclose(out[1][0][it][k], out[0][0][it][k], rtol=5e-5, atol=1e-7, err_msg=f"iter {it + 1} {k}")
+    for k in out[0][1]:
+        assert rel(out[1][1][k], out[0][1][k]) < 2e-5, k
+
+
+def test_accumulate_two_half_batches_then_step():
+    """recon_batch(first_of_group / do_step): gradients of a group of batches ADD in the arena (reconstruction.py:750-760)."""
+    from oracle.ptycho_torch import oracle_step
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.step import GradArena, recon_batch
+    from workloads import make_inputs
+    iv, mp, lp = make_inputs("T64", seed=19)
+    model = PtychoAD(iv, mp, device="cuda", verbose=False)
+    loss_fn = CombinedLoss(lp, device="cuda")
+    arena = GradArena(model)
+
+    class NoStep:
+        def step(self):
+            pass
+    b1, b2 = np.arange(0, 6), np.arange(6, 12)
+    recon_batch(model, loss_fn, NoStep(), b1, arena, grad_accumulation=2, do_step=False, first_of_group=True)
+    recon_batch(model, loss_fn, NoStep(), b2, arena, grad_accumulation=2, do_step=True, first_of_group=False)
+    r1 = oracle_step(iv, mp, lp, b1, torch.float64)["grads"]
+    r2 = oracle_step(iv, mp, lp, b2, torch.float64)["grads"]
+    for k in r1:
+        assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), 0.5 * (r1[k] + r2[k])) < TOL_G[k], k

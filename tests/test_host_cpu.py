@@ -77,7 +77,7 @@ def test_grad_arena_layout_and_direct_step_eligibility():
     accesses), frozen tensors get grad=None; the autograd-free step is chosen only for configurations it covers."""
     from ptyrad_b200 import CombinedLoss
     from ptyrad_b200.step import GradArena, direct_step_eligible
-    from ptyrad_b200.synthetic import default_loss_params
+    from workloads import default_loss_params
     m, iv, mp, lp = _model(tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4, lr_shifts=1e-4)
     arena = GradArena(m)
     base = arena.flat.data_ptr()
@@ -97,8 +97,11 @@ def test_grad_arena_layout_and_direct_step_eligibility():
     simlar = default_loss_params("single"); simlar["loss_simlar"]["state"] = True
     assert not direct_step_eligible(m, CombinedLoss(simlar, device="cpu"), arena, 1, True, None)
     m.detector_blur_std = 1.0
-    assert not direct_step_eligible(m, loss, arena, 1, True, None)
+    assert direct_step_eligible(m, loss, arena, 1, True, None)               # detector blur: native blur + adjoint on dp / G
     m.detector_blur_std = None
+    m.obj_preblur_std = 1.0
+    assert not direct_step_eligible(m, loss, arena, 1, True, None)           # pre-blurred ROIs go through autograd (patch mode)
+    m.obj_preblur_std = None
     with torch.no_grad():
         assert not direct_step_eligible(m, loss, arena, 1, True, None)
 
@@ -106,7 +109,7 @@ def test_grad_arena_layout_and_direct_step_eligibility():
 def _model(name="T32", **kw):
     from dataclasses import replace
     from ptyrad_b200 import PtychoAD
-    from ptyrad_b200.synthetic import make_inputs, CONFIGS
+    from workloads import make_inputs, CONFIGS
     iv, mp, lp = make_inputs(replace(CONFIGS[name], **kw), seed=5)
     return PtychoAD(iv, mp, device="cpu", verbose=False), iv, mp, lp
 
@@ -168,7 +171,7 @@ def test_hot_path_refuses_cpu_tensors():
 
 def test_validation_rejects_bad_inputs():
     from ptyrad_b200 import PtychoAD
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     iv, mp, lp = make_inputs("T32", seed=5)
     bad = dict(iv); bad["crop_pos"] = iv["crop_pos"].copy(); bad["crop_pos"][0] = [10000, 0]
     with pytest.raises(ValueError, match="canvas"):
@@ -181,7 +184,7 @@ def test_validation_rejects_bad_inputs():
 def test_loss_cfg_and_shard_indices():
     from ptyrad_b200 import engine
     from ptyrad_b200.step import shard_indices
-    from ptyrad_b200.synthetic import default_loss_params
+    from workloads import default_loss_params
     l = engine.make_loss_cfg(default_loss_params("poissn"))
     assert (l.single_state, l.poissn_state, l.pacbed_state, l.sparse_state) == (0, 1, 0, 1)
     assert abs(l.poissn_eps - 1e-6) < 1e-12 and l.sparse_order == 1.0
@@ -197,7 +200,7 @@ def _gloo_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     from ptyrad_b200 import PtychoAD
     from ptyrad_b200.step import GradArena, shard_indices
-    from ptyrad_b200.synthetic import make_inputs
+    from workloads import make_inputs
     from oracle.ptycho_torch import oracle_step, ddp_emulated_grads
     iv, mp, lp = make_inputs("T32", seed=5)
     model = PtychoAD(iv, mp, device="cpu", verbose=False)

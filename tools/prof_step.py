@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from ptyrad_b200 import PtychoAD, CombinedLoss
-from ptyrad_b200.synthetic import make_inputs, CONFIGS
+from workloads import make_inputs, CONFIGS
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 path = {"auto": 0, "general": 1, "fused": 2}[sys.argv[2] if len(sys.argv) > 2 else "auto"]

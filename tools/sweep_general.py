@@ -13,7 +13,7 @@ import torch
 from ptyrad_b200 import PtychoAD, CombinedLoss, _lib
 from ptyrad_b200.optim import FusedAdam
 from ptyrad_b200.step import GradArena, recon_batch
-from ptyrad_b200.synthetic import CONFIGS, make_inputs, random_batches
+from workloads import CONFIGS, make_inputs, random_batches
 
 name, B = sys.argv[1], int(sys.argv[2])
 combos = [tuple(int(v) for v in c.split(":")) for c in sys.argv[3].split()]

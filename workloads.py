@@ -1,4 +1,5 @@
-"""Deterministic synthetic 4D-STEM inputs for the multislice hot path.
+"""Deterministic synthetic 4D-STEM inputs for the multislice hot path (bench / test input generation -- NOT part of the
+product package ``ptyrad_b200``; lives at the repo root so that ``bench.py``, ``tests/`` and ``__graft_entry__`` share it).
 
 Produces the ``init_variables`` / ``model_params`` / ``loss_params`` dictionaries the
 reference feeds to ``PtychoAD`` / ``CombinedLoss`` (layouts: reference
@@ -71,6 +72,13 @@ CONFIGS = {
     "C3s": ScanConfig("C3s", N=256, scan=64, P=8, M=1, Z=32, batch=64, kv=300.0, conv_angle=21.4,
                       dz=10.0, defocus=-200.0, tilt_each=True, lr_shifts=1e-4, lr_tilts=1e-4),
     "C4s": ScanConfig("C4s", N=256, scan=96, P=12, M=1, Z=16, batch=256, lr_shifts=1e-4),
+    # BASELINE configs at their OWN depth (same N, P, M, Z, loss and tilt / shift options) on a tiny scan, so the float64 CPU
+    # oracle finishes in seconds: the parity cases for C2..C5 (tests/test_gpu_parity.py::test_baseline_configs_at_depth)
+    "C2d": ScanConfig("C2d", N=128, scan=4, P=6, M=1, Z=8, batch=8, lr_shifts=1e-4),
+    "C3d": ScanConfig("C3d", N=256, scan=3, P=8, M=1, Z=32, batch=4, kv=300.0, conv_angle=21.4,
+                      dz=10.0, defocus=-200.0, tilt_each=True, lr_shifts=1e-4, lr_tilts=1e-4),
+    "C4d": ScanConfig("C4d", N=256, scan=3, P=12, M=1, Z=16, batch=4, lr_shifts=1e-4),
+    "C5d": ScanConfig("C5d", N=192, scan=3, P=1, M=2, Z=10, batch=6, loss="poissn"),
     # tiny cases for parity tests (oracle finishes in well under a second)
     "T32": ScanConfig("T32", N=32, scan=6, P=2, M=2, Z=3, batch=5, lr_shifts=1e-4, step=0.6),
     "T64": ScanConfig("T64", N=64, scan=5, P=3, M=1, Z=4, batch=7, lr_shifts=1e-4),
