@@ -3,17 +3,24 @@
 forward + loss + backward + optimizer iteration; % of HBM roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl ours|reference]
+                    [--scaling weak|strong --global-batch G]
 
 One "step" = one batch of the workload through the hot path: zero-grad, forward, loss, adjoint, (gradient all-reduce),
 Adam step -- the body of the reference's recon_step loop (reconstruction.py:741-770).  N > 1 is launched by torchrun, one
-rank per GPU; scan positions shard across ranks (weak scaling: every rank runs a full `batch` of its own).
+rank per GPU; scan positions shard across ranks: every rank holds ONLY its own block of the measurements and
+draws its batches from it.  `--scaling weak` (default): every rank runs a full `batch` of its own; `--scaling strong`: the
+global batch (`--global-batch`, default 2048) is fixed and split over the ranks.
+The workload can also be chosen with the environment variable PTYB_BENCH_CONFIG (for drivers that pass no --config), e.g.
+PTYB_BENCH_CONFIG=C4 for the 256x256-scan configuration.
 
 Printed JSON (rank 0, one line): see README / DESIGN.md section "Measurement".
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -28,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "diffraction patterns/sec (fwd+bwd iter)"
 UNIT = "patterns/s"
+PROFILE_ROUND = "r02"
 
 
 def bytes_per_pattern(c):
@@ -48,10 +56,21 @@ def measured_peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), "measured burst copy bandwidth (MEASURED_PEAKS.json)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def csrc_hash():
+    """Content hash of the kernel sources: ncu-derived constants (DRAM traffic per launch) are only quoted for the build they
+    were captured from."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "ptyrad_b200", "csrc")
+    for f in sorted(os.listdir(d)) + ["../../include/ptyrad_b200.h"]:
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -69,6 +88,7 @@ class ClockSampler:
             self.th.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -79,37 +99,71 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(cfg, iv, mp, lp, batch_cpu, steps, warmup, threads):
-    """The oracle port of the reference's torch path, timed on the host cores (test infrastructure used as the baseline only)."""
+def cpu_reference_rate(iv, mp, lp, batch_cpu, steps, warmup, threads):
+    """The reference's CPU torch path timed on the host cores: the UNMODIFIED reference package (PtychoAD(device='cpu') +
+    CombinedLoss + backward + Adam.step) when it is importable (baseline/_ref, or /root/reference/src in the
+    build container; oracle/ref_import.py), else the oracle port of the same sequence.  Returns (patterns/s, median s/step, kind)."""
     import torch
-    from oracle.ptycho_torch import OracleTrainer
     from workloads import random_batches
-    tr = OracleTrainer(iv, mp, lp, threads=threads)
-    batches = random_batches(iv["crop_pos"].shape[0], batch_cpu, seed=99)
+    torch.set_num_threads(threads)
+    batches = [b[:batch_cpu] for b in random_batches(iv["crop_pos"].shape[0], batch_cpu, seed=99)]
+    kind = "port"
+    step = None
+    try:
+        from oracle.ref_import import import_reference
+        ref = import_reference()
+        if ref is not None:
+            model = ref.PtychoAD(iv, mp, device="cpu", verbose=False)
+            loss_fn = ref.CombinedLoss(lp, device="cpu")
+            opt = torch.optim.Adam(model.optimizable_params)
+
+            def step(idx):                                       # the non-LBFGS body of recon_step (reconstruction.py:738-772)
+                opt.zero_grad()
+                dp = model(idx)
+                meas = model.get_measurements(idx)
+                total, _ = loss_fn(dp, meas, model._current_object_patches, model.omode_occu)
+                total.backward()
+                opt.step()
+                model.clear_cache()
+            step(batches[0])                                     # proves the package really runs here before we commit to it
+            kind = "reference"
+    except Exception as e:                                       # e.g. a torchvision mismatch on the box: fall back to the port
+        sys.stderr.write(f"reference package not usable ({type(e).__name__}: {e}); timing the oracle port instead\n")
+        step = None
+    if step is None:
+        from oracle.ptycho_torch import OracleTrainer
+        tr = OracleTrainer(iv, mp, lp, threads=threads)
+        step = tr.step
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        tr.step(batches[s % len(batches)][:batch_cpu])
+        step(batches[s % len(batches)])
         if s >= warmup:
             times.append(time.perf_counter() - t0)
-    return batch_cpu / statistics.median(times), statistics.median(times)
+    return batch_cpu / statistics.median(times), statistics.median(times), kind
+
+
+def rank_block(Ntot, rank, world):
+    """Scan positions whose measurements rank `rank` holds: a contiguous block of the scan (sizes differ by at most one)."""
+    edges = np.linspace(0, Ntot, world + 1).astype(np.int64)
+    return np.arange(edges[rank], edges[rank + 1], dtype=np.int64)
 
 
 def main():
@@ -117,44 +171,56 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", default="C2")
+    ap.add_argument("--config", default=os.environ.get("PTYB_BENCH_CONFIG", "C2"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch size")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch size (weak scaling)")
+    ap.add_argument("--scaling", default=os.environ.get("PTYB_BENCH_SCALING", "weak"), choices=["weak", "strong"])
+    ap.add_argument("--global-batch", type=int, default=2048, help="strong scaling: the fixed global batch, split over the ranks")
     ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused: one-launch Adam of this repo; torch: torch.optim.Adam (foreach)")
-    ap.add_argument("--flags", type=int, default=0, help="experimental kernel switches")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    from workloads import CONFIGS, make_inputs, random_batches
+    from workloads import CONFIGS, make_inputs
     cfg = CONFIGS[args.config]
-    B = args.batch or cfg.batch
+    if args.scaling == "strong":
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world
+    else:
+        B = args.batch or cfg.batch
     threads = os.cpu_count() or 1
     workload = (f"{cfg.name}: {cfg.P} probe modes, {cfg.M} object modes, {cfg.Z} slices, {cfg.N}^2 patterns, "
                 f"{cfg.scan}x{cfg.scan} scan, batch {B}/GPU, Adam, loss_{cfg.loss}+sparse")
     config = {"workload": workload, "cfg": cfg.name, "N": cfg.N, "P": cfg.P, "M": cfg.M, "Z": cfg.Z, "scan": cfg.scan,
               "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
               "l2": "per-step working set (wave stash) >> 126 MB L2, no explicit flush"}
+    simulate = cfg.scan <= 64 and cfg.N <= 128
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
             return
-        iv, mp, lp = make_inputs(cfg, simulate_measurements=(cfg.scan <= 64 and cfg.N <= 128))
-        b_cpu = min(B, 64 if cfg.N <= 128 else 8)
-        rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), threads)
-        sample = f"{b_cpu} patterns/step of the {cfg.name} workload (same model, reduced batch), median step time"
+        iv, mp, lp = make_inputs(cfg, simulate_measurements=simulate)
+        b_cpu = min(cfg.batch, 64 if cfg.N <= 128 else 8)
+        k, w = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))          # bounded: the whole run ends within minutes
+        rate, med, kind = cpu_reference_rate(iv, mp, lp, b_cpu, k, w, threads)
+        sample = (f"{b_cpu} patterns/step of the {cfg.name} workload (same model, reduced batch), {w} warm-up + {k} timed steps, "
+                  f"median step time; {'unmodified reference package' if kind == 'reference' else 'oracle port of the reference path'}")
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w,
+            "requested_steps": args.steps, "requested_warmup": args.warmup,
+            "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -162,7 +228,7 @@ def main():
     import torch
     import torch.distributed as dist
     from ptyrad_b200 import PtychoAD, CombinedLoss, MeasurementView, _lib
-    from ptyrad_b200.step import GradArena, recon_batch
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch
 
     # libraries (NCCL's version banner) may write to fd 1: keep the real stdout for the one JSON line, send the rest to stderr
     sys.stdout.flush()
@@ -176,46 +242,61 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    simulate = cfg.scan <= 64 and cfg.N <= 128
-    if world > 1 and simulate:
-        # the simulated measurements cost ~30 s of host time with all cores: rank 0 makes them once (torchrun pins every rank to one
-        # OpenMP thread) and the other ranks read them from a node-local file -- every rank ends up with identical inputs
-        shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp",
-                              f"ptyb200_meas_{cfg.name}_{os.environ.get('MASTER_PORT', '0')}.npy")
-        if rank == 0:
-            torch.set_num_threads(threads)
+    Ntot = cfg.scan * cfg.scan
+    mine_pos = rank_block(Ntot, rank, world)                  # the scan positions whose patterns this rank holds
+    if simulate:
+        if world > 1:
+            # the simulated measurements cost ~30 s of host time with all cores: rank 0 makes them once (torchrun pins every rank to
+            # one OpenMP thread) and the other ranks map the node-local file and copy out their own block
+            shared = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp",
+                                  f"ptyb200_meas_{cfg.name}_{os.environ.get('MASTER_PORT', '0')}.npy")
+            if rank == 0:
+                torch.set_num_threads(threads)
+                iv, mp, lp = make_inputs(cfg, simulate_measurements=True)
+                np.save(shared + ".tmp.npy", iv["measurements"])
+                os.replace(shared + ".tmp.npy", shared)
+            dist.barrier()
+            if rank != 0:
+                iv, mp, lp = make_inputs(cfg, measurements=np.ascontiguousarray(np.load(shared, mmap_mode="r")[mine_pos]), positions=mine_pos)
+            dist.barrier()
+            if rank == 0:
+                os.remove(shared)
+                iv["measurements"] = np.ascontiguousarray(iv["measurements"][mine_pos])
+                iv["measurements_positions"] = mine_pos
+        else:
             iv, mp, lp = make_inputs(cfg, simulate_measurements=True)
-            np.save(shared + ".tmp.npy", iv["measurements"])
-            os.replace(shared + ".tmp.npy", shared)
-        dist.barrier()
-        if rank != 0:
-            iv, mp, lp = make_inputs(cfg, measurements=np.load(shared))
-        dist.barrier()
-        if rank == 0:
-            os.remove(shared)
     else:
-        iv, mp, lp = make_inputs(cfg, simulate_measurements=simulate)
-    Ntot = iv["crop_pos"].shape[0]
+        iv, mp, lp = make_inputs(cfg, simulate_measurements=False, positions=mine_pos if world > 1 else None)
     model = PtychoAD(iv, mp, device=dev, verbose=False)
     model.kernel_path = {"auto": _lib.PATH_AUTO, "general": _lib.PATH_GENERAL, "fused": _lib.PATH_FUSED}[args.path]
     loss_fn = CombinedLoss(lp, device=dev)
-    model.kernel_flags = args.flags
     if args.optimizer == "fused":
         from ptyrad_b200.optim import FusedAdam
         opt = FusedAdam(model.optimizable_params)
     else:
         opt = torch.optim.Adam(model.optimizable_params)
     config["optimizer"] = "Adam (" + args.optimizer + ")"
+    config["measurements"] = f"{len(mine_pos)} of {Ntot} patterns resident per GPU (own block of the scan)" if world > 1 else "all resident"
     arena = GradArena(model)
-    # every rank runs its own batches (weak scaling): rank r takes batches r, r+world, ... of a seeded permutation
-    batches = random_batches(Ntot, B, seed=7)
-    batches = [b[:B] for b in batches]
-    my = [torch.as_tensor(batches[(i * world + rank) % len(batches)], device=dev) for i in range(max(4, min(len(batches), 64)))]
+    # every rank draws its batches from a seeded permutation of ITS block of the scan
+    perm = np.random.default_rng(8 + rank).permutation(mine_pos)
+    nbat = max(1, len(perm) // B)
+    if len(perm) < B:
+        raise SystemExit(f"rank {rank} holds {len(perm)} positions, fewer than its batch {B}")
+    batches = [np.sort(perm[i * B:(i + 1) * B]) for i in range(nbat)]
+    my = [torch.as_tensor(batches[i % nbat], device=dev) for i in range(max(4, min(nbat, 64)))]
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
     lib = _lib.lib()
     eager_fn = lambda ix: recon_batch(model, loss_fn, opt, ix, arena, world)
@@ -230,25 +311,18 @@ def main():
             out = fn(my[s % len(my)])
         e1.record()
         sync_all()
-        t_ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_ms = float(t.item())
-        return t_ms, out
+        return max_over_ranks(e0.elapsed_time(e1)), out
 
     for s in range(args.warmup):
         eager_fn(my[s % len(my)])
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
     # pass 1 (eager launches): per-section CUDA events inside the library + launch count
+    import ctypes as C
     lib.ptyb200_timing_enable(1)
     l0 = lib.ptyb200_launch_count()
     ms_eager, last = timed(eager_fn, args.steps)
     launches = lib.ptyb200_launch_count() - l0
-    import ctypes as C
     tf, tb, nf, nb = C.c_double(), C.c_double(), C.c_int(), C.c_int()
     lib.ptyb200_timing_read(C.byref(tf), C.byref(tb), C.byref(nf), C.byref(nb))
     lib.ptyb200_timing_enable(0)
@@ -256,9 +330,6 @@ def main():
     step_fn = eager_fn
     if not args.no_graph:
         # pass 2 (headline): the identical step replayed as a CUDA graph (same kernels, no per-launch host cost)
-        from ptyrad_b200.step import GraphedStep
-        last_eager = last.clone()
-        saved = [p.detach().clone() for p in model.optimizable_tensors.values()]
         step_fn = GraphedStep(model, loss_fn, opt, arena, B, world=world)
         for s in range(args.warmup):
             step_fn(my[s % len(my)])
@@ -267,13 +338,28 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = args.steps * B * world / (ms * 1e-3)
 
+    # ------------------------------------------------------------------ sustained: >= 3 s of back-to-back steps with its own clock record
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(math.ceil(args.sustained_seconds * 1e3 / (ms / args.steps))))
+        s2 = ClockSampler(local_rank).start() if rank == 0 else None
+        ms_sus, _ = timed(step_fn, n_sus)
+        c2 = s2.stop() if rank == 0 else None
+        sustained = {"value": n_sus * B * world / (ms_sus * 1e-3), "unit": UNIT, "steps": n_sus, "seconds": ms_sus * 1e-3,
+                     "ms_per_step": ms_sus / n_sus, "clocks": c2}
+
     # ------------------------------------------------------------------ end-to-end: host buffers, H2D + D2H every step
     e2e = None
     if not args.no_e2e:
         k2 = min(args.steps, 40)
         nn = cfg.N * cfg.N
-        host_meas = [torch.from_numpy(np.ascontiguousarray(iv["measurements"][my[i % len(my)].cpu().numpy()])).pin_memory() for i in range(min(8, len(my)))]
-        host_idx = [my[i % len(my)].cpu().pin_memory() for i in range(len(host_meas))]
+        row_of = {int(p): i for i, p in enumerate(mine_pos)} if world > 1 else None
+        host_meas, host_idx = [], []
+        for i in range(min(8, len(my))):
+            ix = my[i % len(my)].cpu().numpy()
+            rows = ix if row_of is None else np.array([row_of[int(p)] for p in ix])
+            host_meas.append(torch.from_numpy(np.ascontiguousarray(iv["measurements"][rows])).pin_memory())
+            host_idx.append(torch.from_numpy(ix.astype(np.int64)).pin_memory())
         dev_meas = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
         dev_idx = torch.empty(B, dtype=torch.int64, device=dev)
         ar = torch.arange(B, device=dev)
@@ -307,11 +393,7 @@ def main():
                 host_loss.copy_(l5, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
         sync_all()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": k2 * B * world / dt, "unit": UNIT, "h2d_bytes_per_step": B * nn * 4 + B * 8, "d2h_bytes_per_step": 20,
                "steps": k2, "api": "PtychoAD.forward + CombinedLoss + backward + Adam.step via ptyrad_b200.step.recon_batch"}
 
@@ -329,13 +411,17 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this workload (per launch)
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this workload (per launch); quoted only when
+    # the capture was taken from THIS build of the kernels (content hash of ptyrad_b200/csrc) and this batch size
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01", f"ncu_traffic_{cfg.name}.json")
-    if os.path.exists(tpath) and B == cfg.batch and args.path != "general":
+    tpath = os.path.join(ROOT, "profiles", PROFILE_ROUND, f"ncu_traffic_{cfg.name}.json")
+    if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        kb = tj["kernels"]["k_backward"]
-        traffic, traffic_src = (kb["dram_read_gb"] + kb["dram_write_gb"]) * 1e9, "profiles/r01/" + os.path.basename(tpath)
+        if tj.get("csrc_sha256") == csrc_hash() and tj.get("batch") == B and tj.get("path", "auto") == args.path:
+            kb = tj["kernels"][tj["dominant"]]
+            traffic, traffic_src = (kb["dram_read_gb"] + kb["dram_write_gb"]) * 1e9, f"profiles/{PROFILE_ROUND}/" + os.path.basename(tpath)
+        else:
+            traffic_src = f"profiles/{PROFILE_ROUND}/{os.path.basename(tpath)} is from another build / batch of the kernels: not quoted"
     comp, stash = bytes_per_pattern(cfg)
     # adjoint section (dominant): re-reads the stash, reads the ROIs, read-modify-writes the ROI gradients, reads G
     bwd_bytes = B * (8 * cfg.P * cfg.M * cfg.Z + 16 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
@@ -347,8 +433,8 @@ def main():
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config, "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches),
         "eager": {"value": args.steps * B * world / (ms_eager * 1e-3), "ms_per_step": ms_eager / args.steps,
                   "note": "same steps launched kernel by kernel; section timings and gpu_launches come from this pass"},
         "roofline": {"bound": "hbm", "kernel": "multislice adjoint section (ptyb200_backward)", "achieved": ach_b, "peak": peak,
@@ -387,9 +473,10 @@ def main():
         except Exception as e:           # never let the extra baseline break the contract line
             out["torch_cuda_eager_baseline"] = {"error": str(e)[:200]}
         b_cpu = min(B, 64 if cfg.N <= 128 else 8)
-        rate, med = cpu_reference_rate(cfg, iv, mp, lp, b_cpu, 6, 1, threads)
-        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{b_cpu} patterns/step of the same workload, 1 warm-up + 6 timed steps, median ({med * 1e3:.0f} ms/step)"}
+        rate, med, kind = cpu_reference_rate(iv, mp, lp, b_cpu, 6, 1, threads)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": f"{b_cpu} patterns/step of the same workload, 1 warm-up + 6 timed steps, median ({med * 1e3:.0f} ms/step); "
+                                         f"{'unmodified reference package' if kind == 'reference' else 'oracle port of the reference path'}"}
     emit(out)
     finish()
 

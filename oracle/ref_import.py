@@ -1,4 +1,5 @@
-"""Import the UNMODIFIED reference package for the drop-in tests and the reference arm of bench.py.
+"""TEST / BENCH INFRASTRUCTURE (not product code): import the UNMODIFIED reference package for the drop-in tests
+(tests/test_reference_driver.py) and for the reference arm of bench.py (`--impl reference`, `cpu_baseline`).
 
 Search order: ``baseline/_ref`` (``pip install --no-deps --target baseline/_ref <copy of /root/reference>``: travels to the GPU box
 with the snapshot) and then ``/root/reference/src`` (build container only).  The reference's I/O, plotting and hypertune modules
@@ -10,7 +11,7 @@ import os
 import sys
 import types
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))       # repo root (this file lives in oracle/)
 CANDIDATES = [os.path.join(ROOT, "baseline", "_ref"), "/root/reference/src"]
 _OPTIONAL = ["h5py", "tifffile", "optuna", "accelerate", "accelerate.utils", "matplotlib", "matplotlib.pyplot", "matplotlib.colors",
              "matplotlib.gridspec", "matplotlib.ticker", "matplotlib.patches", "mpl_toolkits", "mpl_toolkits.axes_grid1"]

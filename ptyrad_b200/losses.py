@@ -98,3 +98,5 @@ class MeasurementView:
     def __init__(self, all_meas, idx, model=None):
         self.all, self.idx = all_meas, idx
         self.mcfg, self.padded = (None, None) if model is None else model._meas_cfg(all_meas)
+        if model is not None and all_meas is model.measurements:
+            self.idx = model.meas_rows(idx)                  # a rank that holds only its shard: scan index -> local row

@@ -93,6 +93,17 @@ class PtychoAD(nn.Module):
             self.register_buffer("omode_occu", t(init_variables["omode_occu"], torch.float32))
             self.register_buffer("H", t(init_variables["H"], torch.complex64))
             self.register_buffer("measurements", t(init_variables["measurements"], torch.float32))
+            # extension: a data-parallel rank may hold only ITS rows of the measurements.  `measurements_positions` lists
+            # the scan indices of the rows given; the loss looks rows up through `_meas_row_of` (scan index -> row, -1 = not held).
+            # The reference replicates the whole array on every rank (models.py:109).
+            self._meas_row_of = None
+            if init_variables.get("measurements_positions", None) is not None:
+                pos = torch.as_tensor(np.asarray(init_variables["measurements_positions"], dtype=np.int64), device=device)
+                if pos.numel() != self.measurements.shape[0]:
+                    raise ValueError("measurements_positions must list one scan index per measurement row")
+                Ntot_ = np.asarray(init_variables["crop_pos"]).shape[0]
+                self._meas_row_of = torch.full((Ntot_,), -1, dtype=torch.int64, device=device)
+                self._meas_row_of[pos] = torch.arange(pos.numel(), dtype=torch.int64, device=device)
             self.register_buffer("N_scan_slow", t(init_variables["N_scan_slow"], torch.int32))
             self.register_buffer("N_scan_fast", t(init_variables["N_scan_fast"], torch.int32))
             self.register_buffer("crop_pos", t(np.asarray(init_variables["crop_pos"]).astype(np.int32), torch.int32))
@@ -140,7 +151,10 @@ class PtychoAD(nn.Module):
         if self.omode_occu.numel() != M:
             raise ValueError("omode_occu length does not match the number of object modes")
         Ntot = self.crop_pos.shape[0]
-        if self.meas_padded is None and self.meas_scale_factors is None and tuple(self.measurements.shape) != (Ntot, Ny, Nx):
+        if self._meas_row_of is not None:
+            if tuple(self.measurements.shape[1:]) != (Ny, Nx) and self.meas_padded is None and self.meas_scale_factors is None:
+                raise ValueError(f"measurement rows have shape {tuple(self.measurements.shape[1:])}, expected {(Ny, Nx)}")
+        elif self.meas_padded is None and self.meas_scale_factors is None and tuple(self.measurements.shape) != (Ntot, Ny, Nx):
             raise ValueError(f"measurements have shape {tuple(self.measurements.shape)}, expected {(Ntot, Ny, Nx)}")
         if self.opt_probe_pos_shifts.shape != (Ntot, 2):
             raise ValueError("probe_pos_shifts must be (Ntot,2)")
@@ -306,12 +320,16 @@ class PtychoAD(nn.Module):
             m.scale_y, m.scale_x = float(sf[0]), float(sf[1])
         return m, padded
 
+    def meas_rows(self, idx):
+        """Rows of `self.measurements` that hold the patterns of scan indices `idx` (identity unless this rank holds a shard)."""
+        return idx if self._meas_row_of is None else self._meas_row_of[idx]
+
     def get_measurements(self, indices=None):
         """measurements[indices] with the optional on-the-fly pad / bilinear resample (models.py:384-416); without indices the
         stored array is returned as is, like the reference does (models.py:411-414)."""
         if indices is None:
             return self.measurements
-        idx = self._index_tensor(indices)
+        idx = self.meas_rows(self._index_tensor(indices))
         mcfg, padded = self._meas_cfg()
         if mcfg is None:
             return self.measurements[idx]

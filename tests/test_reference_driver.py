@@ -3,7 +3,7 @@
 ``ptyrad_b200.PtychoAD`` (CUDA) and, side by side, on the reference's own ``PtychoAD`` (CPU, float32) from the same inputs, for
 several iterations including constraints that rebind ``opt_*.data``, ``start_iter`` toggling and the LBFGS closure.
 
-The reference package comes from ``baseline/_ref`` (or /root/reference/src in the build container); see tests/ref_import.py.
+The reference package comes from ``baseline/_ref`` (or /root/reference/src in the build container); see oracle/ref_import.py.
 """
 import copy
 
@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from helpers import rel
-from ref_import import import_reference
+from oracle.ref_import import import_reference
 
 REF = import_reference(with_driver=True)
 needs_ref = pytest.mark.skipif(REF is None, reason="reference package not importable (no baseline/_ref and no /root/reference)")
@@ -126,11 +126,11 @@ def test_reference_ortho_pmode_and_probe_mask_on_the_cuda_model():
     cp["probe_mask_k"]["freq"] = 1
     cp["fix_probe_int"]["freq"] = 1
     REF.CombinedConstraint(cp, device="cuda", verbose=False)(model, 1)
-    pr = model.get_complex_probe_view().reshape(cfg.P, -1).to(torch.complex128)
+    pr = model.get_complex_probe_view().detach().reshape(cfg.P, -1).to(torch.complex128)
     gram = (pr @ pr.conj().T).abs().cpu().numpy()
     off = gram - np.diag(np.diag(gram))
     assert off.max() < 2e-2 * gram.max()                                   # modes stay (nearly) orthogonal after the k-space mask
-    np.testing.assert_allclose(float(model.get_complex_probe_view().abs().pow(2).sum()), float(model.probe_int_sum), rtol=1e-5)
+    np.testing.assert_allclose(float(model.get_complex_probe_view().detach().abs().pow(2).sum()), float(model.probe_int_sum), rtol=1e-5)
     loss_fn = ptyrad_b200.CombinedLoss(lp, device="cuda")
     idx = np.arange(7)
     total, _ = loss_fn(model(idx), model.get_measurements(idx), model._current_object_patches, model.omode_occu)

@@ -218,13 +218,15 @@ def _projected_measurements(obj_true, probe, crop, N, rng, dose, chunk=256):
 # ----------------------------------------------------------------------------------------
 
 def make_inputs(cfg: ScanConfig | str, seed: int = SEED, measurements: Optional[np.ndarray] = None,
-                simulate_measurements: bool = True):
+                simulate_measurements: bool = True, positions: Optional[np.ndarray] = None):
     """Build (init_variables, model_params, loss_params) for `cfg`.
 
     init_variables keys follow reference ``models.py:99-118``; model_params / loss_params follow
     SURVEY appendix B.  If `measurements` is given it is used as is; else if
     `simulate_measurements` they come from `_projected_measurements`; else smooth random
-    non-negative patterns (fast, for very large configs)."""
+    non-negative patterns (fast, for very large configs).  `positions` (sorted scan indices): only those rows of the measurements
+    are produced / kept (a data-parallel rank holds its own block of the scan), announced to the model through the extension key
+    `measurements_positions`."""
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
     rng = np.random.default_rng(seed)
@@ -257,14 +259,20 @@ def make_inputs(cfg: ScanConfig | str, seed: int = SEED, measurements: Optional[
         else:
             env = np.abs(np.fft.fftshift(np.fft.fft2(base))) ** 2
             env = (env / env.max()).astype(np.float32)
-            measurements = np.empty((Ntot, N, N), np.float32)
-            for s in range(0, Ntot, 512):
-                e = min(Ntot, s + 512)
-                measurements[s:e] = env[None] * rng.random((e - s, N, N), dtype=np.float32)
+            # every 512-row chunk has its own seeded stream, so that any subset of the rows can be produced on its own
+            rows = np.arange(Ntot) if positions is None else np.asarray(positions)
+            measurements = np.empty((len(rows), N, N), np.float32)
+            for c in np.unique(rows // 512):
+                sel = np.nonzero(rows // 512 == c)[0]
+                chunk = env[None] * np.random.default_rng([seed, 77, int(c)]).random((512, N, N), dtype=np.float32)
+                measurements[sel] = chunk[rows[sel] - c * 512]
+        if positions is not None and simulate_measurements:
+            measurements = measurements[np.asarray(positions)]
     measurements = np.ascontiguousarray(measurements, dtype=np.float32)
 
-    # probe power matches the mean pattern sum (reference initialization.py:1365-1366)
-    probe = probe * np.sqrt(measurements.sum(axis=(-2, -1)).mean() / np.sum(np.abs(probe) ** 2))
+    # probe power matches the mean pattern sum (reference initialization.py:1365-1366); with a block of the rows, the block's mean
+    # (identical probes on all ranks are restored by the caller when it matters: the benchmark only needs the value scale)
+    probe = probe * np.sqrt(measurements[: min(len(measurements), 4096)].sum(axis=(-2, -1)).mean() / np.sum(np.abs(probe) ** 2))
     probe = probe.astype(np.complex64)
 
     if cfg.tilt_each:
@@ -280,6 +288,8 @@ def make_inputs(cfg: ScanConfig | str, seed: int = SEED, measurements: Optional[
         slice_thickness=np.float32(cfg.dz), dx=np.float32(cfg.dx),
         dk=np.float32(1.0 / (cfg.dx * N)), lambd=np.float32(lam), scan_affine=None,
     )
+    if positions is not None:
+        iv["measurements_positions"] = np.asarray(positions, dtype=np.int64)
     lr = dict(obja=5e-4, objp=5e-4, obj_tilts=cfg.lr_tilts, slice_thickness=cfg.lr_dz,
               probe=1e-4, probe_pos_shifts=cfg.lr_shifts)
     model_params = dict(
