@@ -121,6 +121,16 @@ int ptyb200_forward(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const
                     const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
                     ptyb200_stream s);
 
+/* ptyb200_forward with the mode reduction FUSED with the data losses (forward.py:79 + losses.py:36-89; north star item 3): the kernel
+ * that completes a pattern's intensities also adds the pattern's contribution to the batch sums, so dp is not re-read by a reduction
+ * launch; losses3 / stats / pacbed_scratch as in ptyb200_loss_forward (ptyb200_loss_grad then takes the same stats).  The measured
+ * pattern of sample b is row meas_rows[b] of meas_all (NULL: idx[b]; a rank that holds only its shard passes its own row map). */
+int ptyb200_forward_loss(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                         const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                         const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
+                         const ptyb200_loss_cfg* lc, const float* meas_all, const int64_t* meas_rows, const ptyb200_meas_cfg* mcfg,
+                         const float* meas_padded, float* losses3, double* stats, float* pacbed_scratch, ptyb200_stream s);
+
 /* Adjoint of ptyb200_forward (what torch autograd derives for the reference).  Must follow
  * a forward on the same workspace with the same inputs.  G = dL/d(dp) (B,N,N).  Gradient outputs are DENSE
  * and are OVERWRITTEN (zero-filled where no pattern contributes), as the reference's .grad tensors are:
@@ -168,6 +178,22 @@ int ptyb200_sparse_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, cons
  * scratch of the same size; in, tmp and out must be distinct. */
 int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t planes, int32_t H, int32_t W, float sigma,
                            int32_t transpose, ptyb200_stream s);
+
+/* Per-iteration object constraints, in place, no .data re-binding:
+ * ptyb200_blur_axis: 1-D Gaussian (odd kernel_size <= 15, weights exp(-x^2/2 sigma^2)/sum) along the middle axis of an array viewed as
+ *   (outer, L, inner); pad_mode 0 = reflect (obj_rblur: x pass then y pass = torchvision gaussian_blur, constraints.py:83-99),
+ *   1 = replicate (obj_zblur along z: gaussian_blur_1d, constraints.py:101-114, utils/image_proc.py:443-455).  in != out.
+ * ptyb200_object_constraints: mirrored_amp -> obja_thresh -> objp_postiv (constraints.py:165-208) in ONE pass over the n voxels of
+ *   obja / objp; `scratch` = one device float (only for objp_postiv mode 'subtract_min'). */
+typedef struct ptyb200_obj_constraints {
+    int32_t mirrored_on; float mirrored_relax, mirrored_scale, mirrored_power;   /* constraints.py:165-178 */
+    int32_t thresh_on;   float thresh_relax, thresh_lo, thresh_hi;               /* constraints.py:180-189 */
+    int32_t postiv_on;   float postiv_relax; int32_t postiv_subtract_min;        /* constraints.py:191-208 */
+} ptyb200_obj_constraints;
+int ptyb200_blur_axis(const float* in, float* out, int64_t outer, int32_t L, int64_t inner, int32_t kernel_size, float sigma,
+                      int32_t pad_mode, ptyb200_stream s);
+int ptyb200_object_constraints(const ptyb200_obj_constraints* oc, float* obja, float* objp, int64_t n, float* scratch,
+                               ptyb200_stream s);
 
 /* optimizer.step() for torch.optim.Adam defaults (reconstruction.py:759; built at reconstruction.py:285-368):
  * one launch over up to 8 tensors with per-tensor learning rates.  The host arrays of pointers / lrs / numels are read

@@ -44,6 +44,14 @@ class MeasCfg(C.Structure):
     ]
 
 
+class ObjConstraints(C.Structure):
+    _fields_ = [
+        ("mirrored_on", C.c_int32), ("mirrored_relax", C.c_float), ("mirrored_scale", C.c_float), ("mirrored_power", C.c_float),
+        ("thresh_on", C.c_int32), ("thresh_relax", C.c_float), ("thresh_lo", C.c_float), ("thresh_hi", C.c_float),
+        ("postiv_on", C.c_int32), ("postiv_relax", C.c_float), ("postiv_subtract_min", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "ptyb200_abi_version": (C.c_int, []),
@@ -55,6 +63,7 @@ _SIGNATURES = {
     "ptyb200_propagator": (C.c_int, [C.POINTER(Cfg), _P, _P, _P]),
     "ptyb200_gather_patches": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ptyb200_forward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 12),
+    "ptyb200_forward_loss": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 11 + [C.POINTER(LossCfg), _P, _P, C.POINTER(MeasCfg), _P, _P, _P, _P, _P]),
     "ptyb200_backward": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32] + [_P] * 17 + [C.c_uint32, _P]),
     "ptyb200_loss_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, C.POINTER(MeasCfg), _P, _P]),
     "ptyb200_loss_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(MeasCfg), _P, _P]),
@@ -62,6 +71,8 @@ _SIGNATURES = {
     "ptyb200_sparse_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ptyb200_sparse_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ptyb200_gaussian_blur5": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
+    "ptyb200_blur_axis": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
+    "ptyb200_object_constraints": (C.c_int, [C.POINTER(ObjConstraints), _P, _P, C.c_int64, _P, _P]),
     "ptyb200_adam_step": (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -176,6 +176,7 @@ FwdArgs make_fwd_args(const ptyb200_cfg& c, int B, const Workspace& w, const int
     a.tvec = c.tilt_mode ? w.tvec : nullptr;
     a.occu = occu; a.stash = w.stash; a.phis = c.stash_fourier && c.Z > 1 ? w.phis : nullptr;
     a.G1 = w.G1; a.G2 = w.G2; a.farT = w.farT; a.dp = dp; a.eps = c.eps;
+    memset(&a.lf, 0, sizeof a.lf);
     return a;
 }
 
@@ -354,15 +355,16 @@ int ptyb200_gather_patches(const ptyb200_cfg* c, const int64_t* idx, int32_t B, 
     return 0;
 }
 
-int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
-                    const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
-                    const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
-                    ptyb200_stream s) {
+static int forward_impl(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                        const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                        const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
+                        const LossFuse* lf, ptyb200_stream s) {
     if (int r = check_cfg(c, B)) return r;
     if (!idx || !obja || !objp || (!crop_pos && !(c->reserved[1] & 1)) || !probe || !Hbase || !occu || !dp_out || !workspace) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     Workspace w = carve(*c, B, workspace);
     FwdArgs a = make_fwd_args(*c, B, w, idx, crop_pos, probe, occu, dp_out);
+    if (lf) a.lf = *lf;
     if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
         if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
@@ -371,6 +373,35 @@ int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const f
         else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
         tm_mark(0, 1, st);
     });
+    return 0;
+}
+
+int ptyb200_forward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                    const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                    const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
+                    ptyb200_stream s) {
+    return forward_impl(c, idx, B, obja, objp, crop_pos, probe, shifts, Hbase, tilts, dz, occu, dp_out, workspace, nullptr, s);
+}
+
+int ptyb200_forward_loss(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp,
+                         const int32_t* crop_pos, const float* probe, const float* shifts, const float* Hbase,
+                         const float* tilts, const float* dz, const float* occu, float* dp_out, void* workspace,
+                         const ptyb200_loss_cfg* lc, const float* meas_all, const int64_t* meas_rows, const ptyb200_meas_cfg* mcfg,
+                         const float* meas_padded, float* losses3, double* stats, float* pac, ptyb200_stream s) {
+    if (!c || !lc || !meas_all || !losses3 || !stats || !dp_out) return fail_msg("NULL argument");
+    if (lc->pacbed_state && !pac) return fail_msg("pacbed needs pacbed_scratch");
+    cudaStream_t st = (cudaStream_t)s;
+    LossFuse lf;
+    memset(&lf, 0, sizeof lf);
+    lf.on = 1;
+    lf.k = make_lossk(*lc);
+    if (const char* e = make_meas_view(*c, mcfg, meas_all, meas_padded, dp_out, dp_out, &lf.mv)) return fail_msg(e);
+    lf.stats = stats; lf.pac = pac; lf.rows = meas_rows ? meas_rows : idx;
+    CK(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
+    if (lf.k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
+    if (int r = forward_impl(c, idx, B, obja, objp, crop_pos, probe, shifts, Hbase, tilts, dz, occu, dp_out, workspace, &lf, s)) return r;
+    k_loss_final<<<1, 256, 0, st>>>(lf.k, B, c->N, stats, pac, losses3);
+    CKL();
     return 0;
 }
 
@@ -526,6 +557,47 @@ int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t plan
         k_blur5<1, true><<<grid, 256, 0, st>>>(b, in, tmp, total, H, W); CKL();
         k_blur5<0, true><<<grid, 256, 0, st>>>(b, tmp, out, total, H, W); CKL();
     }
+    return 0;
+}
+
+int ptyb200_blur_axis(const float* in, float* out, int64_t outer, int32_t L, int64_t inner, int32_t ksize, float sigma,
+                      int32_t pad_mode, ptyb200_stream s) {
+    if (!in || !out || in == out) return fail_msg("blur_axis needs distinct in / out buffers");
+    if (outer < 1 || L < 1 || inner < 1) return fail_msg("blur_axis: empty array");
+    if (ksize < 1 || ksize > 15 || !(ksize & 1)) return fail_msg("blur_axis: kernel size must be odd and <= 15");
+    if (!(sigma > 0.f)) return fail_msg("sigma must be positive");
+    if (pad_mode == 0 && ksize / 2 > L - 1) return fail_msg("blur_axis: reflect padding needs kernel_size/2 < length");
+    BlurTaps t;
+    double k[15], sum = 0;
+    for (int i = 0; i < ksize; ++i) { const double x = (i - (ksize - 1) / 2.0) / (double)sigma; k[i] = exp(-0.5 * x * x); sum += k[i]; }
+    for (int i = 0; i < ksize; ++i) t.k[i] = (float)(k[i] / sum);
+    t.n = ksize;
+    const long long total = (long long)outer * L * inner;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (pad_mode == 0) k_blur_axis<0><<<grid, 256, 0, (cudaStream_t)s>>>(t, in, out, total, L, inner);
+    else k_blur_axis<1><<<grid, 256, 0, (cudaStream_t)s>>>(t, in, out, total, L, inner);
+    CKL();
+    return 0;
+}
+
+int ptyb200_object_constraints(const ptyb200_obj_constraints* oc, float* obja, float* objp, int64_t n, float* scratch, ptyb200_stream s) {
+    if (!oc || !obja || !objp || n < 1) return fail_msg("NULL argument");
+    cudaStream_t st = (cudaStream_t)s;
+    ObjConstraints c;
+    c.mirrored_on = oc->mirrored_on; c.mirrored_relax = oc->mirrored_relax; c.mirrored_scale = oc->mirrored_scale; c.mirrored_power = oc->mirrored_power;
+    c.thresh_on = oc->thresh_on; c.thresh_relax = oc->thresh_relax; c.thresh_lo = oc->thresh_lo; c.thresh_hi = oc->thresh_hi;
+    c.postiv_on = oc->postiv_on; c.postiv_relax = oc->postiv_relax; c.postiv_subtract_min = oc->postiv_subtract_min;
+    if (!c.mirrored_on && !c.thresh_on && !c.postiv_on) return 0;
+    if (c.postiv_on && c.postiv_subtract_min) {
+        if (!scratch) return fail_msg("objp_postiv mode 'subtract_min' needs one float of scratch");
+        const unsigned inf_bits = 0x7f800000u;
+        CK(cudaMemsetAsync(scratch, 0, 4, st));
+        CK(cudaMemcpyAsync(scratch, &inf_bits, 4, cudaMemcpyHostToDevice, st));
+        k_obj_min<<<148 * 4, 256, 0, st>>>(objp, n, scratch);
+        CKL();
+    }
+    k_obj_voxel_constraints<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, obja, objp, n, scratch);
+    CKL();
     return 0;
 }
 

@@ -47,7 +47,6 @@ struct Args {
     FwdArgs f;
     const float2* HF;       // (TILE) layout F, pre-scaled by 1/N^2
     const float2* PhatF;    // (P, TILE) layout F, pre-scaled by 1/N^2
-    float* Ipart;           // (B, M, P, TILE) layout F partial intensities
     float2* farF;           // (B, M, P, TILE) layout F far-field spectra F2(psi_{Z-1} O_{Z-1}) (unnormalised), kept for the adjoint
     const float4* Opack;    // (M,Z,Noy,Nox) packed complex object
     float4* gOpack;         // (M,Z,Noy,Nox) packed dense object-gradient scratch
@@ -230,7 +229,7 @@ __device__ __forceinline__ void load_tables(const Smem& s, const Args& a, int b)
 // Every buffer this path owns is laid out so that a thread's two consecutive register elements (2j, 2j+1) are ONE 16-byte
 // word: float4 index j*512 + t inside a tile (t = yl*128 + x in layout R, t = threadIdx in layout F).  The global phases are
 // bound by (LG instruction-queue slots) / (L2 latency), so halving the instruction count matters more than the bytes.
-//   stash, farF, phisF, HF, PhatF, gPhatF : pairs of complex;   Ipart : quads of float
+//   stash, farF, phisF, HF, PhatF, gPhatF : pairs of complex
 //   Opack [m][z][Y][X] = (O[Y][X], O[Y+4][X])   -- a thread's rows yl+4k and yl+4(k+1) of the ROI in one aligned load,
 //                                                   for any crop offset (the plain object is only 8-byte aligned)
 //   gOpack[m][z][Y][X] = (contribution to gO[Y][X], contribution to gO[Y+4][X])  -- one red.global.add.v4.f32
@@ -257,17 +256,11 @@ __global__ void k_unpermute_from_F(const float2* __restrict__ srcF, float2* __re
     dstT[(size_t)c * TILE + kx * 128 + ky] = srcF[(size_t)c * TILE + p2_index(u, t)];
 }
 
-// dp[b][Y][X] = eps + sum_{m,p} Ipart[b,m,p][F index of (ky,kx)],  (Y,X) = fftshift(ky,kx).  grid (TILE/256, B)
-__global__ void k_dp_reduce(const float* __restrict__ Ipart, float* __restrict__ dp, int MP, float eps) {
-    const int b = blockIdx.y;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Y = pix >> 7, X = pix & 127;
-    const int ky = (Y + 64) & 127, kx = (X + 64) & 127;
-    const int r = ky & 31, w2 = r & 15, rsel = r >> 4, q = ky >> 5, vv = kx & 3, u = kx >> 2;
-    const int i = p4_index(u, w2 * 32 + rsel * 16 + q * 4 + vv);
-    float acc = 0.f;
-    for (int c = 0; c < MP; ++c) acc += Ipart[((size_t)b * MP + c) * TILE + i];
-    dp[(size_t)b * TILE + pix] = acc + eps;
+// dp <- eps, arrival counters <- 0: the forward CTAs ADD their mode's intensities into dp (red.global.add.v4.f32)
+__global__ void k_dp_init(float4* __restrict__ dp4, size_t n4, float eps, int* __restrict__ counter, int B) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n4) dp4[i] = make_float4(eps, eps, eps, eps);
+    if (i < (size_t)B) counter[i] = 0;
 }
 
 // Opack from (a, phi): O = a e^{i phi} (torch.polar, forward.py:53) written to [Y][X].xy and to [Y-4][X].zw
@@ -498,17 +491,64 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
         fft2_F_to_R(v, s.E, s.tw, g, [] {});
 #endif
     }
-    // far field: partial intensity of this (object mode, probe mode) in layout F (k_dp_reduce sums modes and fftshifts) and
-    // the spectrum itself for the adjoint
+    // far field: the spectrum itself is kept for the adjoint; this mode's intensity occu_m |Psi|^2 / N^2 is ADDED into dp (pre-set to
+    // eps by k_dp_init) -- the mode reduction of forward.py:79 happens in L2, no partial-intensity buffer, no reduction launch
     const float oc = a.f.occu[m] * (1.0f / (128.0f * 128.0f));
     const size_t ft = ((size_t)b * d.M + m) * d.P + p;
-    float4* __restrict__ ip = reinterpret_cast<float4*>(a.Ipart) + ft * (TILE / 4) + g.t;
     float4* __restrict__ ff = reinterpret_cast<float4*>(a.farF) + ft * (TILE / 2) + g.t;
 #pragma unroll
     for (int j = 0; j < 16; ++j) ff[j * 512] = pack2(v[2 * j], v[2 * j + 1]);
+    // layout F -> natural order through the (now idle) exchange buffer, so that the reds are whole 16-byte words of a row:
+    // float at [ky][kx ^ swz(ky)], swz flips the bank bits that the lanes' different ky would otherwise share
+    float* Ef = reinterpret_cast<float*>(s.E);
+    __syncthreads();                                   // every warp is done with its E2 reads of the last forward FFT
+    {
+        const int swz = (((g.ky >> 5) & 3) << 2) ^ (((g.ky >> 4) & 1) << 4);
+        float* row = Ef + g.ky * 128;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        ip[j * 512] = make_float4(oc * cabs2(v[4 * j]), oc * cabs2(v[4 * j + 1]), oc * cabs2(v[4 * j + 2]), oc * cabs2(v[4 * j + 3]));
+        for (int u = 0; u < 32; ++u) row[g.kx(u) ^ swz] = oc * cabs2(v[u]);
+    }
+    __syncthreads();
+    float* dpb = a.f.dp + (size_t)b * TILE;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i4 = g.t + 512 * j, ky = i4 >> 5, kx0 = (i4 & 31) << 2;
+        const int swz = (((ky >> 5) & 3) << 2) ^ (((ky >> 4) & 1) << 4);
+        const float4 q = *reinterpret_cast<const float4*>(Ef + ky * 128 + (kx0 ^ swz));
+        red_f4(reinterpret_cast<float4*>(dpb + ((ky + 64) & 127) * 128 + ((kx0 + 64) & 127)), make_float2(q.x, q.y), make_float2(q.z, q.w));
+    }
+    if (a.f.lf.on) {
+        // fused loss (north star item 3): the LAST of this pattern's M*P CTAs to arrive finds the finished intensities in L2 and adds
+        // the pattern's contribution to the batch sums of the data losses (what k_loss_partial does in the unfused sequence)
+        __threadfence();                               // this CTA's reds are performed before its arrival is counted
+        __syncthreads();
+        __shared__ int s_last;
+        if (threadIdx.x == 0) s_last = atomicAdd(a.f.lf.counter + b, 1) == d.M * d.P - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const LossFuse& lf = a.f.lf;
+            const float* M_ = lf.mv.meas + (size_t)lf.rows[b] * lf.mv.Hs * lf.mv.Ws;
+            float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (meas_plain(lf.mv)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int q = g.t + 512 * j;
+                    const float4 i4 = __ldcg(reinterpret_cast<const float4*>(dpb) + q);
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(M_) + q);
+                    loss_pixel(lf.k, i4.x, m4.x, 4 * q, TILE, lf.pac, acc5); loss_pixel(lf.k, i4.y, m4.y, 4 * q + 1, TILE, lf.pac, acc5);
+                    loss_pixel(lf.k, i4.z, m4.z, 4 * q + 2, TILE, lf.pac, acc5); loss_pixel(lf.k, i4.w, m4.w, 4 * q + 3, TILE, lf.pac, acc5);
+                }
+            } else {
+                for (int pix = g.t; pix < TILE; pix += FT)
+                    loss_pixel(lf.k, __ldcg(dpb + pix), meas_at(lf.mv, M_, pix >> 7, pix & 127), pix, TILE, lf.pac, acc5);
+            }
+            float* red5 = Ef;                          // 5 x 32 floats of scratch: the exchange buffer is idle
+            __syncthreads();
+            block_sum<5>(acc5, red5);
+            if (threadIdx.x == 0) loss_stats_commit(lf.k, acc5, lf.stats);
+        }
+    }
     if (g.lane == 0) bulk_wait_all();       // the staging blocks must outlive the TMA reads; writes complete before exit
 }
 
@@ -733,7 +773,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
 struct Scratch {
     float2 *HF, *PhatF, *gPhatF, *farF;
     float4 *Opack, *gOpack;
-    float* Ipart;
+    int* counter;           // (B) arrival counters of the fused loss
     size_t total;
 };
 inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
@@ -746,7 +786,7 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.Opack = (float4*)take(F128_OASYNC ? 0 : obj * 16);
     s.gOpack = (float4*)take(obj * 16);
-    s.Ipart = (float*)take((size_t)B * c.M * c.P * TILE * 4);
+    s.counter = (int*)take((size_t)B * 4);
     s.farF = (float2*)take((size_t)B * c.M * c.P * TILE * 8);
     s.total = off;
     return s;
@@ -763,7 +803,7 @@ inline int fail(std::string& err, const char* what, cudaError_t e) {
 inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc, float2* phis) {
     Args a;
     memset(&a, 0, sizeof a);
-    a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.Ipart = sc.Ipart; a.farF = sc.farF; a.phisF = f.phis ? phis : nullptr;
+    a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.farF = sc.farF; a.phisF = f.phis ? phis : nullptr;
     a.Opack = sc.Opack; a.gOpack = sc.gOpack;
     a.gPhatF = sc.gPhatF; a.shift = c.shift_probes;
     return a;
@@ -786,6 +826,12 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
         k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(f.PhatT, sc.PhatF, inv);
         F128_CK(cudaGetLastError()); ++*launches;
     }
+    a.f.lf.counter = sc.counter;
+    {
+        const size_t n4 = (size_t)B * TILE / 4;
+        k_dp_init<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(f.dp), n4, c.eps, sc.counter, B);
+        F128_CK(cudaGetLastError()); ++*launches;
+    }
     const dim3 grid(c.P, c.M, B);
     const bool tilt = f.tvec != nullptr, phis = a.phisF != nullptr;
 #define F128_LAUNCH_FWD(T, PH)                                                                                                     \
@@ -796,8 +842,6 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
     if (tilt) { if (phis) F128_LAUNCH_FWD(true, true); else F128_LAUNCH_FWD(true, false); }
     else      { if (phis) F128_LAUNCH_FWD(false, true); else F128_LAUNCH_FWD(false, false); }
 #undef F128_LAUNCH_FWD
-    F128_CK(cudaGetLastError()); ++*launches;
-    k_dp_reduce<<<dim3(TILE / 256, B), 256, 0, st>>>(sc.Ipart, f.dp, c.M * c.P, c.eps);
     F128_CK(cudaGetLastError()); ++*launches;
     return 0;
 }

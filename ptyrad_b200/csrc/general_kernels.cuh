@@ -241,7 +241,7 @@ template <class F> struct Slab {
             f(i, e % ROWS, e / ROWS);
         }
     }
-    static constexpr size_t smem_bytes() { return sizeof(float2) * (SLAB_ELEMS + N) + sizeof(float) * (ROWS * (N + 1) + 4 * 32); }
+    static constexpr size_t smem_bytes() { return sizeof(float2) * (SLAB_ELEMS + N) + sizeof(float) * (ROWS * (N + 1) + 8 * 32); }
 };
 
 #define PTYB_SMEM_CARVE(F)                                                      \
@@ -284,6 +284,80 @@ template <class F, int DIR, bool TOUT> __global__ void __launch_bounds__(NT, GEN
 }
 
 // ------------------------------------------------------------------------------------------------
+// loss terms and the measurement view (losses.py:36-104, models.py:384-416): used by the loss kernels further down and by the
+// kernels that fuse the mode reduction with the loss
+// ------------------------------------------------------------------------------------------------
+struct LossK {
+    int s_on, p_on, b_on;
+    float s_w, s_p, p_w, p_p, p_eps, b_w, b_p;
+};
+
+// x^p with the exponents the loss terms actually use evaluated exactly-rounded and cheaply (dp_pow = 0.5 and 1 and their
+// derivative exponents -0.5 and 0; powf costs ~10x more and is kept for everything else)
+__device__ __forceinline__ float powp(float x, float p) {
+    if (p == 0.5f) return sqrtf(x);
+    if (p == 1.0f) return x;
+    if (p == -0.5f) return 1.0f / sqrtf(x);
+    if (p == 0.0f) return 1.0f;
+    return powf(x, p);
+}
+
+// Measured pattern of sample b as the loss sees it (models.py:384-416): row idx[b] of the stored (Ntot,Hs,Ws) array, optionally
+// pasted into a padded background canvas (Hp,Wp) at [h1:h2, w1:w2] ("on-the-fly" padding, models.py:401-405) and optionally
+// resampled bilinearly by fixed scale factors and divided by their product (models.py:407-409; the arithmetic follows ATen's
+// upsample_bilinear2d with align_corners = false and a given scale_factor: src = (dst + 0.5) / scale - 0.5, clamped at 0).
+// Evaluated on the fly inside the loss kernels: no gathered / padded / resampled copy is ever materialised.
+struct MeasView {
+    const float* meas;      // (Ntot,Hs,Ws)
+    const float* padded;    // (Hp,Wp) or null
+    int Hs, Ws, Hp, Wp, h1, w1, h2, w2;
+    int resample;           // 0: output pixel = source pixel
+    int vec;                // 1: plain layout and 16-byte aligned rows -> 128-bit reads
+    float ry, rx;           // source pixels per output pixel (1 / scale_factor)
+    float scale;            // 1 / prod(scale_factor)
+};
+__device__ __forceinline__ float meas_src(const MeasView& v, const float* __restrict__ Mrow, int y, int x) {
+    if (!v.padded) return Mrow[(size_t)y * v.Ws + x];
+    if (y >= v.h1 && y < v.h2 && x >= v.w1 && x < v.w2) return Mrow[(size_t)(y - v.h1) * v.Ws + (x - v.w1)];
+    return v.padded[(size_t)y * v.Wp + x];
+}
+__device__ __forceinline__ float meas_at(const MeasView& v, const float* __restrict__ Mrow, int Y, int X) {
+    if (!v.resample) return meas_src(v, Mrow, Y, X);
+    const int H = v.padded ? v.Hp : v.Hs, W = v.padded ? v.Wp : v.Ws;
+    const float sy = fmaxf(v.ry * (float(Y) + 0.5f) - 0.5f, 0.f), sx = fmaxf(v.rx * (float(X) + 0.5f) - 0.5f, 0.f);
+    const int y0 = min(int(sy), H - 1), x0 = min(int(sx), W - 1);
+    const int yp = y0 < H - 1 ? 1 : 0, xp = x0 < W - 1 ? 1 : 0;
+    const float ly = sy - float(y0), lx = sx - float(x0), hy = 1.f - ly, hx = 1.f - lx;
+    const float val = hy * (hx * meas_src(v, Mrow, y0, x0) + lx * meas_src(v, Mrow, y0, x0 + xp)) +
+                      ly * (hx * meas_src(v, Mrow, y0 + yp, x0) + lx * meas_src(v, Mrow, y0 + yp, x0 + xp));
+    return val * v.scale;
+}
+__device__ __forceinline__ bool meas_plain(const MeasView& v) { return v.vec != 0; }
+
+// fused mode reduction + loss (north star item 3): the kernel that completes the intensities of a pattern also forms that pattern's
+// contribution to the batch sums of the data losses, so dp is not re-read by a separate reduction launch
+struct LossFuse {
+    int on;
+    LossK k;
+    MeasView mv;
+    double* stats;          // 8 doubles, zeroed (see k_loss_partial)
+    float* pac;             // 2*N*N floats, zeroed (PACBED sums) or null
+    int* counter;           // fused path: one arrival counter per pattern, zeroed
+    const int64_t* rows;    // (B) row of `mv.meas` holding the pattern of sample b
+};
+// contribution of one pixel to the five running sums (a[0..4]) of k_loss_partial
+__device__ __forceinline__ void loss_pixel(const LossK& k, float I, float Mv, int pix, int NN, float* pac, float (&a)[5]) {
+    if (k.s_on) { float mp = powp(Mv, k.s_p), df = powp(I, k.s_p) - mp; a[0] += df * df; a[1] += mp; }
+    if (k.p_on) { float mq = powp(Mv, k.p_p), iq = powp(I, k.p_p); a[2] += mq * logf(iq + k.p_eps) - iq; a[3] += mq; }
+    if (k.b_on) { a[4] += powp(Mv, k.b_p); atomicAdd(pac + pix, I); atomicAdd(pac + NN + pix, Mv); }
+}
+__device__ __forceinline__ void loss_stats_commit(const LossK& k, const float (&v)[5], double* stats) {
+    if (k.s_on) { atomicAdd(stats + 0, (double)v[0]); atomicAdd(stats + 1, (double)v[1]); }
+    if (k.p_on) { atomicAdd(stats + 2, (double)v[2]); atomicAdd(stats + 3, (double)v[3]); }
+    if (k.b_on) atomicAdd(stats + 4, (double)v[4]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 struct FwdArgs {
@@ -304,6 +378,7 @@ struct FwdArgs {
     float2* farT;           // (B,P,M,N,N) [kx][y]
     float* dp;              // (B,N,N)
     float eps;
+    LossFuse lf;            // lf.on: also accumulate the data-loss sums while the intensities are complete in registers
 };
 
 // psi0 half-shifted: G2[b,p,0][y][kx] = (1/N) * inverse-y( PhatT[p][kx][ky] * wy[ky] * wx[kx] ).  grid (N/ROWS, groups, chunk)
@@ -539,6 +614,16 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_fwd_final(F
     __syncthreads();
     float* dp = a.dp + (size_t)b * N * N;
     Slab<F>::tr([&](int, int rr, int ky) { dp[(size_t)shift_idx(ky, N) * N + shift_idx(kx0 + rr, N)] = fbuf[rr * (N + 1) + ky]; });
+    if (a.lf.on) {                                   // this CTA holds the finished intensities of its slab: add its loss sums
+        const float* M_ = a.lf.mv.meas + (size_t)a.lf.rows[b] * a.lf.mv.Hs * a.lf.mv.Ws;
+        float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        Slab<F>::tr([&](int, int rr, int ky) {
+            const int Y = shift_idx(ky, N), X = shift_idx(kx0 + rr, N);
+            loss_pixel(a.lf.k, fbuf[rr * (N + 1) + ky], meas_at(a.lf.mv, M_, Y, X), Y * N + X, N * N, a.lf.pac, acc5);
+        });
+        block_sum<5>(acc5, red);
+        if (threadIdx.x == 0) loss_stats_commit(a.lf.k, acc5, a.lf.stats);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -905,53 +990,6 @@ __global__ void k_prop_finish(const float* __restrict__ gprop, const float* __re
 // ------------------------------------------------------------------------------------------------
 // losses (losses.py:36-104)
 // ------------------------------------------------------------------------------------------------
-struct LossK {
-    int s_on, p_on, b_on;
-    float s_w, s_p, p_w, p_p, p_eps, b_w, b_p;
-};
-
-// x^p with the exponents the loss terms actually use evaluated exactly-rounded and cheaply (dp_pow = 0.5 and 1 and their
-// derivative exponents -0.5 and 0; powf costs ~10x more and is kept for everything else)
-__device__ __forceinline__ float powp(float x, float p) {
-    if (p == 0.5f) return sqrtf(x);
-    if (p == 1.0f) return x;
-    if (p == -0.5f) return 1.0f / sqrtf(x);
-    if (p == 0.0f) return 1.0f;
-    return powf(x, p);
-}
-
-// Measured pattern of sample b as the loss sees it (models.py:384-416): row idx[b] of the stored (Ntot,Hs,Ws) array, optionally
-// pasted into a padded background canvas (Hp,Wp) at [h1:h2, w1:w2] ("on-the-fly" padding, models.py:401-405) and optionally
-// resampled bilinearly by fixed scale factors and divided by their product (models.py:407-409; the arithmetic follows ATen's
-// upsample_bilinear2d with align_corners = false and a given scale_factor: src = (dst + 0.5) / scale - 0.5, clamped at 0).
-// Evaluated on the fly inside the loss kernels: no gathered / padded / resampled copy is ever materialised.
-struct MeasView {
-    const float* meas;      // (Ntot,Hs,Ws)
-    const float* padded;    // (Hp,Wp) or null
-    int Hs, Ws, Hp, Wp, h1, w1, h2, w2;
-    int resample;           // 0: output pixel = source pixel
-    int vec;                // 1: plain layout and 16-byte aligned rows -> 128-bit reads
-    float ry, rx;           // source pixels per output pixel (1 / scale_factor)
-    float scale;            // 1 / prod(scale_factor)
-};
-__device__ __forceinline__ float meas_src(const MeasView& v, const float* __restrict__ Mrow, int y, int x) {
-    if (!v.padded) return Mrow[(size_t)y * v.Ws + x];
-    if (y >= v.h1 && y < v.h2 && x >= v.w1 && x < v.w2) return Mrow[(size_t)(y - v.h1) * v.Ws + (x - v.w1)];
-    return v.padded[(size_t)y * v.Wp + x];
-}
-__device__ __forceinline__ float meas_at(const MeasView& v, const float* __restrict__ Mrow, int Y, int X) {
-    if (!v.resample) return meas_src(v, Mrow, Y, X);
-    const int H = v.padded ? v.Hp : v.Hs, W = v.padded ? v.Wp : v.Ws;
-    const float sy = fmaxf(v.ry * (float(Y) + 0.5f) - 0.5f, 0.f), sx = fmaxf(v.rx * (float(X) + 0.5f) - 0.5f, 0.f);
-    const int y0 = min(int(sy), H - 1), x0 = min(int(sx), W - 1);
-    const int yp = y0 < H - 1 ? 1 : 0, xp = x0 < W - 1 ? 1 : 0;
-    const float ly = sy - float(y0), lx = sx - float(x0), hy = 1.f - ly, hx = 1.f - lx;
-    const float val = hy * (hx * meas_src(v, Mrow, y0, x0) + lx * meas_src(v, Mrow, y0, x0 + xp)) +
-                      ly * (hx * meas_src(v, Mrow, y0 + yp, x0) + lx * meas_src(v, Mrow, y0 + yp, x0 + xp));
-    return val * v.scale;
-}
-__device__ __forceinline__ bool meas_plain(const MeasView& v) { return v.vec != 0; }
-
 // the transformed patterns as a tensor (PtychoAD.get_measurements(indices), models.py:384-416).  grid (chunks, B)
 __global__ void k_meas_gather(MeasView mv, const int64_t* __restrict__ idx, int N, float* __restrict__ out) {
     const int NN = N * N, b = blockIdx.y;
@@ -967,12 +1005,8 @@ __global__ void k_loss_partial(LossK k, const float* __restrict__ dp, MeasView m
     const int NN = N * N, b = blockIdx.y;
     const float* __restrict__ I_ = dp + (size_t)b * NN;
     const float* __restrict__ M_ = mv.meas + (size_t)idx[b] * mv.Hs * mv.Ws;
-    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-    auto term = [&](int pix, float I, float Mv) {
-        if (k.s_on) { float mp = powp(Mv, k.s_p), df = powp(I, k.s_p) - mp; a0 += df * df; a1 += mp; }
-        if (k.p_on) { float mq = powp(Mv, k.p_p), iq = powp(I, k.p_p); a2 += mq * logf(iq + k.p_eps) - iq; a3 += mq; }
-        if (k.b_on) { a4 += powp(Mv, k.b_p); atomicAdd(pac + pix, I); atomicAdd(pac + NN + pix, Mv); }
-    };
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    auto term = [&](int pix, float I, float Mv) { loss_pixel(k, I, Mv, pix, NN, pac, v); };
     if (meas_plain(mv)) {                                     // 128-bit reads of both streams (N*N is a multiple of 4)
         const float4* __restrict__ I4 = reinterpret_cast<const float4*>(I_);
         const float4* __restrict__ M4 = reinterpret_cast<const float4*>(M_);
@@ -985,13 +1019,8 @@ __global__ void k_loss_partial(LossK k, const float* __restrict__ dp, MeasView m
             term(pix, I_[pix], meas_at(mv, M_, pix / N, pix % N));
     }
     __shared__ float red[5 * 32];
-    float v[5] = {a0, a1, a2, a3, a4};
     block_sum<5>(v, red);
-    if (threadIdx.x == 0) {
-        if (k.s_on) { atomicAdd(stats + 0, (double)v[0]); atomicAdd(stats + 1, (double)v[1]); }
-        if (k.p_on) { atomicAdd(stats + 2, (double)v[2]); atomicAdd(stats + 3, (double)v[3]); }
-        if (k.b_on) atomicAdd(stats + 4, (double)v[4]);
-    }
+    if (threadIdx.x == 0) loss_stats_commit(k, v, stats);
 }
 
 __global__ void k_loss_final(LossK k, int B, int N, double* stats, const float* __restrict__ pac, float* losses3) {
@@ -1142,6 +1171,62 @@ template <int AXIS, bool ADJ> __global__ void k_blur5(Blur5 b, const float* __re
         acc += w * base[(long long)o * stride];
     }
     out[e] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-iteration object constraints (constraints.py:83-114, 165-208), SURVEY 8f rank 3: streaming passes over the object, in place
+// ------------------------------------------------------------------------------------------------
+// 1-D Gaussian blur along one axis of a dense array viewed as (outer, L, inner): obj_rblur (x then y, reflect padding: torchvision
+// gaussian_blur, constraints.py:94-97) and obj_zblur (z, replicate padding: Conv1d(padding_mode='replicate'), image_proc.py:443-455)
+struct BlurTaps { float k[15]; int n; };
+template <int PAD /*0 reflect, 1 replicate*/>
+__global__ void k_blur_axis(BlurTaps t, const float* __restrict__ in, float* __restrict__ out, long long total, int L, long long inner) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int l = int((e / inner) % L);
+    const float* base = in + (e - (long long)l * inner);
+    const int h = t.n >> 1;
+    float acc = 0.f;
+    for (int i = 0; i < t.n; ++i) {
+        int o = l + i - h;
+        if (PAD == 0) { if (o < 0) o = -o; if (o > L - 1) o = 2 * (L - 1) - o; o = max(0, min(L - 1, o)); }
+        else o = max(0, min(L - 1, o));
+        acc += t.k[i] * base[(long long)o * inner];
+    }
+    out[e] = acc;
+}
+
+struct ObjConstraints {
+    int mirrored_on; float mirrored_relax, mirrored_scale, mirrored_power;
+    int thresh_on;   float thresh_relax, thresh_lo, thresh_hi;
+    int postiv_on;   float postiv_relax; int postiv_subtract_min;
+};
+__global__ void k_obj_min(const float* __restrict__ p, long long n, float* out /* pre-set to +inf */) {
+    float m = INFINITY;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fminf(m, p[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) {            // float min through the ordered-int trick (valid for any sign)
+        int* oi = reinterpret_cast<int*>(out);
+        if (m >= 0.f) atomicMin(oi, __float_as_int(m)); else atomicMax(reinterpret_cast<unsigned*>(oi), __float_as_uint(m));
+    }
+}
+// mirrored_amp -> obja_thresh -> objp_postiv in the reference's order (constraints.py:240-243), one read and one write per voxel
+__global__ void k_obj_voxel_constraints(ObjConstraints c, float* __restrict__ a, float* __restrict__ p, long long n, const float* __restrict__ pmin) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float av = a[i], pv = p[i];
+    if (c.mirrored_on) {
+        const float vp = powf(fmaxf(pv, 0.f), c.mirrored_power);
+        av = c.mirrored_relax * av + (1.f - c.mirrored_relax) * (1.f - c.mirrored_scale * vp);
+    }
+    if (c.thresh_on) av = c.thresh_relax * av + (1.f - c.thresh_relax) * fminf(fmaxf(av, c.thresh_lo), c.thresh_hi);
+    if (c.postiv_on) {
+        const float mod = c.postiv_subtract_min ? pv - pmin[0] : fmaxf(pv, 0.f);
+        pv = c.postiv_relax * pv + (1.f - c.postiv_relax) * mod;
+    }
+    if (c.mirrored_on || c.thresh_on) a[i] = av;
+    if (c.postiv_on) p[i] = pv;
 }
 
 // ------------------------------------------------------------------------------------------------

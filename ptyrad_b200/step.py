@@ -117,18 +117,23 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
     dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
     tl = tilts if cfg.tilt_mode else None
     sh = shifts if cfg.shift_probes else None
-    _lib.check(lib.ptyb200_forward(C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
-                                   ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws), st))
-    blur = model.detector_blur_std
-    if blur:                                                  # detector blur (models.py:379-380): native 5x5 kernel on the intensities
-        dp = engine._blur5(dp, float(blur), 0)
     # losses: [single, poissn, pacbed] and [sparse] land in one (5,) tensor; simlar (slot 4) is off on this path
     lcfg = loss_fn.lcfg()
     losses = torch.zeros(5, dtype=torch.float32, device=dev)
     stats = torch.empty(8, dtype=torch.float64, device=dev)
     pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
-    _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
-                                        ptr(pac), engine.mref(meas.mcfg), ptr(meas.padded), st))
+    blur = model.detector_blur_std
+    fwd_args = (C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
+                ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws))
+    if not blur:
+        # forward with the mode reduction fused with the data losses: the kernel that completes a pattern also adds its loss sums
+        _lib.check(lib.ptyb200_forward_loss(*fwd_args, C.byref(lcfg), ptr(meas.all), ptr(meas.idx), engine.mref(meas.mcfg), ptr(meas.padded),
+                                            ptr(losses), ptr(stats), ptr(pac), st))
+    else:
+        _lib.check(lib.ptyb200_forward(*fwd_args, st))
+        dp = engine._blur5(dp, float(blur), 0)                # detector blur (models.py:379-380): native 5x5 kernel on the intensities
+        _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
+                                            ptr(pac), engine.mref(meas.mcfg), ptr(meas.padded), st))
     sparse = bool(lcfg.sparse_state)
     if sparse:
         Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)

@@ -145,3 +145,40 @@ def test_reference_driver_runs_its_own_model_on_cpu():
     batches = [np.arange(0, 5), np.arange(5, 11)]
     h, p, m = _drive(REF.PtychoAD, REF.CombinedLoss, "cpu", iv, mp, lp, batches, 2)
     assert len(h) == 2 and all(np.isfinite(h[1][k]).all() for k in lp) and len(m.loss_iters) == 2
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("postiv_mode", ["clip_neg", "subtract_min"])
+def test_native_object_constraints_match_the_reference(postiv_mode):
+    """ptyrad_b200.constraints.CombinedConstraint (obj_rblur / obj_zblur / mirrored_amp / obja_thresh / objp_postiv in the CUDA library,
+    in place; the rest delegated to the reference at its place in the sequence) against the reference's CombinedConstraint on a twin
+    model: same parameters afterwards, and no .data re-binding for the native ones."""
+    import ptyrad_b200
+    from ptyrad_b200.constraints import CombinedConstraint
+    cfg, iv, mp, lp = _inputs("T64", seed=55, M=2)
+    rng = np.random.default_rng(3)
+    iv = dict(iv)
+    iv["obj"] = (iv["obj"] * np.exp(1j * rng.normal(0, 0.2, iv["obj"].shape))).astype(np.complex64)      # negative phases too
+    cp = constraint_params(cfg.Z)
+    cp["obj_rblur"] = dict(freq=1, obj_type="both", kernel_size=5, std=0.7)
+    cp["obj_zblur"] = dict(freq=1, obj_type="phase", kernel_size=3, std=0.8)
+    cp["mirrored_amp"] = dict(freq=1, relax=0.1, scale=0.03, power=4)
+    cp["obja_thresh"] = dict(freq=1, relax=0.2, thresh=[0.985, 1.0])
+    cp["objp_postiv"] = dict(freq=1, relax=0.1, mode=postiv_mode)
+    cp["kr_filter"]["freq"] = 2                                   # a non-native one in the middle of the sequence (iteration 2)
+    a = ptyrad_b200.PtychoAD(iv, mp, device="cuda", verbose=False)
+    b = ptyrad_b200.PtychoAD(iv, mp, device="cuda", verbose=False)
+    ref_c = REF.CombinedConstraint(cp, device="cuda", verbose=False)
+    ours = CombinedConstraint(cp, device="cuda", verbose=False, fallback=REF.CombinedConstraint(cp, device="cuda", verbose=False))
+    ptr_a, ptr_p = b.opt_obja.data_ptr(), b.opt_objp.data_ptr()
+    for it in (1, 2):
+        ref_c(a, it)
+        ours(b, it)
+        for name in ("opt_obja", "opt_objp", "opt_probe"):
+            x, y = getattr(a, name).detach().cpu().numpy(), getattr(b, name).detach().cpu().numpy()
+            assert rel(y, x) < 2e-6, (it, name, rel(y, x))
+        if it == 1:
+            assert (b.opt_obja.data_ptr(), b.opt_objp.data_ptr()) == (ptr_a, ptr_p)       # in place
+    with pytest.raises(NotImplementedError):
+        CombinedConstraint(cp, device="cuda", verbose=False)(b, 2)                       # kr_filter without a fallback
