@@ -195,6 +195,12 @@ int ptyb200_blur_axis(const float* in, float* out, int64_t outer, int32_t L, int
 int ptyb200_object_constraints(const ptyb200_obj_constraints* oc, float* obja, float* objp, int64_t n, float* scratch,
                                ptyb200_stream s);
 
+/* 'sparse' grouping of scan positions (make_batches, reconstruction.py:540-587): the greedy assignment loop.  pos_ordered = (n,2)
+ * float64 positions, the G group seeds first (group g's seed in row g: the point closest to the centroid of compact group g,
+ * reconstruction.py:556-562), then the remaining points in the order the reference visits them.  labels_out[i] = group of row i:
+ * each point joins the group whose nearest member is farthest from it (first group on ties, np.argmax).  One CTA; O(n^2 / 2). */
+int ptyb200_sparse_groups(const double* pos_ordered, int32_t n, int32_t G, int32_t* labels_out, ptyb200_stream s);
+
 /* optimizer.step() for torch.optim.Adam defaults (reconstruction.py:759; built at reconstruction.py:285-368):
  * one launch over up to 8 tensors with per-tensor learning rates.  The host arrays of pointers / lrs / numels are read
  * during the call.  steps[i] is tensor i's OWN step counter, one device float32 scalar (torch.optim.Adam's state['step']): the call

@@ -3,6 +3,7 @@
 #include "../../include/ptyrad_b200.h"
 #include "general_kernels.cuh"
 #include "fused128.cuh"
+#include "grouping.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -185,10 +186,8 @@ template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace
                                     const float* objp, const float* probe, const float* shifts, const float* Hbase,
                                     const float* tilts, const float* dz, cudaStream_t st) {
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-    if (!use_fused(c) || F128_OASYNC) {        // (the pre-cp.async fused variant builds its own packed copy of the complex object)
-        k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
-        CKL();
-    }
+    k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
+    CKL();
     dim3 tb(32, 8), tg((c.N + 31) / 32, (c.N + 31) / 32);
     k_transpose<<<tg, tb, 0, st>>>((const float2*)Hbase, w.HT, c.N);
     CKL();
@@ -557,6 +556,16 @@ int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t plan
         k_blur5<1, true><<<grid, 256, 0, st>>>(b, in, tmp, total, H, W); CKL();
         k_blur5<0, true><<<grid, 256, 0, st>>>(b, tmp, out, total, H, W); CKL();
     }
+    return 0;
+}
+
+int ptyb200_sparse_groups(const double* pos_ordered, int32_t n, int32_t G, int32_t* labels_out, ptyb200_stream s) {
+    if (!pos_ordered || !labels_out) return fail_msg("NULL argument");
+    if (G < 1 || n < G) return fail_msg("sparse_groups needs 1 <= G <= n (one seed per group comes first)");
+    if (G > 4096) return fail_msg("sparse_groups: at most 4096 groups");
+    const size_t smem = (size_t)G * 8 + 32 * 8 + 32 * 4;
+    k_sparse_groups<<<1, GROUP_THREADS, smem, (cudaStream_t)s>>>(reinterpret_cast<const double2*>(pos_ordered), n, G, labels_out);
+    CKL();
     return 0;
 }
 

@@ -122,9 +122,59 @@ template <int DIR> struct Dft<4, DIR> {
     }
 };
 
-template <int R, int DIR, int A, int B, int... Is>
-PTYB_HD void apply_twiddles(float2 (*y)[B], std::integer_sequence<int, Is...>) {
-    ((y[Is / B][Is % B] = twmul<(Is / B) * (Is % B), R, DIR>(y[Is / B][Is % B])), ...);
+// Butterfly with the twiddle FOLDED into the FMAs (Linzer-Feig):  op = p + w q,  om = p - w q,  w = exp(DIR * 2*pi*i * K/R).
+// With w = c (1 + i t), t = tan (or w = s (cot + i) when |s| > |c|): u = (1 + i t) q costs 2 FFMA and p +- c u costs 4, six
+// instructions where "complex multiply, then add and subtract" costs eight; t and c are compile-time immediates.
+template <int K, int R, int DIR> PTYB_HD void bfly_tw(float2 p, float2 q, float2& op, float2& om) {
+    constexpr int k = ((K % R) + R) % R;
+    if constexpr (k == 0) { op = cadd(p, q); om = csub(p, q); }
+    else if constexpr (2 * k == R) { op = csub(p, q); om = cadd(p, q); }
+    else if constexpr (4 * k == R) { const float2 t = mul_i<DIR>(q); op = cadd(p, t); om = csub(p, t); }
+    else if constexpr (4 * k == 3 * R) { const float2 t = mul_i<DIR>(q); op = csub(p, t); om = cadd(p, t); }
+    else {
+        constexpr cd w = cs2pi(k, R);
+        constexpr double c = w.c, s = DIR * w.s;
+        if constexpr ((c < 0 ? -c : c) >= (s < 0 ? -s : s)) {
+            constexpr float t = float(s / c), cf = float(c);
+            const float2 u = make_float2(fmaf(-t, q.y, q.x), fmaf(t, q.x, q.y));
+            op = make_float2(fmaf(cf, u.x, p.x), fmaf(cf, u.y, p.y));
+            om = make_float2(fmaf(-cf, u.x, p.x), fmaf(-cf, u.y, p.y));
+        } else {
+            constexpr float t = float(c / s), sf = float(s);
+            const float2 u = make_float2(fmaf(t, q.x, -q.y), fmaf(t, q.y, q.x));
+            op = make_float2(fmaf(sf, u.x, p.x), fmaf(sf, u.y, p.y));
+            om = make_float2(fmaf(-sf, u.x, p.x), fmaf(-sf, u.y, p.y));
+        }
+    }
+}
+
+// second stage of the composite transform for one output residue KB: DFT_A over t[a] * W_R^{a KB}, twiddles folded
+template <int R, int DIR, int A, int B, int KB> PTYB_HD void second_stage(float2 (*y)[B], float2* v) {
+    float2 t[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) t[a] = y[a][KB];
+    if constexpr (A == 4) {
+        // s_a = W^{a KB} t_a, W^{3 KB} = W^{KB} W^{2 KB}:  X0,2 = (t0 + W^2KB t2) +- W^KB (t1 + W^2KB t3),
+        //                                                  X1,3 = (t0 - W^2KB t2) +- (DIR i) W^KB (t1 - W^2KB t3)
+        float2 a0, a1, b0, b1;
+        bfly_tw<2 * KB, R, DIR>(t[0], t[2], a0, a1);
+        bfly_tw<2 * KB, R, DIR>(t[1], t[3], b0, b1);
+        bfly_tw<KB, R, DIR>(a0, b0, t[0], t[2]);
+        bfly_tw<KB + R / 4, R, DIR>(a1, b1, t[1], t[3]);
+    } else if constexpr (A == 2) {
+        bfly_tw<KB, R, DIR>(t[0], t[1], t[0], t[1]);
+    } else {
+        static_assert(A == 3, "radix");
+        t[1] = twmul<KB, R, DIR>(t[1]);
+        t[2] = twmul<2 * KB, R, DIR>(t[2]);
+        Dft<A, DIR>::run(t);
+    }
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka) v[KB + B * ka] = t[ka];
+}
+template <int R, int DIR, int A, int B, int... KBs>
+PTYB_HD void second_stages(float2 (*y)[B], float2* v, std::integer_sequence<int, KBs...>) {
+    (second_stage<R, DIR, A, B, KBs>(y, v), ...);
 }
 
 // composite R = A*B:  X[kb + B*ka] = sum_a W_A^{a ka} W_R^{a kb} sum_b W_B^{b kb} x[a + A b]
@@ -139,16 +189,7 @@ template <int R, int DIR> struct Dft {
             for (int b = 0; b < B; ++b) y[a][b] = v[a + A * b];
 #pragma unroll
         for (int a = 0; a < A; ++a) Dft<B, DIR>::run(y[a]);
-        apply_twiddles<R, DIR, A, B>(y, std::make_integer_sequence<int, A * B>{});
-#pragma unroll
-        for (int kb = 0; kb < B; ++kb) {
-            float2 t[A];
-#pragma unroll
-            for (int a = 0; a < A; ++a) t[a] = y[a][kb];
-            Dft<A, DIR>::run(t);
-#pragma unroll
-            for (int ka = 0; ka < A; ++ka) v[kb + B * ka] = t[ka];
-        }
+        second_stages<R, DIR, A, B>(y, v, std::make_integer_sequence<int, B>{});
     }
 };
 

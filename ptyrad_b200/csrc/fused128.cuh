@@ -48,7 +48,6 @@ struct Args {
     const float2* HF;       // (TILE) layout F, pre-scaled by 1/N^2
     const float2* PhatF;    // (P, TILE) layout F, pre-scaled by 1/N^2
     float2* farF;           // (B, M, P, TILE) layout F far-field spectra F2(psi_{Z-1} O_{Z-1}) (unnormalised), kept for the adjoint
-    const float4* Opack;    // (M,Z,Noy,Nox) packed complex object
     float4* gOpack;         // (M,Z,Noy,Nox) packed dense object-gradient scratch
     float2* phisF;          // (B,P,M,Z-1,TILE) layout F or null
     // adjoint only
@@ -230,8 +229,6 @@ __device__ __forceinline__ void load_tables(const Smem& s, const Args& a, int b)
 // word: float4 index j*512 + t inside a tile (t = yl*128 + x in layout R, t = threadIdx in layout F).  The global phases are
 // bound by (LG instruction-queue slots) / (L2 latency), so halving the instruction count matters more than the bytes.
 //   stash, farF, phisF, HF, PhatF, gPhatF : pairs of complex
-//   Opack [m][z][Y][X] = (O[Y][X], O[Y+4][X])   -- a thread's rows yl+4k and yl+4(k+1) of the ROI in one aligned load,
-//                                                   for any crop offset (the plain object is only 8-byte aligned)
 //   gOpack[m][z][Y][X] = (contribution to gO[Y][X], contribution to gO[Y+4][X])  -- one red.global.add.v4.f32
 __device__ __forceinline__ int p2_index(int u, int t) { return (((u >> 1) * 512 + t) << 1) + (u & 1); }   // float2 index
 __device__ __forceinline__ int p4_index(int u, int t) { return (((u >> 2) * 512 + t) << 2) + (u & 3); }   // float index
@@ -263,21 +260,6 @@ __global__ void k_dp_init(float4* __restrict__ dp4, size_t n4, float eps, int* _
     if (i < (size_t)B) counter[i] = 0;
 }
 
-// Opack from (a, phi): O = a e^{i phi} (torch.polar, forward.py:53) written to [Y][X].xy and to [Y-4][X].zw
-__global__ void k_obj_polar_pack(const float* __restrict__ a, const float* __restrict__ ph, float4* __restrict__ Op, int Noy, int Nox,
-                                 size_t n) {
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s, c;
-    sincosf(ph[i], &s, &c);
-    const float av = a[i];
-    const float2 o = make_float2(av * c, av * s);
-    const int Y = int((i / Nox) % Noy);
-    float2* lo = reinterpret_cast<float2*>(Op + i);
-    lo[0] = o;
-    if (Y + 4 >= Noy) lo[1] = make_float2(0.f, 0.f);
-    if (Y >= 4) reinterpret_cast<float2*>(Op + i - (size_t)4 * Nox)[1] = o;
-}
 // g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O)) with gO[Y][X] = gOpack[Y][X].xy + gOpack[Y-4][X].zw
 __global__ void k_obj_finish_pack(const float4* __restrict__ gOp, const float* __restrict__ a, const float* __restrict__ ph,
                                   float* __restrict__ ga, float* __restrict__ gp, int Noy, int Nox, size_t n) {
@@ -310,13 +292,6 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 __device__ __forceinline__ void l2_prefetch_tile(const float4* tile) {
     if (threadIdx.x < 32) l2_prefetch(tile + threadIdx.x * 256, 4096);
 }
-// the 64 packed ROI rows of one slice that this CTA reads (rows cy + yl + 8 j, yl < 4, j < 16; 2 KB each, 16-byte aligned)
-__device__ __forceinline__ void l2_prefetch_roi(const float4* plane, int cy, int cx, int Nox) {
-    if (threadIdx.x >= 32 && threadIdx.x < 96) {
-        const int i = threadIdx.x - 32;
-        l2_prefetch(plane + (size_t)(cy + (i & 3) + 8 * (i >> 2)) * Nox + cx, 2048);
-    }
-}
 // TMA bulk copy shared -> global (asynchronous, issued by one lane; no LSU store traffic, no register reads at drain time)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -333,16 +308,11 @@ __device__ __forceinline__ float2 lo2(float4 q) { return make_float2(q.x, q.y); 
 __device__ __forceinline__ float2 hi2(float4 q) { return make_float2(q.z, q.w); }
 __device__ __forceinline__ float4 pack2(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
 
-// F128_OASYNC 1: the object ROI of the NEXT pointwise phase is copied global -> shared memory asynchronously (cp.async, no
-// registers) while the last register DFT of the inverse FFT runs, into the 32 exchange-buffer slots the thread has just read.
-#ifndef F128_OASYNC
-#define F128_OASYNC 1
-#endif
+// The object ROI of the NEXT pointwise phase is copied global -> shared memory asynchronously (cp.async: no registers, no wait)
+// while the last register DFT of the inverse FFT runs, into the 32 exchange-buffer slots the thread has just read.  (16-byte copies
+// from a pair-packed object copy, two lanes sharing their slots, were measured 15 % slower: profiles/r02/ab_opair16.txt.)
 __device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -357,20 +327,9 @@ __device__ __forceinline__ void prefetch_roi_to_E(float2* E, const Geo& g, const
 #ifndef F128_CHK
 #define F128_CHK 4
 #endif
-#ifndef F128_CHA
-#define F128_CHA 2
-#endif
-constexpr int CHA = F128_CHA;     // chunk of the two-stream (psi, O) adjoint phase
 constexpr int CH2 = F128_CHK;     // pointwise phases load CH2 16-byte words per stream ahead of use
 
 // ---- forward ------------------------------------------------------------------------------------------------------
-struct Ptrs {                       // per-CTA base pointers into the packed object copy
-    const float4* Oplane;           // Opack + m*Z*Noy*Nox
-    size_t plane;                   // Noy*Nox
-    size_t ostr;                    // 8*Nox (float4 units between consecutive pairs j)
-    size_t roi0;                    // (cy + yl)*Nox + cx + x
-};
-
 // TILT: per-sample tilt ramps multiply the propagator; PHIS: the Fourier-domain waves are kept for the tilt / thickness gradients.
 // Compile-time switches: as runtime flags inside the unrolled pointwise loops they cost a branch + convergence barrier per element
 // (BSSY/BSYNC/BRA/UMOV were 8 % of the forward's and 14 % of the adjoint's stall samples).
@@ -384,14 +343,7 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
     int cy, cx;
     roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
     const size_t plane = (size_t)d.Noy * d.Nox;
-#if F128_OASYNC
     const float2* Oroi = a.f.O + (size_t)obj_mode(d, b, m) * d.Z * plane + (size_t)(cy + g.yl) * d.Nox + cx + g.x;   // slice 0, this thread's first row
-#else
-    const float4* Oplane = a.Opack + (size_t)obj_mode(d, b, m) * d.Z * plane;
-    l2_prefetch_roi(Oplane, cy, cx, d.Nox);
-    const size_t ostr = (size_t)8 * d.Nox;
-    const size_t roi0 = (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-#endif
     load_tables(s, a, b);
     __syncthreads();
     const size_t tile = ((size_t)b * d.P + p) * d.M + m;
@@ -412,19 +364,12 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __ldg(pr + k * 512);
     }
-#if F128_OASYNC
     if (!a.shift) prefetch_roi_to_E(s.E, g, Oroi, d.Nox);        // no inverse FFT precedes slice 0: fetch its ROI now
-#endif
     for (int z = a.shift ? -1 : 0; z < d.Z; ++z) {
         if (z >= 0) {
             float4* st = reinterpret_cast<float4*>(a.f.stash) + (tile * d.Z + z) * (TILE / 2);
-#if F128_OASYNC
             cp_async_wait_all();                                  // O_z sits in this thread's own slots of E
             const float2* __restrict__ Os = s.E + tR;
-#else
-            const float4* __restrict__ Oz = Oplane + (size_t)z * plane + roi0;
-            if (z + 1 < d.Z) l2_prefetch_roi(Oplane + (size_t)(z + 1) * plane, cy, cx, d.Nox);
-#endif
             // psi_z -> stash through a per-warp 4 KB staging block and one TMA bulk store per half (8 pairs): the stores
             // leave the LSU path, so the FFT's shared-memory traffic is not queued behind a 128 KB store burst
             float4* sw = reinterpret_cast<float4*>(s.fl) + (g.w2 * 8) * 32 + g.lane;
@@ -432,7 +377,6 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
             for (int h = 0; h < 2; ++h) {
                 if (g.lane == 0) bulk_wait_read0();
                 __syncwarp();
-#if F128_OASYNC
 #pragma unroll
                 for (int j = h * 8; j < h * 8 + 8; ++j) {
                     const int k = 2 * j;
@@ -440,21 +384,6 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
                     v[k] = cmul(v[k], Os[k * CH]);
                     v[k + 1] = cmul(v[k + 1], Os[(k + 1) * CH]);
                 }
-#else
-#pragma unroll
-                for (int j0 = 0; j0 < 8; j0 += CH2) {
-                    float4 o[CH2];
-#pragma unroll
-                    for (int i = 0; i < CH2; ++i) o[i] = __ldg(Oz + (h * 8 + j0 + i) * ostr);
-#pragma unroll
-                    for (int i = 0; i < CH2; ++i) {
-                        const int j = h * 8 + j0 + i, k = 2 * j;
-                        sw[(j0 + i) * 32] = pack2(v[k], v[k + 1]);
-                        v[k] = cmul(v[k], lo2(o[i]));
-                        v[k + 1] = cmul(v[k + 1], hi2(o[i]));
-                    }
-                }
-#endif
                 fence_async_smem();
                 __syncwarp();
                 if (g.lane == 0) {
@@ -482,14 +411,10 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
                 }
             }
         }
-#if F128_OASYNC
         {
             const float2* On = Oroi + (size_t)(z + 1) * plane;    // the ROI the pointwise phase after this inverse FFT multiplies
             fft2_F_to_R(v, s.E, s.tw, g, [&] { prefetch_roi_to_E(s.E, g, On, d.Nox); });
         }
-#else
-        fft2_F_to_R(v, s.E, s.tw, g, [] {});
-#endif
     }
     // far field: the spectrum itself is kept for the adjoint; this mode's intensity occu_m |Psi|^2 / N^2 is ADDED into dp (pre-set to
     // eps by k_dp_init) -- the mode reduction of forward.py:79 happens in L2, no partial-intensity buffer, no reduction launch
@@ -556,15 +481,14 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
 // pointwise phase after the inverse FFT.  MODE 3: scatter conj(psi_z) gphi_z into the dense gradient with vector reds (handing the
 // same data to the TMA engine as cp.reduce.async.bulk from staged shared memory was measured slower: 1.85 vs 1.67 ms per C2 batch);
 // MODE 4: object gradient not wanted.
-#if F128_OASYNC
-#ifndef F128_CHS
-#define F128_CHS 8
-#endif
-// O_z comes from this thread's own slots of E (prefetched during the inverse FFT); only the stash streams through registers
+// O_z comes from this thread's own slots of E (prefetched during the inverse FFT); only the stash streams through registers.
+// (Staging half of the stash tile in shared memory by TMA a whole FFT pair ahead -- cp.async.bulk + one mbarrier per warp -- was
+// measured 16 % SLOWER, profiles/r02/ab_tma_stash_adjoint.txt: the kernel sits at the 128-register limit and the extra live state
+// doubles the spills inside the DFTs.)
 template <int MODE>
 __device__ __forceinline__ void accum_phase_E(float2 (&v)[32], const float4* __restrict__ st, const float2* __restrict__ Os, size_t ostr,
                                               float4* __restrict__ gOz) {
-    constexpr int CS = F128_CHS;
+    constexpr int CS = 8;
 #pragma unroll
     for (int j0 = 0; j0 < 16; j0 += CS) {
         float4 ps[CS];
@@ -581,31 +505,6 @@ __device__ __forceinline__ void accum_phase_E(float2 (&v)[32], const float4* __r
             }
             v[k] = cmulc(v[k], Os[k * CH]);                        // gpsi_z = conj(O_z) gphi_z
             v[k + 1] = cmulc(v[k + 1], Os[(k + 1) * CH]);
-        }
-    }
-}
-#endif
-
-template <int MODE>
-__device__ __forceinline__ void accum_phase(float2 (&v)[32], const float4* __restrict__ st, const float4* __restrict__ Oz, size_t ostr,
-                                            float4* __restrict__ gOz) {
-#pragma unroll
-    for (int j0 = 0; j0 < 16; j0 += CH2) {
-        float4 ps[CH2], o[CH2];
-#pragma unroll
-        for (int i = 0; i < CH2; ++i) {
-            o[i] = __ldg(Oz + (j0 + i) * ostr);
-            if (MODE != 4) ps[i] = __ldg(st + (j0 + i) * 32);
-        }
-#pragma unroll
-        for (int i = 0; i < CH2; ++i) {
-            const int k = 2 * (j0 + i);
-            if (MODE != 4) {
-                const float2 c0 = cmulc(v[k], lo2(ps[i])), c1 = cmulc(v[k + 1], hi2(ps[i]));     // conj(psi) * gphi
-                red_f4(gOz + (j0 + i) * ostr, c0, c1);
-            }
-            v[k] = cmulc(v[k], lo2(o[i]));                     // gpsi_z = conj(O_z) gphi_z
-            v[k + 1] = cmulc(v[k + 1], hi2(o[i]));
         }
     }
 }
@@ -633,11 +532,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
         const int64_t n0 = a.f.idx[b];
         int cy, cx;
         roi_origin(d, a.f.crop, a.f.idx, b, cy, cx);
-#if F128_OASYNC
         const float2* Oroi = a.f.O + (size_t)obj_mode(d, b, m) * d.Z * plane + (size_t)(cy + g.yl) * d.Nox + cx + g.x;
-#else
-        const float4* Oplane = a.Opack + (size_t)obj_mode(d, b, m) * d.Z * plane;
-#endif
         __syncthreads();
         load_tables(s, a, b);
         // dL/dI in layout F, scaled 2 occu_m G~ / N^2, is gathered from global memory in the (single) start phase per mode
@@ -655,12 +550,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
             if (st_i == 0 && !want_probe_fft) break;
             // prefetch what the pointwise phase after the inverse FFT will read: slice zn = (st_i == Z ? Z-1 : st_i-1)
             const int zn = st_i == d.Z ? d.Z - 1 : st_i - 1;
-            if (st_i > 0) {
-                l2_prefetch_tile(stash_t + (size_t)zn * (TILE / 2));
-#if !F128_OASYNC
-                l2_prefetch_roi(Oplane + (size_t)zn * plane, cy, cx, d.Nox);
-#endif
-            }
+            if (st_i > 0 && a.need_obj) l2_prefetch_tile(stash_t + (size_t)zn * (TILE / 2));
             if (st_i < d.Z) fft2_R_to_F(v, s.E, s.tw, g);
             if (st_i == d.Z) {
                 const float4* __restrict__ ff = reinterpret_cast<const float4*>(a.farF) + (((size_t)b * d.M + m) * d.P + p) * (TILE / 2) + g.t;
@@ -739,18 +629,11 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
             {
                 const float4* st = stash_t + (size_t)zn * (TILE / 2) + stash_index(g.t, 0);
                 float4* gOz = a.gOpack + ((size_t)obj_mode(d, b, m) * d.Z + zn) * plane + roi0;
-#if F128_OASYNC
                 const float2* On = Oroi + (size_t)zn * plane;
                 fft2_F_to_R(v, s.E, s.tw, g, [&] { prefetch_roi_to_E(s.E, g, On, d.Nox); });     // gphi_{zn}
                 cp_async_wait_all();
                 if (a.need_obj) accum_phase_E<3>(v, st, s.E + tR, ostr, gOz);
                 else accum_phase_E<4>(v, st, s.E + tR, ostr, gOz);
-#else
-                fft2_F_to_R(v, s.E, s.tw, g, [] {});                            // gphi_{zn}
-                const float4* Oz = Oplane + (size_t)zn * plane + roi0;
-                if (a.need_obj) accum_phase<3>(v, st, Oz, ostr, gOz);
-                else accum_phase<4>(v, st, Oz, ostr, gOz);
-#endif
             }
         }
         if (!a.shift && a.need_probe) {               // unshifted probes: g_probe += gpsi_0 (natural layout)
@@ -772,7 +655,7 @@ __global__ void __launch_bounds__(FT, 1) k_backward(Args a) {
 // ---- host side --------------------------------------------------------------------------------------------------------
 struct Scratch {
     float2 *HF, *PhatF, *gPhatF, *farF;
-    float4 *Opack, *gOpack;
+    float4* gOpack;
     int* counter;           // (B) arrival counters of the fused loss
     size_t total;
 };
@@ -784,7 +667,6 @@ inline Scratch carve_scratch(const ptyb200_cfg& c, int B, unsigned char* base) {
     s.HF = (float2*)take((size_t)TILE * 8);
     s.PhatF = (float2*)take((size_t)c.P * TILE * 8);
     s.gPhatF = (float2*)take((size_t)c.P * TILE * 8);
-    s.Opack = (float4*)take(F128_OASYNC ? 0 : obj * 16);
     s.gOpack = (float4*)take(obj * 16);
     s.counter = (int*)take((size_t)B * 4);
     s.farF = (float2*)take((size_t)B * c.M * c.P * TILE * 8);
@@ -804,7 +686,7 @@ inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc,
     Args a;
     memset(&a, 0, sizeof a);
     a.f = f; a.HF = sc.HF; a.PhatF = sc.PhatF; a.farF = sc.farF; a.phisF = f.phis ? phis : nullptr;
-    a.Opack = sc.Opack; a.gOpack = sc.gOpack;
+    a.gOpack = sc.gOpack;
     a.gPhatF = sc.gPhatF; a.shift = c.shift_probes;
     return a;
 }
@@ -816,10 +698,6 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
     Args a = make_args(c, f, sc, f.phis);
     const float inv = 1.0f / (128.0f * 128.0f);
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-#if !F128_OASYNC
-    k_obj_polar_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, sc.Opack, c.Noy, c.Nox, obj);
-    F128_CK(cudaGetLastError()); ++*launches;
-#endif
     k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
     F128_CK(cudaGetLastError()); ++*launches;
     if (c.shift_probes) {

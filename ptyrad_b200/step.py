@@ -376,6 +376,55 @@ def toggle_grad_requires(model, niter: int):
         model.optimizable_tensors[name].requires_grad = start is not None and niter >= start
 
 
+def _lbfgs_iteration(batches, grad_accumulation, model, optimizer, loss_fn, arena, world, rank):
+    """The LBFGS branch of the reference's ``recon_step`` (reconstruction.py:697-735): the batches are shuffled and cut into groups
+    of `grad_accumulation`; ``optimizer.step(closure)`` runs once per group, the closure evaluating forward + loss over the whole
+    group (several forwards before one backward: every forward keeps its own workspace) and the mean loss of the group driving
+    the line search; one extra closure evaluation at the end yields the logged loss terms.  With `world` > 1 the gradients AND
+    the closure's loss are averaged over the ranks, so that every rank's line search takes the same decisions (the reference
+    leaves the loss rank-local).  Returns the five loss terms of that last evaluation as a device tensor."""
+    nb = len(batches)
+    order = np.arange(nb)
+    np.random.shuffle(order)
+    groups = np.array_split(order, max(nb // max(int(grad_accumulation), 1), 1))
+    state = {}
+
+    def closure(group):
+        if arena is not None:
+            arena.attach()
+            arena.zero()
+        else:
+            optimizer.zero_grad()
+        total = 0
+        for bi in group:
+            mine = shard_indices(batches[bi], rank, world) if world > 1 else batches[bi]
+            dp = model(mine)
+            idx = model._index_tensor(mine)
+            meas = MeasurementView(model.measurements, idx, model) if type(loss_fn) is CombinedLoss else model.get_measurements(idx)
+            loss_batch, losses = loss_fn(dp, meas, model._current_object_patches, model.omode_occu)
+            total = total + loss_batch
+        total = total / len(group)
+        total.backward()
+        if world > 1:
+            arena.allreduce(world)
+            total = total.detach().clone()
+            dist.all_reduce(total)
+            total /= world
+        state["losses"] = losses
+        return total
+
+    for group in groups:
+        optimizer.step(lambda: closure(group))
+    with torch.enable_grad():
+        closure(groups[-1])                                    # logging only, like the reference's extra evaluation
+    if arena is not None:
+        arena.zero()
+    else:
+        optimizer.zero_grad()
+    model.clear_cache()
+    return torch.stack([l.detach().reshape(()) for l in state["losses"]])
+
+
 def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint_fn, niter, verbose=True, arena: GradArena | None = None,
                world: int = 1, rank: int = 0, graphed: dict | None = None):
     """One iteration over all batches: the non-LBFGS branch of the reference's ``recon_step`` (reconstruction.py:658-781) with the
@@ -384,12 +433,10 @@ def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint
     the per-batch losses stay on the device until the end of the iteration.
 
     `graphed`: optional {batch_size: GraphedStep}; batches of a captured size are replayed as CUDA graphs.  With `world` > 1
-    every rank passes the same global batches and takes its own slice (split_batches=True semantics).  LBFGS needs the
-    closure-based loop of the reference and is not handled here.
+    every rank passes the same global batches and takes its own slice (split_batches=True semantics).  A ``torch.optim.LBFGS``
+    optimizer takes the closure loop of the reference (``_lbfgs_iteration``, reconstruction.py:697-735).
     """
     import time
-    if isinstance(optimizer, torch.optim.LBFGS):
-        raise NotImplementedError("LBFGS: use the reference's closure loop (works unchanged with this model)")
     dev = model.opt_obja.device
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
@@ -397,12 +444,16 @@ def recon_step(batches, grad_accumulation, model, optimizer, loss_fn, constraint
     if world > 1 and arena is None:
         raise RuntimeError("multi-GPU iterations need a GradArena (the gradient exchange is one all-reduce over its flat buffer)")
     toggle_grad_requires(model, niter)
-    if arena is not None:
+    if isinstance(optimizer, torch.optim.LBFGS):
+        per_batch = [_lbfgs_iteration(batches, grad_accumulation, model, optimizer, loss_fn, arena, world, rank)]
+        batches = []                                           # the mini-batch loop below has nothing left to do
+    elif arena is not None:
         arena.attach()
         arena.zero()
+        per_batch = []
     else:
         optimizer.zero_grad()
-    per_batch = []
+        per_batch = []
     nb = len(batches)
     for bi, batch in enumerate(batches):
         mine = shard_indices(batch, rank, world) if world > 1 else batch

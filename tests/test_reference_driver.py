@@ -47,7 +47,7 @@ def _inputs(cfg_name="T64", seed=51, **over):
     return cfg, iv, mp, lp
 
 
-def _drive(model_cls, loss_cls, device, iv, mp, lp, batches, niters, optimizer="Adam", grad_accumulation=1, constraints=True):
+def _drive(model_cls, loss_cls, device, iv, mp, lp, batches, niters, optimizer="Adam", grad_accumulation=1, constraints=True, step_fn=None):
     model = model_cls(iv, mp, device=device, verbose=False)
     loss_fn = loss_cls(lp, device=device)
     Z = model.opt_obja.shape[1]
@@ -62,7 +62,7 @@ def _drive(model_cls, loss_cls, device, iv, mp, lp, batches, niters, optimizer="
     hist = []
     for it in range(1, niters + 1):
         np.random.seed(100 + it)                                  # the LBFGS branch shuffles the batch order with np.random
-        bl = REF.recon_step(batches, grad_accumulation, model, opt, loss_fn, constraint_fn, it, verbose=False)
+        bl = (step_fn or REF.recon_step)(batches, grad_accumulation, model, opt, loss_fn, constraint_fn, it, verbose=False)
         hist.append({k: [float(x) for x in v] for k, v in bl.items()})
     params = {k: t.detach().cpu().numpy().astype(np.float64) for k, t in model.optimizable_tensors.items()}
     return hist, params, model
@@ -111,6 +111,27 @@ def test_reference_lbfgs_closure_drives_the_cuda_model():
             np.testing.assert_allclose(h[it][k], h_ref[it][k], rtol=2e-3, atol=1e-7, err_msg=f"iter {it + 1} {k}")
     for k in ("obja", "objp"):
         assert rel(p[k], p_ref[k]) < 5e-3, (k, rel(p[k], p_ref[k]))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_native_recon_step_lbfgs_branch_matches_the_reference_driver():
+    """ptyrad_b200.step.recon_step with a torch.optim.LBFGS optimizer (its own closure loop, mirroring reconstruction.py:697-735)
+    against the REFERENCE's recon_step on the reference model (CPU): same shuffled groups (np.random seeded alike), same losses."""
+    import ptyrad_b200
+    from ptyrad_b200.step import recon_step
+    cfg, iv, mp, lp = _inputs(seed=54)
+    mp["update_params"]["probe"]["start_iter"] = 1
+    batches = [np.arange(0, 6), np.arange(6, 12), np.arange(12, 18), np.arange(18, 25)]
+    h_ref, p_ref, _ = _drive(REF.PtychoAD, REF.CombinedLoss, "cpu", iv, mp, lp, batches, 2, optimizer="LBFGS", grad_accumulation=2, constraints=False)
+    h, p, m = _drive(ptyrad_b200.PtychoAD, ptyrad_b200.CombinedLoss, "cuda", iv, mp, lp, batches, 2, optimizer="LBFGS", grad_accumulation=2,
+                     constraints=False, step_fn=recon_step)
+    for it in range(2):
+        for k in lp:
+            np.testing.assert_allclose(h[it][k], h_ref[it][k], rtol=2e-3, atol=1e-7, err_msg=f"iter {it + 1} {k}")
+    for k in ("obja", "objp"):
+        assert rel(p[k], p_ref[k]) < 5e-3, (k, rel(p[k], p_ref[k]))
+    assert len(m.loss_iters) == 2 and len(m.iter_times) == 2
 
 
 @needs_ref
