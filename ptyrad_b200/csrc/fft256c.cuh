@@ -38,12 +38,13 @@ constexpr int SA = 264;                  // Ea: float2 stride between the 32 a-p
 constexpr int SB = 33;                   // Eb: per-warp [a2][lane] rows padded to 33
 constexpr int E_ELEMS = 32 * SA;         // 8448 float2 = 67584 B (Eb: 8 warps x 32 x 33 = the same 8448)
 
-enum { TX_L2 = 0, TX_DSMEM = 1, TX_NONE = 2, TX_BARRIER = 3 };   // the last two (no exchange / barrier only) exist for the microbenchmark
+enum { TX_L2 = 0, TX_DSMEM = 1, TX_NONE = 2, TX_BARRIER = 3, TX_L2G = 4 };   // 2, 3 (no exchange / barrier only) exist for the microbenchmark
 
 struct Geo {
-    int t, w, l, a, xl, al, rank;
+    int t, w, l, a, xl, al, rank, grp;
     __device__ __forceinline__ Geo() {
-        t = threadIdx.x; w = t >> 5; l = t & 31; a = t >> 3; xl = t & 7; al = l >> 3;
+        grp = threadIdx.x >> 8;                      // two independent 256-thread groups per CTA in the ping-pong kernels, else 0
+        t = threadIdx.x & 255; w = t >> 5; l = t & 31; a = t >> 3; xl = t & 7; al = l >> 3;
         uint32_t r;
         asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
         rank = (int)r;
@@ -62,18 +63,58 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float2 a, float2 b)
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
 
-// Transposition state of one cluster: the two alternating L2 scratch tiles (TX_L2) and which one is next
+// Transposition state of one wave: the two alternating L2 scratch tiles (TX_L2 / TX_L2G) and which one is next; TX_L2G: the
+// group's mbarrier in this CTA's shared memory (8 arrivals per phase, one from the same group of every CTA of the cluster)
 struct Tx {
-    float4* scr;        // this cluster's 2 x (TILE/2) float4
+    float4* scr;        // this wave's 2 x (TILE/2) float4
     int phase;
+    uint64_t* mbar;
+    uint32_t parity;
 };
+
+// barrier over the 256 threads that share a wave slab: the whole CTA, or one of the two groups of a ping-pong CTA (named barrier)
+template <int GROUPS> __device__ __forceinline__ void group_sync(const Geo& g) {
+    if (GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, 256;" ::"r"(1 + g.grp) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* mb, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* mb, uint32_t rank) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(smem_addr(mb), rank)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* mb, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(smem_addr(mb)), "r"(parity) : "memory");
+}
 
 // pair q of this thread goes to CTA q >> 1, slot [2 rank + (q & 1)][t]; this thread's new pair q is slot [q][t] of its own CTA.
 // TX_DSMEM: `armed` says that the split-phase "receive buffer is free" arrive has been issued (after the caller's last read of E).
-template <int TX>
+template <int TX, int GROUPS>
 __device__ __forceinline__ void transpose_T(float2 (&v)[32], Tx& tx, float2* E, const Geo& g) {
     if (TX == TX_NONE) {
-        __syncthreads();
+        group_sync<GROUPS>(g);
+    } else if (TX == TX_L2G) {
+        // like TX_L2, but the crossing is synchronised per GROUP: the group's stores are ordered by its named barrier, eight lanes
+        // release-arrive on the same group's mbarrier of every CTA of the cluster, everybody acquires on its own.  The other group of
+        // the CTA keeps computing meanwhile (barrier.cluster would stop both).
+        float4* buf = tx.scr + (size_t)(tx.phase & 1) * (TILE / 2);
+        tx.phase ^= 1;
+        float4* dst = buf + (2 * g.rank) * FT + g.t;
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            dst[((q >> 1) * 16 + (q & 1)) * FT] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+        group_sync<GROUPS>(g);
+        if (g.t < CL) mbar_arrive_remote(tx.mbar, (uint32_t)g.t);
+        mbar_wait_cluster(tx.mbar, tx.parity);
+        tx.parity ^= 1;
+        const float4* src = buf + (size_t)(g.rank * 16) * FT + g.t;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 r = __ldcg(src + q * FT);
+            v[2 * q] = make_float2(r.x, r.y);
+            v[2 * q + 1] = make_float2(r.z, r.w);
+        }
     } else if (TX == TX_BARRIER) {
         cluster_arrive();
         cluster_wait();
@@ -108,21 +149,21 @@ __device__ __forceinline__ void transpose_T(float2 (&v)[32], Tx& tx, float2* E, 
             v[2 * q] = make_float2(r.x, r.y);
             v[2 * q + 1] = make_float2(r.z, r.w);
         }
-        __syncthreads();                                    // the next exchange writes other warps' slots of the same buffer
+        group_sync<GROUPS>(g);                              // the next exchange writes other warps' slots of the same buffer
     }
 }
 
 // tw[n] = exp(-2 pi i n / 256), n < 256 (shared memory)
-template <int TX>
+template <int TX, int GROUPS = 1>
 __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const float2* tw, const Geo& g, Tx& tx) {
     Dft<32, -1>::run(v);
-    __syncthreads();                                        // earlier readers of E are done
+    group_sync<GROUPS>(g);                                  // earlier readers of E are done
     {
         float2* p = E + g.w * 32 + g.l;
 #pragma unroll
         for (int a = 0; a < 32; ++a) p[a * SA] = v[a];
     }
-    __syncthreads();
+    group_sync<GROUPS>(g);
     {
         const float2* q = E + g.a * SA + g.xl;
         float2 c[4][8];
@@ -144,7 +185,7 @@ __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const fl
             for (int b = 0; b < 8; ++b) v[4 * b + i] = c[i][b];
         }
     }
-    transpose_T<TX>(v, tx, E, g);
+    transpose_T<TX, GROUPS>(v, tx, E, g);
     Dft<32, -1>::run(v);
     float2* eb = E + g.w * (32 * SB);
     {
@@ -171,7 +212,7 @@ __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const fl
 // `pre` runs between the last shared-memory read and the last register DFT: from there on the 32 slots this thread has just read
 // (E[a*SA + w*32 + l]) belong to it alone until the next forward FFT's first barrier (the kernels park the asynchronous copy of the
 // next slice's object ROI there, like fused128.cuh).
-template <int TX, class Pre>
+template <int TX, int GROUPS = 1, class Pre>
 __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const float2* tw, const Geo& g, Tx& tx, Pre pre) {
     float2* eb = E + g.w * (32 * SB);
     __syncwarp();
@@ -195,7 +236,7 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const fl
     }
     if (TX == TX_DSMEM) cluster_arrive();                   // (aligned: every thread of the CTA arrives after its own last read)
     Dft<32, +1>::run(v);
-    transpose_T<TX>(v, tx, E, g);
+    transpose_T<TX, GROUPS>(v, tx, E, g);
     {
         float2* q = E + g.a * SA + g.xl;
 #pragma unroll
@@ -209,7 +250,7 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const fl
             for (int y = 1; y < 8; ++y) q[y * 32 + 8 * i] = cmulc(c[y], tw[y * g.a]);
         }
     }
-    __syncthreads();
+    group_sync<GROUPS>(g);
     {
         const float2* p = E + g.w * 32 + g.l;
 #pragma unroll
