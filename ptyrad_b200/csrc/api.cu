@@ -3,6 +3,7 @@
 #include "../../include/ptyrad_b200.h"
 #include "general_kernels.cuh"
 #include "fused128.cuh"
+#include "fused64.cuh"
 #include "grouping.cuh"
 
 #include <cmath>
@@ -68,7 +69,10 @@ struct Workspace {
 };
 
 bool supported_N(int N) { return N == 16 || N == 32 || N == 48 || N == 64 || N == 96 || N == 128 || N == 192 || N == 256; }
-bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && fused128::covers(c); }
+// register-resident on-chip kernels exist for N = 128 (fused128.cuh) and N = 64 (fused64.cuh)
+bool fused_covers(const ptyb200_cfg& c) { return fused128::covers(c) || fused64::covers(c); }
+bool use_fused(const ptyb200_cfg& c) { return c.path != PTYB200_PATH_GENERAL && fused_covers(c); }
+size_t fused_scratch_bytes(const ptyb200_cfg& c, int B) { return fused64::covers(c) ? fused64::scratch_bytes(c, B) : fused128::scratch_bytes(c, B); }
 
 // General path: optionally the slice sequence runs on CHUNKS of the batch (pass buffers G1/G2 sized for one chunk, so that they can
 // stay L2-resident from the kernel that writes a tile to the kernel that reads it) with the probe modes split into per-CTA groups
@@ -116,7 +120,7 @@ Workspace carve(const ptyb200_cfg& c, int B, void* base) {
     w.G1 = (float2*)take(ctiles * NN * 8);
     w.G2 = (float2*)take(ctiles * NN * 8);
     w.farT = (float2*)take(use_fused(c) ? 0 : tiles * NN * 8);
-    w.fused = take(fused128::scratch_bytes(c, B));
+    w.fused = take(use_fused(c) ? fused_scratch_bytes(c, B) : 0);
     w.total = off;
     return w;
 }
@@ -364,11 +368,14 @@ static int forward_impl(const ptyb200_cfg* c, const int64_t* idx, int32_t B, con
     Workspace w = carve(*c, B, workspace);
     FwdArgs a = make_fwd_args(*c, B, w, idx, crop_pos, probe, occu, dp_out);
     if (lf) a.lf = *lf;
-    if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
+    if (c->path == PTYB200_PATH_FUSED && !fused_covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
         if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
         tm_mark(0, 0, st);
-        if (use_fused(*c)) { if (int r = fused128::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches)) return r; }
+        if (use_fused(*c)) {
+            if (int r = fused64::covers(*c) ? fused64::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches)
+                                            : fused128::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches)) return r;
+        }
         else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
         tm_mark(0, 1, st);
     });
@@ -439,10 +446,14 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (need_t || need_dz) CK(cudaMemsetAsync(w.gprop, 0, (size_t)B * 3 * 4, st));
     if (need_t) CK(cudaMemsetAsync(g_tilts, 0, (size_t)(c->tilt_mode == 2 ? c->Ntot : 1) * 2 * 4, st));
     if (need_dz) CK(cudaMemsetAsync(g_dz, 0, 4, st));
-    if (c->path == PTYB200_PATH_FUSED && !fused128::covers(*c)) return fail_msg("fused path does not cover this configuration");
+    if (c->path == PTYB200_PATH_FUSED && !fused_covers(*c)) return fail_msg("fused path does not cover this configuration");
     DISPATCH_N(c->N, {
         tm_mark(1, 0, st);
-        if (use_fused(*c)) { if (int r = fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)) return r; }
+        if (use_fused(*c)) {
+            if (int r = fused64::covers(*c)
+                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)
+                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)) return r;
+        }
         else if (int r = backward_general<F>(*c, B, w, a, g_probe, st)) return r;
         tm_mark(1, 1, st);
         if (use_fused(*c) && a.need_probe && c->shift_probes)

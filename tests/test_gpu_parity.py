@@ -141,9 +141,9 @@ def test_depth_margins_table():
         print("MARGIN", row)
 
 
-@pytest.mark.parametrize("cfg_name", ["T128", "T128m"])
+@pytest.mark.parametrize("cfg_name", ["T128", "T128m", "T64"])
 def test_general_path_matches_auto_path(cfg_name):
-    """N = 128 has two implementations (fused on-chip and general row/column passes): both must agree with the oracle."""
+    """N = 128 and N = 64 have two implementations (fused on-chip and general row/column passes): both must agree with the oracle."""
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import _lib
     from workloads import make_inputs, CONFIGS
@@ -251,15 +251,16 @@ def test_tilt_and_thickness_gradients():
         _check(r, ref["dp"], ref["losses"], ref["grads"], label)
 
 
+@pytest.mark.parametrize("base_name", ["T128", "T64"])
 @pytest.mark.parametrize("label", ["tilt_each+dz", "tilt_global", "noshift_single_slice", "noshift_multi", "poissn_pacbed"])
-def test_fused128_variants(label):
-    """Every branch of the fused N = 128 kernels (tilt ramps, propagator gradients, unshifted probes, Z = 1, mixed object
-    modes, all data losses) against the float64 oracle."""
+def test_fused_kernel_variants(label, base_name):
+    """Every branch of the fused on-chip kernels (fused128.cuh, fused64.cuh: tilt ramps, propagator gradients, unshifted probes,
+    Z = 1, mixed object modes, all data losses) against the float64 oracle."""
     from dataclasses import replace
     from oracle.ptycho_torch import oracle_step
     from ptyrad_b200 import _lib
     from workloads import make_inputs, CONFIGS, default_loss_params
-    base = CONFIGS["T128"]
+    base = CONFIGS[base_name]
     lp_over = None
     if label == "tilt_each+dz":
         cfg = replace(base, tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4)

@@ -74,6 +74,8 @@ CONFIGS = {
     "C4s": ScanConfig("C4s", N=256, scan=96, P=12, M=1, Z=16, batch=256, lr_shifts=1e-4),
     # BASELINE configs at their OWN depth (same N, P, M, Z, loss and tilt / shift options) on a tiny scan, so the float64 CPU
     # oracle finishes in seconds: the parity cases for C2..C5 (tests/test_gpu_parity.py::test_baseline_configs_at_depth)
+    # the C2 physics on 64^2 patterns (the reference's small-pattern use: demo batch 32; here a saturating batch): fused64 vs general
+    "S64": ScanConfig("S64", N=64, scan=64, P=6, M=1, Z=8, batch=1024, lr_shifts=1e-4, dx=0.2988),
     "C2d": ScanConfig("C2d", N=128, scan=4, P=6, M=1, Z=8, batch=8, lr_shifts=1e-4),
     "C3d": ScanConfig("C3d", N=256, scan=3, P=8, M=1, Z=32, batch=4, kv=300.0, conv_angle=21.4,
                       dz=10.0, defocus=-200.0, tilt_each=True, lr_shifts=1e-4, lr_tilts=1e-4),
