@@ -166,13 +166,16 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const fl
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) Dft<4, +1>::run(a[q]);      // over vv -> s
+        float2 yt[4];                                           // loaded once: the stores below would stop the compiler from reusing them
+#pragma unroll
+        for (int y = 1; y < 4; ++y) yt[y] = tw[y * r];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {                           // over q -> yl
             float2 c[4] = {a[0][s], a[1][s], a[2][s], a[3][s]};
             Dft<4, +1>::run(c);
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
-                float2 o = y ? cmulc(c[y], tw[y * r]) : c[y];   // conj(W^{yl r})
+                float2 o = y ? cmulc(c[y], yt[y]) : c[y];       // conj(W^{yl r})
                 ch[y * 128 + j + 32 * s] = o;
             }
         }

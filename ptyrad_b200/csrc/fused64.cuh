@@ -72,6 +72,9 @@ __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[R], float2* E, const flo
     __syncthreads();
     const int j = g.e16, r = g.w2 + NW * g.rsel;       // this half-warp's chunk
     float2* ch = E + r * CH;
+    float2 xt[4];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) xt[c] = tw[j * c];
     {
         float2 a[4][4];                                // [yl][s]
 #pragma unroll
@@ -96,7 +99,7 @@ __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[R], float2* E, const flo
             Dft<4, -1>::run(a[q]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                float2 o = c ? cmul(a[q][c], tw[j * c]) : a[q][c];
+                float2 o = c ? cmul(a[q][c], xt[c]) : a[q][c];
                 ch[(q * 4 + c) * (R + 1) + j] = o;
             }
         }
@@ -126,6 +129,9 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[R], float2* E, const flo
         for (int jj = 0; jj < R; ++jj) p[jj] = v[jj];
     }
     __syncwarp();
+    float2 xt[4];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) xt[c] = tw[j * c];
     {
         float2 a[4][4];                                // [q][vv]
 #pragma unroll
@@ -133,18 +139,21 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[R], float2* E, const flo
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float2 o = ch[(q * 4 + c) * (R + 1) + j];
-                a[q][c] = c ? cmulc(o, tw[j * c]) : o;
+                a[q][c] = c ? cmulc(o, xt[c]) : o;
             }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) Dft<4, +1>::run(a[q]);      // over vv -> s
+        float2 yt[4];                                           // loaded once: the stores below would stop the compiler from reusing them
+#pragma unroll
+        for (int y = 1; y < 4; ++y) yt[y] = tw[y * r];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {                           // over q -> yl
             float2 c[4] = {a[0][s], a[1][s], a[2][s], a[3][s]};
             Dft<4, +1>::run(c);
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
-                float2 o = y ? cmulc(c[y], tw[y * r]) : c[y];   // conj(W^{yl r})
+                float2 o = y ? cmulc(c[y], yt[y]) : c[y];       // conj(W^{yl r})
                 ch[y * FN + j + R * s] = o;
             }
         }
@@ -311,20 +320,23 @@ __global__ void __launch_bounds__(FT, MINB) k_forward(Args a) {
     float4* __restrict__ ff = reinterpret_cast<float4*>(a.farF) + ft * (TILE / 2) + g.t;
 #pragma unroll
     for (int j = 0; j < R / 2; ++j) ff[j * FT] = pack2(v[2 * j], v[2 * j + 1]);
-    // layout F -> natural order through the (now idle) exchange buffer (rows padded to N + 4 floats), then whole 16-byte words of a row
+    // layout F -> natural order through the (now idle) exchange buffer (rows padded to N + 4 floats), then whole 16-byte words of a
+    // row: float at [ky][kx ^ swz(ky)], swz flips the bank bits that the lanes' different ky (q, rsel) would otherwise share
     float* Ef = reinterpret_cast<float*>(s.E);
     __syncthreads();                                   // every warp is done with its E2 reads of the last forward FFT
     {
+        const int swz = (((g.ky >> 4) & 3) << 2) ^ (((g.ky >> 3) & 1) << 4);
         float* row = Ef + g.ky * (FN + 4);
 #pragma unroll
-        for (int u = 0; u < R; ++u) row[g.kx(u)] = oc * cabs2(v[u]);
+        for (int u = 0; u < R; ++u) row[g.kx(u) ^ swz] = oc * cabs2(v[u]);
     }
     __syncthreads();
     float* dpb = a.f.dp + (size_t)b * TILE;
 #pragma unroll
     for (int j = 0; j < TILE / 4 / FT; ++j) {
         const int i4 = g.t + FT * j, ky = i4 / (FN / 4), kx0 = (i4 % (FN / 4)) << 2;
-        const float4 q = *reinterpret_cast<const float4*>(Ef + ky * (FN + 4) + kx0);
+        const int swz = (((ky >> 4) & 3) << 2) ^ (((ky >> 3) & 1) << 4);
+        const float4 q = *reinterpret_cast<const float4*>(Ef + ky * (FN + 4) + (kx0 ^ swz));
         red_f4(reinterpret_cast<float4*>(dpb + ((ky + HN) & (FN - 1)) * FN + ((kx0 + HN) & (FN - 1))), make_float2(q.x, q.y), make_float2(q.z, q.w));
     }
     if (a.f.lf.on) {
