@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch size (weak scaling)")
     ap.add_argument("--scaling", default=os.environ.get("PTYB_BENCH_SCALING", "weak"), choices=["weak", "strong"])
     ap.add_argument("--global-batch", type=int, default=2048, help="strong scaling: the fixed global batch, split over the ranks")
+    ap.add_argument("--chunk", type=int, default=-1, help="samples per internal chunk of a step (bounds the wave stash; the step still "
+                    "yields the loss / gradients of the whole batch); -1: the config's batch when the per-GPU batch is larger, 0: off")
     ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"], help="fused: one-launch Adam of this repo; torch: torch.optim.Adam (foreach)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
@@ -197,12 +199,15 @@ def main():
         B = args.global_batch // world
     else:
         B = args.batch or cfg.batch
+    chunk = args.chunk if args.chunk >= 0 else (cfg.batch if B > cfg.batch else 0)
     threads = os.cpu_count() or 1
     workload = (f"{cfg.name}: {cfg.P} probe modes, {cfg.M} object modes, {cfg.Z} slices, {cfg.N}^2 patterns, "
                 f"{cfg.scan}x{cfg.scan} scan, batch {B}/GPU, Adam, loss_{cfg.loss}+sparse")
     config = {"workload": workload, "cfg": cfg.name, "N": cfg.N, "P": cfg.P, "M": cfg.M, "Z": cfg.Z, "scan": cfg.scan,
               "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
               "l2": "per-step working set (wave stash) >> 126 MB L2, no explicit flush"}
+    if chunk and B > chunk:
+        config["chunk"] = chunk                                   # the step runs `chunk` samples at a time (one chunk's stash alive)
     simulate = cfg.scan <= 64 and cfg.N <= 128
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -299,7 +304,7 @@ def main():
         return x
 
     lib = _lib.lib()
-    eager_fn = lambda ix: recon_batch(model, loss_fn, opt, ix, arena, world)
+    eager_fn = lambda ix: recon_batch(model, loss_fn, opt, ix, arena, world, chunk=chunk)
 
     def timed(fn, steps):
         """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
@@ -330,7 +335,7 @@ def main():
     step_fn = eager_fn
     if not args.no_graph:
         # pass 2 (headline): the identical step replayed as a CUDA graph (same kernels, no per-launch host cost)
-        step_fn = GraphedStep(model, loss_fn, opt, arena, B, world=world)
+        step_fn = GraphedStep(model, loss_fn, opt, arena, B, world=world, chunk=chunk)
         for s in range(args.warmup):
             step_fn(my[s % len(my)])
         ms, last = timed(step_fn, args.steps)
@@ -368,9 +373,9 @@ def main():
             def e2e_step(j):
                 dev_meas.copy_(host_meas[j], non_blocking=True)
                 dev_idx.copy_(host_idx[j], non_blocking=True)
-                return recon_batch(model, loss_fn, opt, dev_idx, arena, world, measurements=MeasurementView(dev_meas, ar))
+                return recon_batch(model, loss_fn, opt, dev_idx, arena, world, measurements=MeasurementView(dev_meas, ar), chunk=chunk)
         else:
-            g2 = GraphedStep(model, loss_fn, opt, arena, B, world=world, stream_measurements=True)
+            g2 = GraphedStep(model, loss_fn, opt, arena, B, world=world, stream_measurements=True, chunk=chunk)
             e2e_step = lambda j: g2(host_idx[j], host_meas[j])       # H2D of indices + patterns into the graph's static inputs
         for s in range(3):
             e2e_step(s % len(host_meas))

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PTYB200_ABI_VERSION 2
+#define PTYB200_ABI_VERSION 3
 
 /* cudaStream_t without pulling in the CUDA headers */
 typedef void* ptyb200_stream;
@@ -32,7 +32,7 @@ typedef void* ptyb200_stream;
 #define PTYB200_NEED_DZ     16u
 
 /* code paths (ptyb200_cfg.path) */
-#define PTYB200_PATH_AUTO    0    /* fused on-chip kernels where available (N == 128), else general */
+#define PTYB200_PATH_AUTO    0    /* fused on-chip kernels where available (N == 128, N == 64), else general */
 #define PTYB200_PATH_GENERAL 1    /* row/column-pass kernels, any supported N */
 #define PTYB200_PATH_FUSED   2    /* fail if the fused kernels do not cover this configuration */
 
@@ -47,17 +47,29 @@ typedef struct ptyb200_cfg {
     int32_t tilt_mode;     /* 0: propagator shared by all positions; 1: one global tilt (1,2); 2: per-position (Ntot,2) */
     int32_t stash_fourier; /* 1: keep the Fourier-domain waves so tilt / thickness gradients can be formed */
     int32_t path;          /* PTYB200_PATH_* */
-    int32_t reserved[5];   /* [0] unused;
+    int32_t reserved[5];   /* [0] workspace batch capacity: the B the workspace was sized for (ptyb200_workspace_bytes) when calls
+                                  run on chunks of <= that many samples that share one workspace (chunked steps), 0 = the call's B;
                               [1] bit 0: PATCH MODE -- obja/objp (and their gradients) are per-sample ROI stacks (B,M,Z,N,N),
                                   e.g. pre-blurred patches (models.py:275-284); needs Noy == Nox == N, crop_pos is ignored;
                               [2] general path: samples per chunk (the slice sequence runs chunk by chunk so that the pass buffers
                                   stay L2-resident), 0 = heuristic;  [3] general path: probe modes per CTA, 0 = heuristic.
-                                  [2] and [3] change the workspace size: use the same cfg for ptyb200_workspace_bytes */
+                                  [2] and [3] change the workspace size: use the same cfg for ptyb200_workspace_bytes;
+                              [4] PTYB200_ACC_* flags of a chunked step (below), 0 = a whole batch per call */
     float   dx;            /* real-space pixel size (propagator k-grid, models.py:164-171) */
     float   lambd;         /* wavelength (Kz, models.py:222-223) */
     float   eps;           /* added to the intensities after the mode sum (forward.py:79); reference: 1e-10 */
     float   reserved_f;
 } ptyb200_cfg;
+
+/* Chunked steps: a batch larger than the workspace allows is processed chunk by chunk (forward, unscaled loss gradient, adjoint per
+ * chunk; only one chunk's wave stash is alive), the way SURVEY 8e asks ("memory must not grow with B").  The data losses are not
+ * additive over chunks -- loss_single = sqrt(mean((I^p - M^p)^2)) / mean(M^p) over the WHOLE batch (losses.py:42-47) -- but dL/dI
+ * factors into (a scalar of the batch sums) x (a per-pixel term), and the adjoint is linear in dL/dI: every chunk runs its adjoint on
+ * the per-pixel term (ptyb200_loss_grad with stats = upstream = NULL) into shared accumulators, and ptyb200_backward_finish applies
+ * the scalar (ptyb200_loss_scale, from the completed sums) when it forms the gradients.  cfg.reserved[4] carries: */
+#define PTYB200_ACC_KEEP_STATS 1   /* ptyb200_forward_loss: add to the loss sums of the earlier chunks (no zeroing, no final scalars) */
+#define PTYB200_ACC_KEEP_GRADS 2   /* ptyb200_backward: add to the gradient accumulators of the earlier chunks (no zeroing) */
+#define PTYB200_ACC_NO_FINISH  4   /* ptyb200_backward: leave the accumulators raw; ptyb200_backward_finish completes them */
 
 typedef struct ptyb200_loss_cfg {
     /* CombinedLoss terms computed natively (losses.py:36-104); state 0 => term is 0 */
@@ -194,6 +206,20 @@ int ptyb200_blur_axis(const float* in, float* out, int64_t outer, int32_t L, int
                       int32_t pad_mode, ptyb200_stream s);
 int ptyb200_object_constraints(const ptyb200_obj_constraints* oc, float* obja, float* objp, int64_t n, float* scratch,
                                ptyb200_stream s);
+
+/* Completion of a chunked step (see PTYB200_ACC_*): object polar backward, probe-spectrum inverse FFT and the batch-level `scale`
+ * (device float, e.g. from ptyb200_loss_scale; NULL = 1) applied to every requested gradient.  Same buffers / need_mask as the
+ * ptyb200_backward calls whose accumulators (in `workspace`) it completes; tilt / thickness gradients are not available chunked. */
+int ptyb200_backward_finish(const ptyb200_cfg* cfg, int32_t B, const float* obja, const float* objp, void* workspace, float* g_obja,
+                            float* g_objp, float* g_probe, float* g_shifts, uint32_t need_mask, const float* scale, ptyb200_stream s);
+/* losses3 = the data-loss scalars from the sums in `stats` accumulated over B_total samples (what ptyb200_forward_loss does at the
+ * end of an unchunked call). */
+int ptyb200_loss_finalize(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, int32_t B_total, const double* stats, const float* pac,
+                          float* losses3, ptyb200_stream s);
+/* scale_out[0] = upstream * (the factor of dL/dI that depends on the sums over all B_total samples); exactly one of loss_single /
+ * loss_poissn must be active and loss_pacbed off (its gradient is not separable per pattern). */
+int ptyb200_loss_scale(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, int32_t B_total, const double* stats, const float* upstream3,
+                       float* scale_out, ptyb200_stream s);
 
 /* 'sparse' grouping of scan positions (make_batches, reconstruction.py:540-587): the greedy assignment loop.  pos_ordered = (n,2)
  * float64 positions, the G group seeds first (group g's seed in row g: the point closest to the centroid of compact group g,

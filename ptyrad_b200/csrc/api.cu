@@ -100,7 +100,10 @@ GenPlan gen_plan(const ptyb200_cfg& c, int B) {
 }
 constexpr int kProbeCtas = 4 * 148 * 4;   // probe pass: ~4 waves of 148 SMs x 4 resident CTAs, so that no CTA loops over more than B/7 samples
 
-Workspace carve(const ptyb200_cfg& c, int B, void* base) {
+// B = samples of this call; the layout follows the batch CAPACITY the workspace was sized for (cfg.reserved[0], chunked steps), so
+// that the gradient accumulators keep their place when the last chunk is smaller
+Workspace carve(const ptyb200_cfg& c, int B_call, void* base) {
+    const int B = c.reserved[0] > B_call ? c.reserved[0] : B_call;
     Workspace w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return reinterpret_cast<unsigned char*>(base) + o; };
@@ -121,6 +124,7 @@ Workspace carve(const ptyb200_cfg& c, int B, void* base) {
     w.G2 = (float2*)take(ctiles * NN * 8);
     w.farT = (float2*)take(use_fused(c) ? 0 : tiles * NN * 8);
     w.fused = take(use_fused(c) ? fused_scratch_bytes(c, B) : 0);
+    (void)B_call;
     w.total = off;
     return w;
 }
@@ -229,7 +233,7 @@ template <class F> int forward_general(const ptyb200_cfg& c, int B, const Worksp
     return 0;
 }
 
-template <class F> int backward_general(const ptyb200_cfg& c, int B, const Workspace& w, BwdArgs a, float* g_probe, cudaStream_t st) {
+template <class F> int backward_general(const ptyb200_cfg& c, int B, const Workspace& w, BwdArgs a, float* g_probe, cudaStream_t st, int acc = 0) {
     const int nb = c.N / ROWS;
     const bool want_p = a.need_probe || a.need_shift;
     const GenPlan gp = gen_plan(c, B);
@@ -258,13 +262,13 @@ template <class F> int backward_general(const ptyb200_cfg& c, int B, const Works
                 nsub = (nbc + bsub - 1) / bsub;
                 LAUNCH((k_bwd_probe<F>), dim3(nb, c.P, nsub), st, a, nbc, bsub);
             } else if (a.need_probe) {
-                k_bwd_probe_noshift<<<dim3((c.N * c.N + 255) / 256, c.P), 256, 0, st>>>(a.f.d, nbc, b0 == 0 ? 1 : 0, w.G1, (float2*)g_probe);
+                k_bwd_probe_noshift<<<dim3((c.N * c.N + 255) / 256, c.P), 256, 0, st>>>(a.f.d, nbc, (b0 == 0 && !(acc & PTYB200_ACC_KEEP_GRADS)) ? 1 : 0, w.G1, (float2*)g_probe);
                 CKL();
             }
         }
     }
     a.f.d.b0 = 0;
-    if (want_p && c.shift_probes && a.need_probe)
+    if (want_p && c.shift_probes && a.need_probe && !(acc & PTYB200_ACC_NO_FINISH))
         if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c.P, +1, st)) return r;
     return 0;
 }
@@ -403,8 +407,10 @@ int ptyb200_forward_loss(const ptyb200_cfg* c, const int64_t* idx, int32_t B, co
     lf.k = make_lossk(*lc);
     if (const char* e = make_meas_view(*c, mcfg, meas_all, meas_padded, dp_out, dp_out, &lf.mv)) return fail_msg(e);
     lf.stats = stats; lf.pac = pac; lf.rows = meas_rows ? meas_rows : idx;
-    CK(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
-    if (lf.k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
+    if (!(c->reserved[4] & PTYB200_ACC_KEEP_STATS)) {
+        CK(cudaMemsetAsync(stats, 0, 8 * sizeof(double), st));
+        if (lf.k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
+    }
     if (int r = forward_impl(c, idx, B, obja, objp, crop_pos, probe, shifts, Hbase, tilts, dz, occu, dp_out, workspace, &lf, s)) return r;
     k_loss_final<<<1, 256, 0, st>>>(lf.k, B, c->N, stats, pac, losses3);
     CKL();
@@ -440,9 +446,16 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (misaligned(g_obja, 16) || misaligned(g_objp, 16) || misaligned(g_probe, 16) || misaligned(g_shifts, 8) || misaligned(g_tilts, 8))
         return fail_msg("gradient buffers must be 16-byte aligned (g_shifts / g_tilts: 8-byte)");
     const size_t obj = (size_t)((c->reserved[1] & 1) ? B : 1) * c->M * c->Z * c->Noy * c->Nox;
-    if (a.need_obj && !use_fused(*c)) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
-    if (a.need_probe && c->shift_probes) CK(cudaMemsetAsync(w.gPhatT, 0, (size_t)c->P * c->N * c->N * 8, st));
-    if (need_mask & PTYB200_NEED_SHIFTS) CK(cudaMemsetAsync(g_shifts, 0, (size_t)c->Ntot * 2 * 4, st));
+    const int acc = c->reserved[4];
+    if (acc & (PTYB200_ACC_KEEP_GRADS | PTYB200_ACC_NO_FINISH)) {
+        if (a.need_prop) return fail_msg("chunked steps do not cover tilt / thickness gradients");
+        if (c->reserved[1] & 1) return fail_msg("chunked steps do not cover patch mode");
+    }
+    if (!(acc & PTYB200_ACC_KEEP_GRADS)) {
+        if (a.need_obj && !use_fused(*c)) CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
+        if (a.need_probe && c->shift_probes) CK(cudaMemsetAsync(w.gPhatT, 0, (size_t)c->P * c->N * c->N * 8, st));
+        if (need_mask & PTYB200_NEED_SHIFTS) CK(cudaMemsetAsync(g_shifts, 0, (size_t)c->Ntot * 2 * 4, st));
+    }
     if (need_t || need_dz) CK(cudaMemsetAsync(w.gprop, 0, (size_t)B * 3 * 4, st));
     if (need_t) CK(cudaMemsetAsync(g_tilts, 0, (size_t)(c->tilt_mode == 2 ? c->Ntot : 1) * 2 * 4, st));
     if (need_dz) CK(cudaMemsetAsync(g_dz, 0, 4, st));
@@ -451,16 +464,16 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
         tm_mark(1, 0, st);
         if (use_fused(*c)) {
             if (int r = fused64::covers(*c)
-                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)
-                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches)) return r;
+                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, acc)
+                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, acc)) return r;
         }
-        else if (int r = backward_general<F>(*c, B, w, a, g_probe, st)) return r;
+        else if (int r = backward_general<F>(*c, B, w, a, g_probe, st, acc)) return r;
         tm_mark(1, 1, st);
-        if (use_fused(*c) && a.need_probe && c->shift_probes)
+        if (use_fused(*c) && a.need_probe && c->shift_probes && !(acc & PTYB200_ACC_NO_FINISH))
             if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, st)) return r;
     });
-    if (a.need_obj && !use_fused(*c)) {
-        k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj);
+    if (a.need_obj && !use_fused(*c) && !(acc & PTYB200_ACC_NO_FINISH)) {
+        k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj, nullptr);
         CKL();
     }
     if (a.need_prop) {
@@ -504,9 +517,16 @@ int ptyb200_loss_forward(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const
 int ptyb200_loss_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const float* dp, const float* meas_all,
                       const int64_t* idx, int32_t B, const double* stats, const float* pac, const float* upstream3,
                       float* G_out, const ptyb200_meas_cfg* mcfg, const float* meas_padded, ptyb200_stream s) {
-    if (!c || !lc || !dp || !meas_all || !idx || !stats || !upstream3 || !G_out) return fail_msg("NULL argument");
+    if (!c || !lc || !dp || !meas_all || !idx || !G_out) return fail_msg("NULL argument");
     cudaStream_t st = (cudaStream_t)s;
     LossK k = make_lossk(*lc);
+    if (!stats || !upstream3) {
+        // unscaled form for chunked steps (stats = upstream3 = NULL): the per-pixel factor of dL/dI only
+        if (stats || upstream3) return fail_msg("loss_grad: stats and upstream3 must both be given, or both NULL (unscaled form)");
+        if (k.b_on || (k.s_on != 0) == (k.p_on != 0))
+            return fail_msg("the unscaled loss gradient (chunked steps) needs exactly one of loss_single / loss_poissn and no loss_pacbed");
+        upstream3 = nullptr;
+    }
     MeasView mv;
     if (const char* e = make_meas_view(*c, mcfg, meas_all, meas_padded, dp, G_out, &mv)) return fail_msg(e);
     unsigned chunks = (unsigned)((c->N * c->N + 256 * 8 - 1) / (256 * 8));
@@ -566,6 +586,62 @@ int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t plan
     } else {
         k_blur5<1, true><<<grid, 256, 0, st>>>(b, in, tmp, total, H, W); CKL();
         k_blur5<0, true><<<grid, 256, 0, st>>>(b, tmp, out, total, H, W); CKL();
+    }
+    return 0;
+}
+
+int ptyb200_loss_finalize(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, int32_t B_total, const double* stats, const float* pac,
+                          float* losses3, ptyb200_stream s) {
+    if (!c || !lc || !stats || !losses3 || B_total < 1) return fail_msg("NULL argument");
+    LossK k = make_lossk(*lc);
+    k_loss_final<<<1, 256, 0, (cudaStream_t)s>>>(k, B_total, c->N, const_cast<double*>(stats), const_cast<float*>(pac), losses3);
+    CKL();
+    return 0;
+}
+
+int ptyb200_loss_scale(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, int32_t B_total, const double* stats, const float* upstream3,
+                       float* scale_out, ptyb200_stream s) {
+    if (!c || !lc || !stats || !upstream3 || !scale_out || B_total < 1) return fail_msg("NULL argument");
+    LossK k = make_lossk(*lc);
+    if (k.b_on || (k.s_on != 0) == (k.p_on != 0))
+        return fail_msg("loss_scale needs exactly one of loss_single / loss_poissn and no loss_pacbed");
+    k_loss_scale<<<1, 32, 0, (cudaStream_t)s>>>(k, (double)B_total * c->N * c->N, stats, upstream3, scale_out);
+    CKL();
+    return 0;
+}
+
+int ptyb200_backward_finish(const ptyb200_cfg* c, int32_t B, const float* obja, const float* objp, void* workspace, float* g_obja,
+                            float* g_objp, float* g_probe, float* g_shifts, uint32_t need_mask, const float* scale, ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!obja || !objp || !workspace) return fail_msg("NULL argument");
+    if (c->reserved[1] & 1) return fail_msg("chunked steps do not cover patch mode");
+    if (need_mask & (PTYB200_NEED_TILTS | PTYB200_NEED_DZ)) return fail_msg("chunked steps do not cover tilt / thickness gradients");
+    cudaStream_t st = (cudaStream_t)s;
+    Workspace w = carve(*c, B, workspace);
+    const bool need_obj = (need_mask & PTYB200_NEED_OBJ) != 0, need_probe = (need_mask & PTYB200_NEED_PROBE) != 0;
+    const bool need_shift = (need_mask & PTYB200_NEED_SHIFTS) && c->shift_probes;
+    if (need_obj && (!g_obja || !g_objp)) return fail_msg("g_obja/g_objp is NULL");
+    if (need_probe && !g_probe) return fail_msg("g_probe is NULL");
+    const size_t obj = (size_t)c->M * c->Z * c->Noy * c->Nox, pn = (size_t)c->P * c->N * c->N * 2;
+    DISPATCH_N(c->N, {
+        if (use_fused(*c)) {
+            BwdArgs a;
+            memset(&a, 0, sizeof a);
+            a.f = make_fwd_args(*c, B, w, nullptr, nullptr, nullptr, nullptr, nullptr);
+            a.need_obj = need_obj; a.need_probe = need_probe;
+            if (int r = fused64::covers(*c)
+                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, 0, scale, true)
+                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, 0, scale, true)) return r;
+        } else if (need_obj) {
+            k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj, scale);
+            CKL();
+        }
+        if (need_probe && c->shift_probes)
+            if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, st)) return r;
+    });
+    if (scale) {
+        if (need_probe) { k_scale<<<(unsigned)((pn + 255) / 256), 256, 0, st>>>(g_probe, pn, scale); CKL(); }
+        if (need_shift && g_shifts) { const size_t n = (size_t)c->Ntot * 2; k_scale<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g_shifts, n, scale); CKL(); }
     }
     return 0;
 }

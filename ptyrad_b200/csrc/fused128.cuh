@@ -265,17 +265,18 @@ __global__ void k_dp_init(float4* __restrict__ dp4, size_t n4, float eps, int* _
 
 // g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O)) with gO[Y][X] = gOpack[Y][X].xy + gOpack[Y-4][X].zw
 __global__ void k_obj_finish_pack(const float4* __restrict__ gOp, const float* __restrict__ a, const float* __restrict__ ph,
-                                  float* __restrict__ ga, float* __restrict__ gp, int Noy, int Nox, size_t n) {
+                                  float* __restrict__ ga, float* __restrict__ gp, int Noy, int Nox, size_t n, const float* __restrict__ scale) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float sc = scale ? scale[0] : 1.0f;           // batch-level factor of dL/dI (chunked steps), else 1
     const int Y = int((i / Nox) % Noy);
     const float4 lo = gOp[i];
     float2 g = make_float2(lo.x, lo.y);
     if (Y >= 4) { const float4 up = gOp[i - (size_t)4 * Nox]; g.x += up.z; g.y += up.w; }
     float s, c;
     sincosf(ph[i], &s, &c);
-    ga[i] = g.x * c + g.y * s;
-    gp[i] = a[i] * (g.y * c - g.x * s);
+    ga[i] = sc * (g.x * c + g.y * s);
+    gp[i] = sc * a[i] * (g.y * c - g.x * s);
 }
 
 // ---- memory helpers -----------------------------------------------------------------------------------------------
@@ -730,7 +731,10 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
 // adjoint incl. the polar backward of the object gradient; the caller zeroes gPhatT / gprop / gshift and runs the
 // probe-spectrum inverse FFT
 inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float* obja, const float* objp, float* g_obja, float* g_objp,
-                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches) {
+                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches,
+                    int acc_flags = 0, const float* scale = nullptr, bool finish_only = false) {
+    // acc_flags (PTYB200_ACC_*): KEEP_GRADS = the accumulators already hold earlier chunks of the batch; NO_FINISH = leave them raw.
+    // finish_only: no adjoint, only the completion of the accumulators (with the batch-level `scale` of an unscaled loss gradient).
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, bw.f, sc, bw.f.phis);
     a.G = bw.G; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
@@ -738,10 +742,12 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
     a.units = B * c.M * c.P;
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-    if (a.need_obj) F128_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
-    if (a.need_probe) {
-        if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
-        else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
+    if (!finish_only && !(acc_flags & PTYB200_ACC_KEEP_GRADS)) {
+        if (a.need_obj) F128_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
+        if (a.need_probe) {
+            if (c.shift_probes) F128_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
+            else F128_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
+        }
     }
     const bool tilt = bw.f.tvec != nullptr, prop = a.need_prop != 0;
 #define F128_LAUNCH_BWD(T, PR)                                                                                                     \
@@ -749,16 +755,19 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
         F128_CK(cudaFuncSetAttribute(k_backward<T, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));        \
         k_backward<T, PR><<<a.units, FT, SMEM_BYTES_BWD, st>>>(a);                                                                 \
     } while (0)
-    if (tilt) { if (prop) F128_LAUNCH_BWD(true, true); else F128_LAUNCH_BWD(true, false); }
-    else      { if (prop) F128_LAUNCH_BWD(false, true); else F128_LAUNCH_BWD(false, false); }
+    if (!finish_only) {
+        if (tilt) { if (prop) F128_LAUNCH_BWD(true, true); else F128_LAUNCH_BWD(true, false); }
+        else      { if (prop) F128_LAUNCH_BWD(false, true); else F128_LAUNCH_BWD(false, false); }
+        F128_CK(cudaGetLastError()); ++*launches;
+    }
 #undef F128_LAUNCH_BWD
-    F128_CK(cudaGetLastError()); ++*launches;
+    if (acc_flags & PTYB200_ACC_NO_FINISH) return 0;
     if (a.need_probe && c.shift_probes) {
         k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
         F128_CK(cudaGetLastError()); ++*launches;
     }
     if (a.need_obj) {
-        k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj);
+        k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj, scale);
         F128_CK(cudaGetLastError()); ++*launches;
     }
     return 0;

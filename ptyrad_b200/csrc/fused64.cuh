@@ -584,7 +584,10 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
 }
 
 inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float* obja, const float* objp, float* g_obja, float* g_objp,
-                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches) {
+                    unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches,
+                    int acc_flags = 0, const float* scale = nullptr, bool finish_only = false) {
+    // acc_flags (PTYB200_ACC_*): KEEP_GRADS = the accumulators already hold earlier chunks of the batch; NO_FINISH = leave them raw.
+    // finish_only: no adjoint, only the completion of the accumulators (with the batch-level `scale` of an unscaled loss gradient).
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = fused64::make_args(c, bw.f, sc, bw.f.phis);
     a.G = bw.G; a.gprop = bw.gprop; a.gshift = bw.gshift; a.gprobe = g_probe;
@@ -592,10 +595,12 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
     a.need_obj = bw.need_obj; a.need_probe = bw.need_probe; a.need_shift = bw.need_shift; a.need_prop = bw.need_prop;
     a.units = B * c.M * c.P;
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-    if (a.need_obj) F64_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
-    if (a.need_probe) {
-        if (c.shift_probes) F64_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
-        else F64_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
+    if (!finish_only && !(acc_flags & PTYB200_ACC_KEEP_GRADS)) {
+        if (a.need_obj) F64_CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
+        if (a.need_probe) {
+            if (c.shift_probes) F64_CK(cudaMemsetAsync(sc.gPhatF, 0, (size_t)c.P * TILE * 8, st));
+            else F64_CK(cudaMemsetAsync(g_probe, 0, (size_t)c.P * TILE * 8, st));
+        }
     }
     const bool tilt = bw.f.tvec != nullptr, prop = a.need_prop != 0;
 #define F64_LAUNCH_BWD(T, PR)                                                                                                      \
@@ -603,16 +608,19 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
         F64_CK(cudaFuncSetAttribute(fused64::k_backward<T, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_BWD));         \
         fused64::k_backward<T, PR><<<a.units, FT, SMEM_BYTES_BWD, st>>>(a);                                                                 \
     } while (0)
-    if (tilt) { if (prop) F64_LAUNCH_BWD(true, true); else F64_LAUNCH_BWD(true, false); }
-    else      { if (prop) F64_LAUNCH_BWD(false, true); else F64_LAUNCH_BWD(false, false); }
+    if (!finish_only) {
+        if (tilt) { if (prop) F64_LAUNCH_BWD(true, true); else F64_LAUNCH_BWD(true, false); }
+        else      { if (prop) F64_LAUNCH_BWD(false, true); else F64_LAUNCH_BWD(false, false); }
+        F64_CK(cudaGetLastError()); ++*launches;
+    }
 #undef F64_LAUNCH_BWD
-    F64_CK(cudaGetLastError()); ++*launches;
+    if (acc_flags & PTYB200_ACC_NO_FINISH) return 0;
     if (a.need_probe && c.shift_probes) {
         k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
         F64_CK(cudaGetLastError()); ++*launches;
     }
     if (a.need_obj) {
-        fused128::k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj);
+        fused128::k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj, scale);
         F64_CK(cudaGetLastError()); ++*launches;
     }
     return 0;

@@ -945,15 +945,21 @@ __global__ void k_bwd_probe_noshift(Dims d, int nb, int first, const float2* __r
 }
 
 // g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O))   (polar backward, forward.py:53)
+// `scale` (device scalar or null): the batch-level factor of dL/dI when the adjoint ran on the unscaled loss gradient (chunked steps)
 __global__ void k_obj_finish(const float2* __restrict__ gO, const float* __restrict__ a, const float* __restrict__ ph,
-                             float* __restrict__ ga, float* __restrict__ gp, size_t n) {
+                             float* __restrict__ ga, float* __restrict__ gp, size_t n, const float* __restrict__ scale) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float sc = scale ? scale[0] : 1.0f;
     float s, c;
     sincosf(ph[i], &s, &c);
     float2 g = gO[i];
-    ga[i] = g.x * c + g.y * s;
-    gp[i] = a[i] * (g.y * c - g.x * s);
+    ga[i] = sc * (g.x * c + g.y * s);
+    gp[i] = sc * a[i] * (g.y * c - g.x * s);
+}
+__global__ void k_scale(float* __restrict__ x, size_t n, const float* __restrict__ scale) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= scale[0];
 }
 
 // tilt / thickness chain rule from the per-sample sums (models.py:336-356).  single block.
@@ -1053,9 +1059,16 @@ __global__ void k_loss_grad(LossK k, const float* __restrict__ dp, MeasView mv, 
     const int NN = N * N, b = blockIdx.y;
     const double nel = (double)B * NN;
     float cs = 0.f, cp = 0.f, cb = 0.f;
-    if (k.s_on) cs = float(up[0] * k.s_w * k.s_p / (nel * sqrt(stats[0] / nel) * (stats[1] / nel)));
-    if (k.p_on) cp = float(-up[1] * k.p_w * k.p_p / (nel * (stats[3] / nel)));
-    if (k.b_on) cb = float(up[2] * k.b_w * k.b_p / (nel * sqrt(stats[5] / NN) * (stats[4] / nel)));
+    if (!up) {
+        // unscaled form (chunked steps): the factor that depends on the sums over the WHOLE batch is left out and applied to the
+        // finished gradients instead (k_loss_scale); the adjoint is linear in G.  One data term only (checked by the caller).
+        if (k.s_on) cs = k.s_w * k.s_p;
+        if (k.p_on) cp = -k.p_w * k.p_p;
+    } else {
+        if (k.s_on) cs = float(up[0] * k.s_w * k.s_p / (nel * sqrt(stats[0] / nel) * (stats[1] / nel)));
+        if (k.p_on) cp = float(-up[1] * k.p_w * k.p_p / (nel * (stats[3] / nel)));
+        if (k.b_on) cb = float(up[2] * k.b_w * k.b_p / (nel * sqrt(stats[5] / NN) * (stats[4] / nel)));
+    }
     const float* __restrict__ I_ = dp + (size_t)b * NN;
     const float* __restrict__ M_ = mv.meas + (size_t)idx[b] * mv.Hs * mv.Ws;
     float* __restrict__ G_ = G + (size_t)b * NN;
@@ -1083,6 +1096,13 @@ __global__ void k_loss_grad(LossK k, const float* __restrict__ dp, MeasView mv, 
         for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < NN; pix += gridDim.x * blockDim.x)
             G_[pix] = grad(pix, I_[pix], need_m ? meas_at(mv, M_, pix / N, pix % N) : 0.f);
     }
+}
+
+// the batch-level factor that k_loss_grad's unscaled form leaves out: nel = elements of the WHOLE batch
+__global__ void k_loss_scale(LossK k, double nel, const double* __restrict__ stats, const float* __restrict__ up, float* __restrict__ scale) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (k.s_on) scale[0] = float(up[0] / (nel * sqrt(stats[0] / nel) * (stats[1] / nel)));
+    else scale[0] = float(up[1] / (nel * (stats[3] / nel)));
 }
 
 // sparse: sum over the batch ROIs of |phi|^n == sum over object pixels of cover[px] * |phi[px]|^n, where cover counts

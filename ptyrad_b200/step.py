@@ -90,6 +90,93 @@ def direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, meas
     return True
 
 
+def chunked_step_eligible(model, loss_fn) -> bool:
+    """A chunked step needs dL/dI = (scalar of the batch sums) x (per-pixel term): exactly one of loss_single / loss_poissn, no
+    loss_pacbed, no detector blur; tilt / thickness gradients are not covered."""
+    lp = loss_fn.loss_params
+    one = bool(lp["loss_single"]["state"]) != bool(lp["loss_poissn"]["state"])
+    prop = (model.opt_obj_tilts.requires_grad and model.tilt_obj) or (model.opt_slice_thickness.requires_grad and model.change_thickness)
+    return one and not lp["loss_pacbed"]["state"] and not model.detector_blur_std and not prop
+
+
+def _direct_grads_chunked(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, chunk: int):
+    """`_direct_grads` for a batch that is processed `chunk` samples at a time so that only one chunk's wave stash is alive
+    (memory must not grow with the per-GPU batch; the strong-scaling runs put 2 048 patterns of C4 on one GPU, whose
+    stash alone would be 206 GB).  The result is the gradient of the loss of the WHOLE batch, not a sum of per-chunk losses: every
+    chunk adds its loss sums and runs its adjoint on the unscaled loss gradient into shared accumulators; the batch-level factor is
+    applied once, when the accumulators are turned into gradients (include/ptyrad_b200.h, PTYB200_ACC_*)."""
+    if not chunked_step_eligible(model, loss_fn):
+        raise ValueError("a chunked step needs exactly one of loss_single / loss_poissn, no loss_pacbed, no detector blur and no "
+                         "tilt / thickness gradients")
+    lib = _lib.lib()
+    st = engine._stream()
+    dev = model.opt_obja.device
+    B = idx.numel()
+    obja, objp, probe = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous(), model.opt_probe.data.contiguous()
+    dz, shifts = model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
+    tilts = model.opt_obj_tilts.data.contiguous()
+    n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
+    n_probe = model.opt_probe.requires_grad
+    n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
+    base = model._cfg(stash_fourier=False)
+    base.reserved[0] = chunk                                   # every call lays the workspace out for `chunk` samples
+    Hbase = engine.propagator(base, dz) if model.change_thickness else model.H
+    ws_bytes = lib.ptyb200_workspace_bytes(C.byref(base), chunk)
+    if ws_bytes == 0:
+        _lib.check(1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    dp = torch.empty((chunk, base.N, base.N), dtype=torch.float32, device=dev)
+    G = torch.empty_like(dp)
+    tl = tilts if base.tilt_mode else None
+    sh = shifts if base.shift_probes else None
+    lcfg = loss_fn.lcfg()
+    losses = torch.zeros(5, dtype=torch.float32, device=dev)
+    stats = torch.empty(8, dtype=torch.float64, device=dev)
+    need = (_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0)
+
+    def out(p, wanted):
+        if not wanted:
+            return None
+        return p.grad if p.requires_grad else torch.empty_like(p.data)
+
+    g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
+    g_probe, g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
+    for i, lo in enumerate(range(0, B, chunk)):
+        hi = min(B, lo + chunk)
+        n = hi - lo
+        cfg = type(base).from_buffer_copy(base)
+        cfg.reserved[4] = _lib.ACC_NO_FINISH | ((_lib.ACC_KEEP_STATS | _lib.ACC_KEEP_GRADS) if i else 0)
+        ci, cr = idx[lo:hi], meas.idx[lo:hi]
+        _lib.check(lib.ptyb200_forward_loss(C.byref(cfg), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
+                                            ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws), C.byref(lcfg), ptr(meas.all), ptr(cr),
+                                            engine.mref(meas.mcfg), ptr(meas.padded), ptr(losses), ptr(stats), None, st))
+        if need:
+            _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(cr), n, None, None, None, ptr(G),
+                                             engine.mref(meas.mcfg), ptr(meas.padded), st))
+            _lib.check(lib.ptyb200_backward(
+                C.byref(cfg), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
+                ptr(model.omode_occu), ptr(G), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), None, None, need, st))
+    _lib.check(lib.ptyb200_loss_finalize(C.byref(base), C.byref(lcfg), B, ptr(stats), None, ptr(losses), st))
+    sparse = bool(lcfg.sparse_state)
+    if sparse:
+        Ssum = torch.empty(base.M, dtype=torch.float64, device=dev)
+        cover = torch.empty(base.Noy * base.Nox, dtype=torch.int32, device=dev)
+        _lib.check(lib.ptyb200_sparse_forward(C.byref(base), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                              C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), st))
+    if need:
+        ones = getattr(model, "_ones3", None)
+        if ones is None or ones.device != dev:
+            ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
+        scale = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.check(lib.ptyb200_loss_scale(C.byref(base), C.byref(lcfg), B, ptr(stats), ptr(ones), ptr(scale), st))
+        _lib.check(lib.ptyb200_backward_finish(C.byref(base), chunk, ptr(obja), ptr(objp), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(g_probe),
+                                               ptr(g_shifts), need, ptr(scale), st))
+        if sparse and model.opt_objp.requires_grad:
+            _lib.check(lib.ptyb200_sparse_grad(C.byref(base), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                               ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), st))
+    return losses
+
+
 def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
     """Forward, loss, loss gradient and adjoint through the C ABI with the gradient tensors of the arena as the kernels' output
     buffers -- what ``model(idx)`` -> ``loss_fn`` -> ``backward()`` computes (engine.MultisliceFunction / DataLossFunction /
@@ -173,12 +260,15 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
 
 def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = None, world: int = 1,
                 grad_accumulation: int = 1, do_step: bool = True, measurements=None, direct: bool | None = None,
-                first_of_group: bool = True):
+                first_of_group: bool = True, chunk: int = 0):
     """One batch: (zero grads), forward, loss, backward, (all-reduce), optimizer step.  Returns the 5 loss terms as a device
     tensor (no host sync).  `direct` (default: whenever eligible) takes the autograd-free route of `_direct_grads`.
 
     Gradient accumulation (reconstruction.py:750-760): pass `grad_accumulation` = group size, `first_of_group` = True only for the
-    first batch of a group (gradients are zeroed there and nowhere else) and `do_step` = True only for the last one."""
+    first batch of a group (gradients are zeroed there and nowhere else) and `do_step` = True only for the last one.
+
+    `chunk` > 0 bounds the memory of the step: the batch runs through the kernels `chunk` samples at a time (one chunk's wave stash
+    alive) and still yields the loss and gradients of the whole batch (`_direct_grads_chunked`; direct route only)."""
     if world > 1 and arena is None:
         raise RuntimeError("multi-GPU steps need a GradArena (the gradient exchange is one all-reduce over its flat buffer)")
     if direct is None:
@@ -190,11 +280,16 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         arena.zero()
         idx = model._index_tensor(indices)
         meas = measurements if measurements is not None else MeasurementView(model.measurements, idx, model)
-        losses = _direct_grads(model, loss_fn, idx, meas, arena)
+        if chunk and idx.numel() > chunk:
+            losses = _direct_grads_chunked(model, loss_fn, idx, meas, arena, int(chunk))
+        else:
+            losses = _direct_grads(model, loss_fn, idx, meas, arena)
         if world > 1:
             arena.allreduce(world)
         optimizer.step()
         return losses
+    if chunk and len(indices) > chunk:
+        raise ValueError("chunked steps exist on the direct (autograd-free) route only")
     if arena is not None:
         arena.attach()
         if first_of_group:
@@ -237,13 +332,13 @@ class GraphedStep:
     """
 
     def __init__(self, model, loss_fn, optimizer, arena: GradArena, batch_size: int, grad_accumulation: int = 1, warmup: int = 2,
-                 world: int = 1, stream_measurements: bool = False):
+                 world: int = 1, stream_measurements: bool = False, chunk: int = 0):
         if grad_accumulation != 1:
             raise ValueError("GraphedStep captures a whole step (zero, forward, adjoint, exchange, optimizer): use the eager "
                              "recon_batch / recon_step for gradient accumulation")
         self.model, self.loss_fn, self.opt, self.arena = model, loss_fn, optimizer, arena
         self.B = int(batch_size)
-        self.world, self.warmup = world, warmup
+        self.world, self.warmup, self.chunk = world, warmup, int(chunk)
         dev = model.opt_obja.device
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.params = list(model.optimizable_tensors.values())
@@ -298,7 +393,7 @@ class GraphedStep:
         self._rebind()
         snap_p = [p.detach().clone() for p in self.params]
         snap_o = self._snapshot_opt()
-        run = lambda: recon_batch(model, self.loss_fn, self.opt, self.idx, self.arena, self.world, measurements=self._mv)
+        run = lambda: recon_batch(model, self.loss_fn, self.opt, self.idx, self.arena, self.world, measurements=self._mv, chunk=self.chunk)
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
@@ -308,6 +403,8 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         # the warm-up may have created optimiser state; restore values before capture so that nothing captured depends on them
         self._restore(snap_p, snap_o)
+        # the graph allocates from its own pool: hand the warm-up's cached blocks (a wave stash can be > 100 GB) back first
+        torch.cuda.empty_cache()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             losses = run()

@@ -232,7 +232,7 @@ def test_direct_step_matches_autograd_step(case):
         else:
             assert rel(out[True][1][k], g) < (2e-6 if k in ("obja", "objp", "probe") else 2e-4), k   # run-to-run atomics noise
     for k, v in out[False][2].items():
-        assert rel(out[True][2][k], v) < 1e-6, k
+        assert rel(out[True][2][k], v) < 3e-6, k       # first Adam step ~ lr * sign(g): atomics noise on near-zero gradients shows up here
 
 
 def test_tilt_and_thickness_gradients():
@@ -837,3 +837,56 @@ def test_loss_simlar_scale_factors_against_the_oracle(scale_factor):
     np.testing.assert_allclose(r["losses"], ref["losses"], rtol=TOL_LOSS, atol=1e-9)
     for k in ("obja", "objp", "probe"):
         assert rel(r["grads"][k], ref["grads"][k]) < 5e-4, (k, rel(r["grads"][k], ref["grads"][k]))
+
+
+@pytest.mark.parametrize("case,chunk", [("T128", 4), ("T128", 1), ("T64", 3), ("T256", 2), ("T192", 3), ("T128-noshift", 5), ("T128-graph", 4)])
+def test_chunked_step_equals_the_whole_batch_step(case, chunk):
+    """A step that runs its batch `chunk` samples at a time (one chunk's wave stash alive: SURVEY 8e, memory must not grow with B)
+    must produce the loss and the gradients of the WHOLE batch -- not a sum of per-chunk losses (losses.py:42-47 normalises over the
+    batch): ragged chunks, fused128 / fused64 / general kernels, shifted and unshifted probes, Poisson loss, eager and graph replay."""
+    from dataclasses import replace
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch, chunked_step_eligible
+    from workloads import make_inputs, CONFIGS
+    name = case.split("-")[0]
+    cfg = CONFIGS[name]
+    if "noshift" in case:
+        cfg = replace(cfg, lr_shifts=0.0)
+    iv, mp, lp = make_inputs(cfg, seed=23)
+    idx = np.arange(cfg.batch, dtype=np.int64)
+    out = {}
+    for ch in (0, chunk):
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        opt = FusedAdam(model.optimizable_params)
+        arena = GradArena(model)
+        assert chunked_step_eligible(model, loss_fn)
+        if "graph" in case:
+            losses = GraphedStep(model, loss_fn, opt, arena, cfg.batch, chunk=ch)(idx)
+        else:
+            losses = recon_batch(model, loss_fn, opt, idx, arena, direct=True, chunk=ch)
+        torch.cuda.synchronize()
+        out[ch] = (losses.cpu().numpy().copy(), {k: (None if t.grad is None else t.grad.detach().cpu().numpy().copy()) for k, t in model.optimizable_tensors.items()},
+                   {k: t.detach().cpu().numpy().copy() for k, t in model.optimizable_tensors.items()})
+    np.testing.assert_allclose(out[chunk][0], out[0][0], rtol=2e-6, atol=1e-9)
+    for k, g in out[0][1].items():
+        if g is None:
+            assert out[chunk][1][k] is None, k
+        else:
+            assert rel(out[chunk][1][k], g) < (5e-6 if k in ("obja", "objp", "probe") else 2e-4), (k, rel(out[chunk][1][k], g))
+    for k, v in out[0][2].items():
+        assert rel(out[chunk][2][k], v) < 1e-6, k
+
+
+def test_chunked_step_rejects_what_it_cannot_separate():
+    """pacbed (a statistic of the batch-mean pattern) and two simultaneous data terms have no per-pattern factorisation."""
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, recon_batch
+    from workloads import make_inputs
+    iv, mp, lp = make_inputs("T128", seed=3)
+    lp["loss_poissn"]["state"] = True
+    model = PtychoAD(iv, mp, device="cuda", verbose=False)
+    with pytest.raises(ValueError):
+        recon_batch(model, CombinedLoss(lp, device="cuda"), FusedAdam(model.optimizable_params), np.arange(6), GradArena(model), direct=True, chunk=2)
