@@ -70,6 +70,11 @@ typedef struct ptyb200_cfg {
 #define PTYB200_ACC_KEEP_STATS 1   /* ptyb200_forward_loss: add to the loss sums of the earlier chunks (no zeroing, no final scalars) */
 #define PTYB200_ACC_KEEP_GRADS 2   /* ptyb200_backward: add to the gradient accumulators of the earlier chunks (no zeroing) */
 #define PTYB200_ACC_NO_FINISH  4   /* ptyb200_backward: leave the accumulators raw; ptyb200_backward_finish completes them */
+/* Two more bits let a caller take short, independent launches off the critical path of a step (run them on a second stream while the
+ * multislice forward occupies the first): */
+#define PTYB200_ACC_NO_LOSS_FINAL 8 /* ptyb200_forward_loss: leave losses3 to a later ptyb200_loss_finalize */
+#define PTYB200_ACC_ADD_OBJ   16   /* ptyb200_backward(_finish): ADD the object gradients to g_obja / g_objp, which the caller zeroed and
+                                      may have pre-loaded with other terms (ptyb200_sparse_grad), instead of overwriting them */
 
 typedef struct ptyb200_loss_cfg {
     /* CombinedLoss terms computed natively (losses.py:36-104); state 0 => term is 0 */
@@ -206,6 +211,12 @@ int ptyb200_blur_axis(const float* in, float* out, int64_t outer, int32_t L, int
                       int32_t pad_mode, ptyb200_stream s);
 int ptyb200_object_constraints(const ptyb200_obj_constraints* oc, float* obja, float* objp, int64_t n, float* scratch,
                                ptyb200_stream s);
+
+/* Zeroes what a following ptyb200_backward(cfg.reserved[4] & PTYB200_ACC_KEEP_GRADS) accumulates into (the workspace accumulators, the
+ * dense shift gradient, the probe gradient of unshifted probes): the same memsets ptyb200_backward starts with, as a call of their
+ * own so that they can run early on another stream. */
+int ptyb200_backward_zero(const ptyb200_cfg* cfg, int32_t B, void* workspace, float* g_probe, float* g_shifts, uint32_t need_mask,
+                          ptyb200_stream s);
 
 /* Completion of a chunked step (see PTYB200_ACC_*): object polar backward, probe-spectrum inverse FFT and the batch-level `scale`
  * (device float, e.g. from ptyb200_loss_scale; NULL = 1) applied to every requested gradient.  Same buffers / need_mask as the

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PTYB_LIB") or os.path.join(_HERE, "lib", "libptyrad_b200.so")   # PTYB_LIB: kernel-variant experiments
 ABI_VERSION = 3
-ACC_KEEP_STATS, ACC_KEEP_GRADS, ACC_NO_FINISH = 1, 2, 4      # cfg.reserved[4] of a chunked step (include/ptyrad_b200.h)
+ACC_KEEP_STATS, ACC_KEEP_GRADS, ACC_NO_FINISH, ACC_NO_LOSS_FINAL, ACC_ADD_OBJ = 1, 2, 4, 8, 16      # cfg.reserved[4] of a chunked step (include/ptyrad_b200.h)
 
 NEED_OBJ, NEED_PROBE, NEED_SHIFTS, NEED_TILTS, NEED_DZ = 1, 2, 4, 8, 16
 PATH_AUTO, PATH_GENERAL, PATH_FUSED = 0, 1, 2
@@ -74,6 +74,7 @@ _SIGNATURES = {
     "ptyb200_gaussian_blur5": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
     "ptyb200_blur_axis": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
     "ptyb200_object_constraints": (C.c_int, [C.POINTER(ObjConstraints), _P, _P, C.c_int64, _P, _P]),
+    "ptyb200_backward_zero": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, _P, C.c_uint32, _P]),
     "ptyb200_backward_finish": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P]),
     "ptyb200_loss_finalize": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), C.c_int32, _P, _P, _P, _P]),
     "ptyb200_loss_scale": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), C.c_int32, _P, _P, _P, _P]),

@@ -44,6 +44,51 @@ void tm_mark(int section, int which, cudaStream_t st) {
     if (which == 1) ++g_tm.n[section];
 }
 
+// Independent short kernels of one call (object polar form | propagator transpose + permute | probe-spectrum FFT + permute before
+// the multislice kernels; probe-gradient inverse FFT | object polar backward after them) run as parallel branches: a step is a chain
+// of ~30 launches of which two matter, and every link of a serial chain costs a few microseconds of launch latency even inside a
+// CUDA graph.  The branches use two internal non-blocking streams that are forked from and joined back into the caller's stream
+// with events inside the same call, so the caller still sees one stream (and a stream capture sees a fork/join subgraph).
+struct SidePool {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        ok = true;
+        return true;
+    }
+} g_side;
+std::mutex g_side_mu;
+static const bool g_no_branches = [] { const char* e = getenv("PTYB200_NO_BRANCHES"); return e && atoi(e) != 0; }();
+// fork: both side streams wait for everything enqueued on `st` so far; returns false (caller stays serial) if unavailable
+bool side_fork(cudaStream_t st, cudaStream_t out[2]) {
+    out[0] = out[1] = st;
+    if (g_no_branches) return false;
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    if (!g_side.init()) { cudaGetLastError(); return false; }
+    if (cudaEventRecord(g_side.fork, st) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamWaitEvent(g_side.s[i], g_side.fork, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+    out[0] = g_side.s[0]; out[1] = g_side.s[1];
+    return true;
+}
+// join: `st` waits for both side streams
+int side_join(cudaStream_t st, bool forked) {
+    if (!forked) return 0;
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventRecord(g_side.join[i], g_side.s[i]) != cudaSuccess) return 1;
+        if (cudaStreamWaitEvent(st, g_side.join[i], 0) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+
 int fail(const char* what, cudaError_t e, const char* file, int line) {
     char buf[512];
     snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
@@ -192,16 +237,17 @@ FwdArgs make_fwd_args(const ptyb200_cfg& c, int B, const Workspace& w, const int
 // shared setup: complex object, transposed propagator, probe spectrum, per-sample ramps
 template <class F> int setup_common(const ptyb200_cfg& c, int B, const Workspace& w, const int64_t* idx, const float* obja,
                                     const float* objp, const float* probe, const float* shifts, const float* Hbase,
-                                    const float* tilts, const float* dz, cudaStream_t st) {
+                                    const float* tilts, const float* dz, cudaStream_t st, cudaStream_t sH, cudaStream_t sP) {
+    // st: complex object + per-sample ramps; sH: transposed propagator; sP: probe spectrum (the caller joins sH / sP into st)
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
     k_obj_polar<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(obja, objp, w.O, obj);
     CKL();
     dim3 tb(32, 8), tg((c.N + 31) / 32, (c.N + 31) / 32);
-    k_transpose<<<tg, tb, 0, st>>>((const float2*)Hbase, w.HT, c.N);
+    k_transpose<<<tg, tb, 0, sH>>>((const float2*)Hbase, w.HT, c.N);
     CKL();
     if (c.shift_probes) {
         if (!shifts) return fail_msg("shift_probes set but shifts is NULL");
-        if (int r = fft2_tiles<F>((const float2*)probe, w.tmpP, w.PhatT, c.P, -1, st)) return r;
+        if (int r = fft2_tiles<F>((const float2*)probe, w.tmpP, w.PhatT, c.P, -1, sP)) return r;
         k_shift_vectors<<<B, 128, 0, st>>>(shifts, idx, B, c.N, w.wvec);
         CKL();
     }
@@ -373,14 +419,20 @@ static int forward_impl(const ptyb200_cfg* c, const int64_t* idx, int32_t B, con
     FwdArgs a = make_fwd_args(*c, B, w, idx, crop_pos, probe, occu, dp_out);
     if (lf) a.lf = *lf;
     if (c->path == PTYB200_PATH_FUSED && !fused_covers(*c)) return fail_msg("fused path does not cover this configuration");
+    cudaStream_t side[2];
+    const bool forked = side_fork(st, side);
     DISPATCH_N(c->N, {
-        if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st)) return r;
-        tm_mark(0, 0, st);
+        if (int r = setup_common<F>(*c, B, w, idx, obja, objp, probe, shifts, Hbase, tilts, dz, st, side[0], side[1])) return r;
         if (use_fused(*c)) {
-            if (int r = fused64::covers(*c) ? fused64::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches)
-                                            : fused128::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches)) return r;
+            // the fused paths permute the two tables on the branches that made them and join inside, just before the wave kernel
+            auto join = [&]() -> int { if (side_join(st, forked)) return fail_msg("side-stream join failed"); tm_mark(0, 0, st); return 0; };
+            if (int r = fused64::covers(*c) ? fused64::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches, side[0], side[1], join)
+                                            : fused128::forward(*c, B, a, obja, objp, w.fused, st, g_err, &g_launches, side[0], side[1], join)) return r;
+        } else {
+            if (side_join(st, forked)) return fail_msg("side-stream join failed");
+            tm_mark(0, 0, st);
+            if (int r = forward_general<F>(*c, B, w, a, st)) return r;
         }
-        else if (int r = forward_general<F>(*c, B, w, a, st)) return r;
         tm_mark(0, 1, st);
     });
     return 0;
@@ -412,8 +464,10 @@ int ptyb200_forward_loss(const ptyb200_cfg* c, const int64_t* idx, int32_t B, co
         if (lf.k.b_on) CK(cudaMemsetAsync(pac, 0, (size_t)2 * c->N * c->N * 4, st));
     }
     if (int r = forward_impl(c, idx, B, obja, objp, crop_pos, probe, shifts, Hbase, tilts, dz, occu, dp_out, workspace, &lf, s)) return r;
-    k_loss_final<<<1, 256, 0, st>>>(lf.k, B, c->N, stats, pac, losses3);
-    CKL();
+    if (!(c->reserved[4] & PTYB200_ACC_NO_LOSS_FINAL)) {
+        k_loss_final<<<1, 256, 0, st>>>(lf.k, B, c->N, stats, pac, losses3);
+        CKL();
+    }
     return 0;
 }
 
@@ -447,7 +501,7 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
         return fail_msg("gradient buffers must be 16-byte aligned (g_shifts / g_tilts: 8-byte)");
     const size_t obj = (size_t)((c->reserved[1] & 1) ? B : 1) * c->M * c->Z * c->Noy * c->Nox;
     const int acc = c->reserved[4];
-    if (acc & (PTYB200_ACC_KEEP_GRADS | PTYB200_ACC_NO_FINISH)) {
+    if (acc & PTYB200_ACC_NO_FINISH) {                    // (KEEP_GRADS alone = accumulators zeroed early by ptyb200_backward_zero: any configuration)
         if (a.need_prop) return fail_msg("chunked steps do not cover tilt / thickness gradients");
         if (c->reserved[1] & 1) return fail_msg("chunked steps do not cover patch mode");
     }
@@ -460,22 +514,28 @@ int ptyb200_backward(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const 
     if (need_t) CK(cudaMemsetAsync(g_tilts, 0, (size_t)(c->tilt_mode == 2 ? c->Ntot : 1) * 2 * 4, st));
     if (need_dz) CK(cudaMemsetAsync(g_dz, 0, 4, st));
     if (c->path == PTYB200_PATH_FUSED && !fused_covers(*c)) return fail_msg("fused path does not cover this configuration");
+    // after the adjoint kernel of the fused paths: probe-spectrum gradient (unpermute + inverse FFT) on a branch, object polar backward
+    // on the caller's stream
+    cudaStream_t sfin[2] = {st, st};
+    bool fin_forked = false;
+    auto fork_fin = [&]() -> cudaStream_t { tm_mark(1, 1, st); fin_forked = side_fork(st, sfin); return sfin[0]; };
     DISPATCH_N(c->N, {
         tm_mark(1, 0, st);
         if (use_fused(*c)) {
             if (int r = fused64::covers(*c)
-                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, acc)
-                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, acc)) return r;
+                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, acc, nullptr, false, fork_fin)
+                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, acc, nullptr, false, fork_fin)) return r;
         }
         else if (int r = backward_general<F>(*c, B, w, a, g_probe, st, acc)) return r;
-        tm_mark(1, 1, st);
+        if (!use_fused(*c)) tm_mark(1, 1, st);
         if (use_fused(*c) && a.need_probe && c->shift_probes && !(acc & PTYB200_ACC_NO_FINISH))
-            if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, st)) return r;
+            if (int r = fft2_tiles<F>(w.gPhatT, w.tmpP, (float2*)g_probe, c->P, +1, sfin[0])) return r;
     });
     if (a.need_obj && !use_fused(*c) && !(acc & PTYB200_ACC_NO_FINISH)) {
-        k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj, nullptr);
+        k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj, nullptr, (acc & PTYB200_ACC_ADD_OBJ) ? 1 : 0);
         CKL();
     }
+    if (side_join(st, fin_forked)) return fail_msg("side-stream join failed");
     if (a.need_prop) {
         k_prop_finish<<<1, 256, 0, st>>>(w.gprop, tilts, c->tilt_mode, idx, B, dz, need_t ? g_tilts : nullptr, need_dz ? g_dz : nullptr);
         CKL();
@@ -610,6 +670,36 @@ int ptyb200_loss_scale(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, int32_t
     return 0;
 }
 
+int ptyb200_backward_zero(const ptyb200_cfg* c, int32_t B, void* workspace, float* g_probe, float* g_shifts, uint32_t need_mask,
+                          ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!workspace) return fail_msg("NULL argument");
+    if (c->reserved[1] & 1) return fail_msg("backward_zero does not cover patch mode");
+    cudaStream_t st = (cudaStream_t)s;
+    Workspace w = carve(*c, B, workspace);
+    const size_t obj = (size_t)c->M * c->Z * c->Noy * c->Nox, pn = (size_t)c->P * c->N * c->N * 8;
+    if (need_mask & PTYB200_NEED_OBJ) {
+        if (use_fused(*c)) {
+            fused128::Scratch sc = fused64::covers(*c) ? fused64::carve_scratch(*c, B, w.fused) : fused128::carve_scratch(*c, B, w.fused);
+            CK(cudaMemsetAsync(sc.gOpack, 0, obj * 16, st));
+        } else CK(cudaMemsetAsync(w.gO, 0, obj * 8, st));
+    }
+    if (need_mask & PTYB200_NEED_PROBE) {
+        if (c->shift_probes) {
+            CK(cudaMemsetAsync(w.gPhatT, 0, pn, st));
+            if (use_fused(*c)) {
+                fused128::Scratch sc = fused64::covers(*c) ? fused64::carve_scratch(*c, B, w.fused) : fused128::carve_scratch(*c, B, w.fused);
+                CK(cudaMemsetAsync(sc.gPhatF, 0, pn, st));
+            }
+        } else {
+            if (!g_probe) return fail_msg("g_probe is NULL");
+            CK(cudaMemsetAsync(g_probe, 0, pn, st));
+        }
+    }
+    if ((need_mask & PTYB200_NEED_SHIFTS) && g_shifts) CK(cudaMemsetAsync(g_shifts, 0, (size_t)c->Ntot * 2 * 4, st));
+    return 0;
+}
+
 int ptyb200_backward_finish(const ptyb200_cfg* c, int32_t B, const float* obja, const float* objp, void* workspace, float* g_obja,
                             float* g_objp, float* g_probe, float* g_shifts, uint32_t need_mask, const float* scale, ptyb200_stream s) {
     if (int r = check_cfg(c, B)) return r;
@@ -630,10 +720,10 @@ int ptyb200_backward_finish(const ptyb200_cfg* c, int32_t B, const float* obja, 
             a.f = make_fwd_args(*c, B, w, nullptr, nullptr, nullptr, nullptr, nullptr);
             a.need_obj = need_obj; a.need_probe = need_probe;
             if (int r = fused64::covers(*c)
-                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, 0, scale, true)
-                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, 0, scale, true)) return r;
+                            ? fused64::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, c->reserved[4] & PTYB200_ACC_ADD_OBJ, scale, true)
+                            : fused128::backward(*c, B, a, obja, objp, g_obja, g_objp, w.fused, (float2*)g_probe, w.gPhatT, st, g_err, &g_launches, c->reserved[4] & PTYB200_ACC_ADD_OBJ, scale, true)) return r;
         } else if (need_obj) {
-            k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj, scale);
+            k_obj_finish<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(w.gO, obja, objp, g_obja, g_objp, obj, scale, (c->reserved[4] & PTYB200_ACC_ADD_OBJ) ? 1 : 0);
             CKL();
         }
         if (need_probe && c->shift_probes)

@@ -28,6 +28,7 @@
 #include "general_kernels.cuh"
 #include "../../include/ptyrad_b200.h"
 #include <atomic>
+#include <functional>
 #include <string>
 #include <cstring>
 
@@ -265,7 +266,7 @@ __global__ void k_dp_init(float4* __restrict__ dp4, size_t n4, float eps, int* _
 
 // g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O)) with gO[Y][X] = gOpack[Y][X].xy + gOpack[Y-4][X].zw
 __global__ void k_obj_finish_pack(const float4* __restrict__ gOp, const float* __restrict__ a, const float* __restrict__ ph,
-                                  float* __restrict__ ga, float* __restrict__ gp, int Noy, int Nox, size_t n, const float* __restrict__ scale) {
+                                  float* __restrict__ ga, float* __restrict__ gp, int Noy, int Nox, size_t n, const float* __restrict__ scale, int add) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float sc = scale ? scale[0] : 1.0f;           // batch-level factor of dL/dI (chunked steps), else 1
@@ -275,8 +276,9 @@ __global__ void k_obj_finish_pack(const float4* __restrict__ gOp, const float* _
     if (Y >= 4) { const float4 up = gOp[i - (size_t)4 * Nox]; g.x += up.z; g.y += up.w; }
     float s, c;
     sincosf(ph[i], &s, &c);
-    ga[i] = sc * (g.x * c + g.y * s);
-    gp[i] = sc * a[i] * (g.y * c - g.x * s);
+    const float va = sc * (g.x * c + g.y * s), vp = sc * a[i] * (g.y * c - g.x * s);
+    if (add) { ga[i] += va; gp[i] += vp; }      // the gradient arrays already hold other terms (loss_sparse, written early on a side stream)
+    else { ga[i] = va; gp[i] = vp; }
 }
 
 // ---- memory helpers -----------------------------------------------------------------------------------------------
@@ -696,16 +698,19 @@ inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc,
 }
 
 // f.HT = transposed propagator [kx][ky]; f.PhatT = probe spectrum [kx][ky] (both made by setup_common)
+// sH / sP: the branches on which the transposed propagator / the probe spectrum are being made (api.cu: setup_common); their permuted
+// copies are made there too, and `join` brings both back into `st` just before the wave kernel
+template <class Join>
 inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, const float* objp, unsigned char* scratch, cudaStream_t st,
-                   std::string& err, std::atomic<long long>* launches) {
+                   std::string& err, std::atomic<long long>* launches, cudaStream_t sH, cudaStream_t sP, Join join) {
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = make_args(c, f, sc, f.phis);
     const float inv = 1.0f / (128.0f * 128.0f);
     const size_t obj = (size_t)((c.reserved[1] & 1) ? B : 1) * c.M * c.Z * c.Noy * c.Nox;
-    k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
+    k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, sH>>>(f.HT, sc.HF, inv);
     F128_CK(cudaGetLastError()); ++*launches;
     if (c.shift_probes) {
-        k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(f.PhatT, sc.PhatF, inv);
+        k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, sP>>>(f.PhatT, sc.PhatF, inv);
         F128_CK(cudaGetLastError()); ++*launches;
     }
     a.f.lf.counter = sc.counter;
@@ -714,6 +719,7 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
         k_dp_init<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(f.dp), n4, c.eps, sc.counter, B);
         F128_CK(cudaGetLastError()); ++*launches;
     }
+    if (int r = join()) return r;
     const dim3 grid(c.P, c.M, B);
     const bool tilt = f.tvec != nullptr, phis = a.phisF != nullptr;
 #define F128_LAUNCH_FWD(T, PH)                                                                                                     \
@@ -732,7 +738,8 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
 // probe-spectrum inverse FFT
 inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float* obja, const float* objp, float* g_obja, float* g_objp,
                     unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches,
-                    int acc_flags = 0, const float* scale = nullptr, bool finish_only = false) {
+                    int acc_flags = 0, const float* scale = nullptr, bool finish_only = false,
+                    const std::function<cudaStream_t()>& fork_fin = nullptr) {
     // acc_flags (PTYB200_ACC_*): KEEP_GRADS = the accumulators already hold earlier chunks of the batch; NO_FINISH = leave them raw.
     // finish_only: no adjoint, only the completion of the accumulators (with the batch-level `scale` of an unscaled loss gradient).
     Scratch sc = carve_scratch(c, B, scratch);
@@ -761,13 +768,14 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
         F128_CK(cudaGetLastError()); ++*launches;
     }
 #undef F128_LAUNCH_BWD
+    const cudaStream_t sp = fork_fin ? fork_fin() : st;        // branch of the probe-gradient chain (api.cu continues it and joins)
     if (acc_flags & PTYB200_ACC_NO_FINISH) return 0;
     if (a.need_probe && c.shift_probes) {
-        k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
+        k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, sp>>>(sc.gPhatF, gPhatT);
         F128_CK(cudaGetLastError()); ++*launches;
     }
     if (a.need_obj) {
-        k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj, scale);
+        k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj, scale, (acc_flags & PTYB200_ACC_ADD_OBJ) ? 1 : 0);
         F128_CK(cudaGetLastError()); ++*launches;
     }
     return 0;

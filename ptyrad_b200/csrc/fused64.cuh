@@ -552,15 +552,18 @@ inline Args make_args(const ptyb200_cfg& c, const FwdArgs& f, const Scratch& sc,
     return a;
 }
 
+// sH / sP: the branches on which the transposed propagator / the probe spectrum are being made (api.cu: setup_common); their permuted
+// copies are made there too, and `join` brings both back into `st` just before the wave kernel
+template <class Join>
 inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, const float* objp, unsigned char* scratch, cudaStream_t st,
-                   std::string& err, std::atomic<long long>* launches) {
+                   std::string& err, std::atomic<long long>* launches, cudaStream_t sH, cudaStream_t sP, Join join) {
     Scratch sc = carve_scratch(c, B, scratch);
     Args a = fused64::make_args(c, f, sc, f.phis);
     const float inv = 1.0f / float(TILE);
-    k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, st>>>(f.HT, sc.HF, inv);
+    k_permute_to_F<<<dim3(TILE / 256, 1), 256, 0, sH>>>(f.HT, sc.HF, inv);
     F64_CK(cudaGetLastError()); ++*launches;
     if (c.shift_probes) {
-        k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(f.PhatT, sc.PhatF, inv);
+        k_permute_to_F<<<dim3(TILE / 256, c.P), 256, 0, sP>>>(f.PhatT, sc.PhatF, inv);
         F64_CK(cudaGetLastError()); ++*launches;
     }
     a.f.lf.counter = sc.counter;
@@ -569,6 +572,7 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
         fused128::k_dp_init<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(f.dp), n4, c.eps, sc.counter, B);
         F64_CK(cudaGetLastError()); ++*launches;
     }
+    if (int r = join()) return r;
     const dim3 grid(c.P, c.M, B);
     const bool tilt = f.tvec != nullptr, phis = a.phisF != nullptr;
 #define F64_LAUNCH_FWD(T, PH)                                                                                                      \
@@ -585,7 +589,8 @@ inline int forward(const ptyb200_cfg& c, int B, FwdArgs f, const float* obja, co
 
 inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float* obja, const float* objp, float* g_obja, float* g_objp,
                     unsigned char* scratch, float2* g_probe, float2* gPhatT, cudaStream_t st, std::string& err, std::atomic<long long>* launches,
-                    int acc_flags = 0, const float* scale = nullptr, bool finish_only = false) {
+                    int acc_flags = 0, const float* scale = nullptr, bool finish_only = false,
+                    const std::function<cudaStream_t()>& fork_fin = nullptr) {
     // acc_flags (PTYB200_ACC_*): KEEP_GRADS = the accumulators already hold earlier chunks of the batch; NO_FINISH = leave them raw.
     // finish_only: no adjoint, only the completion of the accumulators (with the batch-level `scale` of an unscaled loss gradient).
     Scratch sc = carve_scratch(c, B, scratch);
@@ -614,13 +619,14 @@ inline int backward(const ptyb200_cfg& c, int B, const BwdArgs& bw, const float*
         F64_CK(cudaGetLastError()); ++*launches;
     }
 #undef F64_LAUNCH_BWD
+    const cudaStream_t sp = fork_fin ? fork_fin() : st;        // branch of the probe-gradient chain (api.cu continues it and joins)
     if (acc_flags & PTYB200_ACC_NO_FINISH) return 0;
     if (a.need_probe && c.shift_probes) {
-        k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, st>>>(sc.gPhatF, gPhatT);
+        k_unpermute_from_F<<<dim3(TILE / 256, c.P), 256, 0, sp>>>(sc.gPhatF, gPhatT);
         F64_CK(cudaGetLastError()); ++*launches;
     }
     if (a.need_obj) {
-        fused128::k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj, scale);
+        fused128::k_obj_finish_pack<<<(unsigned)((obj + 255) / 256), 256, 0, st>>>(sc.gOpack, obja, objp, g_obja, g_objp, c.Noy, c.Nox, obj, scale, (acc_flags & PTYB200_ACC_ADD_OBJ) ? 1 : 0);
         F64_CK(cudaGetLastError()); ++*launches;
     }
     return 0;

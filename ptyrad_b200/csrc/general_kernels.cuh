@@ -947,15 +947,16 @@ __global__ void k_bwd_probe_noshift(Dims d, int nb, int first, const float2* __r
 // g_a = Re(gO e^{-i phi}), g_phi = Im(gO conj(O))   (polar backward, forward.py:53)
 // `scale` (device scalar or null): the batch-level factor of dL/dI when the adjoint ran on the unscaled loss gradient (chunked steps)
 __global__ void k_obj_finish(const float2* __restrict__ gO, const float* __restrict__ a, const float* __restrict__ ph,
-                             float* __restrict__ ga, float* __restrict__ gp, size_t n, const float* __restrict__ scale) {
+                             float* __restrict__ ga, float* __restrict__ gp, size_t n, const float* __restrict__ scale, int add) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float sc = scale ? scale[0] : 1.0f;
     float s, c;
     sincosf(ph[i], &s, &c);
     float2 g = gO[i];
-    ga[i] = sc * (g.x * c + g.y * s);
-    gp[i] = sc * a[i] * (g.y * c - g.x * s);
+    const float va = sc * (g.x * c + g.y * s), vp = sc * a[i] * (g.y * c - g.x * s);
+    if (add) { ga[i] += va; gp[i] += vp; }      // the gradient arrays already hold other terms (loss_sparse, written early on a side stream)
+    else { ga[i] = va; gp[i] = vp; }
 }
 __global__ void k_scale(float* __restrict__ x, size_t n, const float* __restrict__ scale) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

@@ -72,6 +72,18 @@ def shard_indices(indices, rank: int, world: int):
     return np.array_split(indices, world)[rank]
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for work that is independent of the multislice kernels (forked from / joined into the caller's
+    stream; a stream capture records it as a parallel branch)."""
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def direct_step_eligible(model, loss_fn, arena, grad_accumulation, do_step, measurements) -> bool:
     """The autograd-free step covers: native loss terms (single / poissn / pacbed / sparse), detector blur, on-the-fly measurement
     pad / resample; gradients written once into the arena (no accumulation over batches).  Object pre-blur and loss_simlar take
@@ -177,7 +189,7 @@ def _direct_grads_chunked(model, loss_fn, idx, meas: MeasurementView, arena: Gra
     return losses
 
 
-def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
+def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, zero_arena: bool = False):
     """Forward, loss, loss gradient and adjoint through the C ABI with the gradient tensors of the arena as the kernels' output
     buffers -- what ``model(idx)`` -> ``loss_fn`` -> ``backward()`` computes (engine.MultisliceFunction / DataLossFunction /
     SparseLossFunction), minus the autograd graph, its ~30 small elementwise launches per step and the accumulate-into-.grad copies.
@@ -210,51 +222,78 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena):
     stats = torch.empty(8, dtype=torch.float64, device=dev)
     pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
     blur = model.detector_blur_std
-    fwd_args = (C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
-                ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws))
-    if not blur:
-        # forward with the mode reduction fused with the data losses: the kernel that completes a pattern also adds its loss sums
-        _lib.check(lib.ptyb200_forward_loss(*fwd_args, C.byref(lcfg), ptr(meas.all), ptr(meas.idx), engine.mref(meas.mcfg), ptr(meas.padded),
-                                            ptr(losses), ptr(stats), ptr(pac), st))
-    else:
-        _lib.check(lib.ptyb200_forward(*fwd_args, st))
-        dp = engine._blur5(dp, float(blur), 0)                # detector blur (models.py:379-380): native 5x5 kernel on the intensities
-        _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
-                                            ptr(pac), engine.mref(meas.mcfg), ptr(meas.padded), st))
+    need = ((_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0) |
+            (_lib.NEED_TILTS if n_tilts else 0) | (_lib.NEED_DZ if n_dz else 0))
     sparse = bool(lcfg.sparse_state)
+    if sparse and not need and model.opt_objp.requires_grad:
+        raise RuntimeError("unreachable: objp.requires_grad implies NEED_OBJ")
+    ones = getattr(model, "_ones3", None)                     # d(total)/d(term) = 1 for every term: total is their plain sum
+    if ones is None or ones.device != dev:
+        ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
+
+    def out(p, wanted):                                       # the arena view of a live parameter, scratch for a frozen one
+        if not wanted:
+            return None
+        return p.grad if p.requires_grad else torch.empty_like(p.data)
+
+    g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
+    g_probe, g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
+    g_tilts, g_dz = out(model.opt_obj_tilts, n_tilts), out(model.opt_slice_thickness, n_dz)
     if sparse:
         Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
         cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
-        _lib.check(lib.ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                              C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), st))
-    need = ((_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0) |
-            (_lib.NEED_TILTS if n_tilts else 0) | (_lib.NEED_DZ if n_dz else 0))
+    # A step is a chain of ~30 launches of which two matter.  Everything that does not depend on the multislice kernels runs on a
+    # side stream while the forward occupies the caller's stream (the short kernels fill its last, partial wave): zeroing of the
+    # gradient arena and of the adjoint's accumulators, loss_sparse (object and batch indices only) and its gradient, and -- once
+    # the forward is through -- the loss scalars.  The adjoint then ADDS the object gradients on top (PTYB200_ACC_ADD_OBJ).
+    cur = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        sst = engine._stream()
+        if zero_arena:
+            arena.zero()
+        if need:
+            _lib.check(lib.ptyb200_backward_zero(C.byref(cfg), B, ptr(ws), ptr(g_probe), ptr(g_shifts), need, sst))
+        if sparse:
+            _lib.check(lib.ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                                  C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), sst))
+            if need and model.opt_objp.requires_grad:
+                _lib.check(lib.ptyb200_sparse_grad(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                                   ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), sst))
+    # (loss_pacbed: the kernel that forms the loss scalars also completes a sum the loss gradient reads, so it stays in line)
+    defer_final = not lcfg.pacbed_state
+    cfg_f = type(cfg).from_buffer_copy(cfg)
+    cfg_f.reserved[4] = _lib.ACC_NO_LOSS_FINAL if defer_final else 0
+    fwd_args = (ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
+                ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws))
+    if not blur:
+        # forward with the mode reduction fused with the data losses: the kernel that completes a pattern also adds its loss sums
+        _lib.check(lib.ptyb200_forward_loss(C.byref(cfg_f), *fwd_args, C.byref(lcfg), ptr(meas.all), ptr(meas.idx), engine.mref(meas.mcfg),
+                                            ptr(meas.padded), ptr(losses), ptr(stats), ptr(pac), st))
+        if defer_final:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _lib.check(lib.ptyb200_loss_finalize(C.byref(cfg), C.byref(lcfg), B, ptr(stats), ptr(pac), ptr(losses), engine._stream()))
+    else:
+        _lib.check(lib.ptyb200_forward(C.byref(cfg), *fwd_args, st))
+        dp = engine._blur5(dp, float(blur), 0)                # detector blur (models.py:379-380): native 5x5 kernel on the intensities
+        _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
+                                            ptr(pac), engine.mref(meas.mcfg), ptr(meas.padded), st))
     if need:
-        ones = getattr(model, "_ones3", None)                 # d(total)/d(term) = 1 for every term: total is their plain sum
-        if ones is None or ones.device != dev:
-            ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
         G = torch.empty_like(dp)
         _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(stats), ptr(pac),
                                          ptr(ones), ptr(G), engine.mref(meas.mcfg), ptr(meas.padded), st))
         if blur:
             G = engine._blur5(G, float(blur), 1)              # adjoint of the blur
-
-        def out(p, wanted):                                   # the arena view of a live parameter, scratch for a frozen one
-            if not wanted:
-                return None
-            return p.grad if p.requires_grad else torch.empty_like(p.data)
-
-        g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
+        cur.wait_stream(side)                                 # accumulators zeroed, sparse term in place
+        cfg_b = type(cfg).from_buffer_copy(cfg)
+        cfg_b.reserved[4] = _lib.ACC_KEEP_GRADS | _lib.ACC_ADD_OBJ
         _lib.check(lib.ptyb200_backward(
-            C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
-            ptr(model.omode_occu), ptr(G), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(out(model.opt_probe, n_probe)),
-            ptr(out(model.opt_probe_pos_shifts, n_shifts)), ptr(out(model.opt_obj_tilts, n_tilts)),
-            ptr(out(model.opt_slice_thickness, n_dz)), need, st))
-        if sparse and model.opt_objp.requires_grad:
-            _lib.check(lib.ptyb200_sparse_grad(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                               ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), st))
-    elif sparse and model.opt_objp.requires_grad:
-        raise RuntimeError("unreachable: objp.requires_grad implies NEED_OBJ")
+            C.byref(cfg_b), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
+            ptr(model.omode_occu), ptr(G), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), ptr(g_tilts), ptr(g_dz), need, st))
+    else:
+        cur.wait_stream(side)
     return losses
 
 
@@ -277,13 +316,13 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         raise ValueError("this configuration needs the autograd path (direct=False)")
     if direct:
         arena.attach()
-        arena.zero()
         idx = model._index_tensor(indices)
         meas = measurements if measurements is not None else MeasurementView(model.measurements, idx, model)
         if chunk and idx.numel() > chunk:
+            arena.zero()
             losses = _direct_grads_chunked(model, loss_fn, idx, meas, arena, int(chunk))
         else:
-            losses = _direct_grads(model, loss_fn, idx, meas, arena)
+            losses = _direct_grads(model, loss_fn, idx, meas, arena, zero_arena=True)     # zeroes the arena itself, on its side stream
         if world > 1:
             arena.allreduce(world)
         optimizer.step()
