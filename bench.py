@@ -421,7 +421,10 @@ def main():
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", PROFILE_ROUND, f"ncu_traffic_{cfg.name}.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
+        try:
+            tj = json.load(open(tpath))
+        except ValueError:
+            tj = {}
         if tj.get("csrc_sha256") == csrc_hash() and tj.get("batch") == B and tj.get("path", "auto") == args.path:
             kb = tj["kernels"][tj["dominant"]]
             traffic, traffic_src = (kb["dram_read_gb"] + kb["dram_write_gb"]) * 1e9, f"profiles/{PROFILE_ROUND}/" + os.path.basename(tpath)

@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(FT, 1) k_forward(Args a) {
             const float* M_ = lf.mv.meas + (size_t)lf.rows[b] * lf.mv.Hs * lf.mv.Ws;
             float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (meas_plain(lf.mv)) {
-#pragma unroll
+                // cold code (one CTA per pattern) kept ROLLED: unrolled, its pow / log expansions made the kernel 482 KB and the forward
+                // 3.5 % slower (1.215 -> 1.173 ms at C2); out of line (__noinline__) it costs a 480-byte frame and is slower again (1.224)
+#pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
                     const int q = g.t + 512 * j;
                     const float4 i4 = __ldcg(reinterpret_cast<const float4*>(dpb) + q);

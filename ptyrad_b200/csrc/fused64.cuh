@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(FT, MINB) k_forward(Args a) {
             const float* M_ = lf.mv.meas + (size_t)lf.rows[b] * lf.mv.Hs * lf.mv.Ws;
             float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (meas_plain(lf.mv)) {
-#pragma unroll
+#pragma unroll 1                                       // cold code (one CTA per pattern): kept rolled, see fused128.cuh
                 for (int j = 0; j < TILE / 4 / FT; ++j) {
                     const int q = g.t + FT * j;
                     const float4 i4 = __ldcg(reinterpret_cast<const float4*>(dpb) + q);
