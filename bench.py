@@ -432,8 +432,9 @@ def main():
             traffic_src = f"profiles/{PROFILE_ROUND}/{os.path.basename(tpath)} is from another build / batch of the kernels: not quoted"
     comp, stash = bytes_per_pattern(cfg)
     # adjoint section (dominant): re-reads the stash, reads the ROIs, read-modify-writes the ROI gradients, reads G
-    bwd_bytes = B * (8 * cfg.P * cfg.M * cfg.Z + 16 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
-    fwd_bytes = B * (8 * cfg.P * cfg.M * cfg.Z + 8 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
+    Bl = chunk if (chunk and B > chunk) else B            # samples per launch of the section (a chunked step launches it per chunk)
+    bwd_bytes = Bl * (8 * cfg.P * cfg.M * cfg.Z + 16 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
+    fwd_bytes = Bl * (8 * cfg.P * cfg.M * cfg.Z + 8 * cfg.M * cfg.Z + 4) * cfg.N * cfg.N
     ms_b = tb.value / max(1, nb.value)
     ms_f = tf.value / max(1, nf.value)
     ach_b = bwd_bytes / (ms_b * 1e-3) / 1e9 if ms_b > 0 else 0.0

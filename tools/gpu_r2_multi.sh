@@ -21,4 +21,4 @@ PY
 }
 run C2 --steps 60 --warmup 5 --no-cpu-baseline
 run C4 --config C4 --steps 8 --warmup 3 --no-cpu-baseline --no-e2e
-run C4strong --config C4 --scaling strong --steps 8 --warmup 3 --no-cpu-baseline --no-e2e
+run C4strong --config C4 --scaling strong --steps 6 --warmup 3 --no-cpu-baseline --no-e2e
