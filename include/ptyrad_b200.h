@@ -196,6 +196,26 @@ int ptyb200_sparse_grad(const ptyb200_cfg* cfg, const ptyb200_loss_cfg* lc, cons
 int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t planes, int32_t H, int32_t W, float sigma,
                            int32_t transpose, ptyb200_stream s);
 
+/* Object pre-blur without the gather tensor (models.py:251-284): out_a / out_p (B,M,Z,N,N) = the ROI planes of amplitude / phase for the
+ * batch, 5x5 Gaussian-blurred with reflect padding inside the patch when sigma > 0 (sigma = 0: the plain ROI planes, what
+ * get_obj_ROI gathers).  tmp = 2 * B*M*Z*N*N floats of scratch (sigma > 0).  These planes are what the multislice kernels take as their
+ * object in patch mode (cfg.reserved[1]) and what loss_simlar works on.
+ * ptyb200_roi_blur_adjoint: the backward pass -- patch gradients (either may be NULL) through the adjoint blur, scatter-ADDED into the
+ * dense (M,Z,Noy,Nox) gradients (the caller zeroes them; atomics, like the reference's index_put_(accumulate=True)). */
+int ptyb200_roi_blur(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const float* obja, const float* objp, const int32_t* crop_pos,
+                     float sigma, float* tmp, float* out_a, float* out_p, ptyb200_stream s);
+int ptyb200_roi_blur_adjoint(const ptyb200_cfg* cfg, const int64_t* idx, int32_t B, const int32_t* crop_pos, float sigma,
+                             const float* g_out_a, const float* g_out_p, float* tmp, float* g_obja, float* g_objp, ptyb200_stream s);
+
+/* loss_simlar (losses.py:106-141) on one set of ROI planes (B,M,Z,N,N) from ptyb200_roi_blur (sigma = blur_std or 0): area
+ * interpolation (adaptive average pooling to (Zo,Yo,Xo) = floor(size * scale_factor)), times occu_m, unbiased std over the M object
+ * modes, mean over the pooled batch volume.  forward: sum_out[0] (double) += weight * that mean.  backward: g_plane (B,M,Z,N,N), zeroed
+ * by the caller, += upstream[0] * d/d(plane); ptyb200_roi_blur_adjoint takes it to the dense gradients.  2 <= M <= 8. */
+int ptyb200_simlar_forward(const ptyb200_cfg* cfg, int32_t B, const float* plane, const float* occu, int32_t Zo, int32_t Yo, int32_t Xo,
+                           float weight, double* sum_out, ptyb200_stream s);
+int ptyb200_simlar_backward(const ptyb200_cfg* cfg, int32_t B, const float* plane, const float* occu, int32_t Zo, int32_t Yo, int32_t Xo,
+                            float weight, const float* upstream, float* g_plane, ptyb200_stream s);
+
 /* Per-iteration object constraints, in place, no .data re-binding:
  * ptyb200_blur_axis: 1-D Gaussian (odd kernel_size <= 15, weights exp(-x^2/2 sigma^2)/sum) along the middle axis of an array viewed as
  *   (outer, L, inner); pad_mode 0 = reflect (obj_rblur: x pass then y pass = torchvision gaussian_blur, constraints.py:83-99),

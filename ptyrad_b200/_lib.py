@@ -72,6 +72,10 @@ _SIGNATURES = {
     "ptyb200_sparse_forward": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "ptyb200_sparse_grad": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "ptyb200_gaussian_blur5": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
+    "ptyb200_roi_blur": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
+    "ptyb200_roi_blur_adjoint": (C.c_int, [C.POINTER(Cfg), _P, C.c_int32, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "ptyb200_simlar_forward": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "ptyb200_simlar_backward": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P]),
     "ptyb200_blur_axis": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
     "ptyb200_object_constraints": (C.c_int, [C.POINTER(ObjConstraints), _P, _P, C.c_int64, _P, _P]),
     "ptyb200_backward_zero": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, _P, C.c_uint32, _P]),

@@ -626,6 +626,89 @@ int ptyb200_sparse_grad(const ptyb200_cfg* c, const ptyb200_loss_cfg* lc, const 
     return 0;
 }
 
+namespace {
+Blur5 make_blur5(float sigma) {
+    Blur5 b;
+    double sum = 0, k[5];
+    for (int i = 0; i < 5; ++i) { const double t = (i - 2) / (double)sigma; k[i] = exp(-0.5 * t * t); sum += k[i]; }
+    for (int i = 0; i < 5; ++i) b.k[i] = (float)(k[i] / sum);
+    return b;
+}
+}  // namespace
+
+int ptyb200_roi_blur(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const float* obja, const float* objp, const int32_t* crop_pos,
+                     float sigma, float* tmp, float* out_a, float* out_p, ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!idx || !obja || !objp || !crop_pos || !out_a || !out_p) return fail_msg("NULL argument");
+    if (sigma < 0.f) return fail_msg("sigma must be >= 0");
+    if (sigma > 0.f && !tmp) return fail_msg("roi_blur needs tmp (2 x B*M*Z*N*N floats) when sigma > 0");
+    cudaStream_t st = (cudaStream_t)s;
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B, 0};
+    const long long per = (long long)B * c->M * c->Z * c->N * c->N;
+    const dim3 grid((unsigned)((per + 255) / 256), 2);
+    if (sigma > 0.f) {
+        const Blur5 b = make_blur5(sigma);
+        k_roi_blurx<true><<<grid, 256, 0, st>>>(d, b, idx, crop_pos, obja, objp, tmp, tmp + per); CKL();
+        k_blur5<1, false><<<grid.x, 256, 0, st>>>(b, tmp, out_a, per, c->N, c->N); CKL();
+        k_blur5<1, false><<<grid.x, 256, 0, st>>>(b, tmp + per, out_p, per, c->N, c->N); CKL();
+    } else {
+        k_roi_blurx<false><<<grid, 256, 0, st>>>(d, Blur5{}, idx, crop_pos, obja, objp, out_a, out_p); CKL();
+    }
+    return 0;
+}
+
+int ptyb200_roi_blur_adjoint(const ptyb200_cfg* c, const int64_t* idx, int32_t B, const int32_t* crop_pos, float sigma, const float* g_out_a,
+                             const float* g_out_p, float* tmp, float* g_obja, float* g_objp, ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!idx || !crop_pos) return fail_msg("NULL argument");
+    if (sigma < 0.f) return fail_msg("sigma must be >= 0");
+    if ((g_out_a && !g_obja) || (g_out_p && !g_objp)) return fail_msg("a patch gradient was given without its dense gradient buffer");
+    if (sigma > 0.f && !tmp) return fail_msg("roi_blur_adjoint needs tmp (2 x B*M*Z*N*N floats) when sigma > 0");
+    cudaStream_t st = (cudaStream_t)s;
+    Dims d{c->N, c->P, c->M, c->Z, c->Noy, c->Nox, B, 0};
+    const long long per = (long long)B * c->M * c->Z * c->N * c->N;
+    const dim3 grid((unsigned)((per + 255) / 256), 2);
+    if (sigma > 0.f) {
+        const Blur5 b = make_blur5(sigma);
+        if (g_out_a) { k_blur5<1, true><<<grid.x, 256, 0, st>>>(b, g_out_a, tmp, per, c->N, c->N); CKL(); }
+        if (g_out_p) { k_blur5<1, true><<<grid.x, 256, 0, st>>>(b, g_out_p, tmp + per, per, c->N, c->N); CKL(); }
+        k_roi_blurx_adj_scatter<true><<<grid, 256, 0, st>>>(d, b, idx, crop_pos, g_out_a ? tmp : nullptr, g_out_p ? tmp + per : nullptr, g_obja, g_objp); CKL();
+    } else {
+        k_roi_blurx_adj_scatter<false><<<grid, 256, 0, st>>>(d, Blur5{}, idx, crop_pos, g_out_a, g_out_p, g_obja, g_objp); CKL();
+    }
+    return 0;
+}
+
+int ptyb200_simlar_forward(const ptyb200_cfg* c, int32_t B, const float* plane, const float* occu, int32_t Zo, int32_t Yo, int32_t Xo,
+                           float weight, double* sum_out, ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!plane || !occu || !sum_out) return fail_msg("NULL argument");
+    if (c->M < 2 || c->M > 8) return fail_msg("loss_simlar needs 2 <= M <= 8 object modes");
+    if (Zo < 1 || Yo < 1 || Xo < 1 || Zo > c->Z || Yo > c->N || Xo > c->N) return fail_msg("loss_simlar: pooled size must be in [1, input size]");
+    SimlarDims d{B, c->M, c->Z, c->N, Zo, Yo, Xo};
+    const long long cells = (long long)B * Zo * Yo * Xo;
+    unsigned grid = (unsigned)((cells + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_simlar_fwd<<<grid, 256, 0, (cudaStream_t)s>>>(d, plane, occu, (double)weight / (double)cells, sum_out);
+    CKL();
+    return 0;
+}
+
+int ptyb200_simlar_backward(const ptyb200_cfg* c, int32_t B, const float* plane, const float* occu, int32_t Zo, int32_t Yo, int32_t Xo,
+                            float weight, const float* upstream, float* g_plane, ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!plane || !occu || !upstream || !g_plane) return fail_msg("NULL argument");
+    if (c->M < 2 || c->M > 8) return fail_msg("loss_simlar needs 2 <= M <= 8 object modes");
+    if (Zo < 1 || Yo < 1 || Xo < 1 || Zo > c->Z || Yo > c->N || Xo > c->N) return fail_msg("loss_simlar: pooled size must be in [1, input size]");
+    SimlarDims d{B, c->M, c->Z, c->N, Zo, Yo, Xo};
+    const long long cells = (long long)B * Zo * Yo * Xo;
+    unsigned grid = (unsigned)((cells + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_simlar_bwd<<<grid, 256, 0, (cudaStream_t)s>>>(d, plane, occu, (float)((double)weight / (double)cells), upstream, g_plane);
+    CKL();
+    return 0;
+}
+
 int ptyb200_gaussian_blur5(const float* in, float* tmp, float* out, int64_t planes, int32_t H, int32_t W, float sigma,
                            int32_t transpose, ptyb200_stream s) {
     if (!in || !tmp || !out) return fail_msg("NULL argument");

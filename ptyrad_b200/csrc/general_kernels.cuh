@@ -1194,6 +1194,120 @@ template <int AXIS, bool ADJ> __global__ void k_blur5(Blur5 b, const float* __re
     out[e] = acc;
 }
 
+// Object pre-blur (models.py:267-284) without the reference's gather tensor: pass 1 reads the ROI of every (sample, object mode, slice)
+// straight from the dense object and blurs it along x (reflect INSIDE the patch, as torchvision pads the gathered patch), pass 2 is
+// k_blur5<1> along y.  BLUR = false: the plain ROI planes (loss_simlar without blur).  grid (ceil(B*M*Z*N*N / 256), 2 planes: amp, phase)
+template <bool BLUR> __global__ void k_roi_blurx(Dims d, Blur5 bl, const int64_t* __restrict__ idx, const int32_t* __restrict__ crop,
+                                                 const float* __restrict__ obja, const float* __restrict__ objp, float* __restrict__ outa,
+                                                 float* __restrict__ outp) {
+    const long long NN = (long long)d.N * d.N, total = (long long)d.B * d.M * d.Z * NN;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int x = int(e % d.N), y = int((e / d.N) % d.N), mz = int((e / NN) % (d.M * d.Z)), b = int(e / (NN * d.M * d.Z));
+    const int64_t n0 = idx[b];
+    const int cy = crop[2 * n0], cx = crop[2 * n0 + 1];
+    const float* src = (blockIdx.y ? objp : obja) + ((size_t)mz * d.Noy + cy + y) * d.Nox + cx;
+    float acc;
+    if (BLUR) {
+        acc = 0.f;
+#pragma unroll
+        for (int dlt = -2; dlt <= 2; ++dlt) {
+            const int o = x + dlt;
+            if (o < 0 || o >= d.N) continue;
+            acc += blur_w(bl, x, o, d.N) * src[o];
+        }
+    } else acc = src[x];
+    (blockIdx.y ? outp : outa)[e] = acc;
+}
+// adjoint of the pair above for patch gradients that were already taken through the adjoint of the y pass (k_blur5<1, true>): adjoint
+// along x (5-point gather) and scatter-ADD into the dense object gradient.  Null plane pointers are skipped.
+template <bool BLUR> __global__ void k_roi_blurx_adj_scatter(Dims d, Blur5 bl, const int64_t* __restrict__ idx, const int32_t* __restrict__ crop,
+                                                             const float* __restrict__ ga_patch, const float* __restrict__ gp_patch,
+                                                             float* __restrict__ g_obja, float* __restrict__ g_objp) {
+    const float* in = blockIdx.y ? gp_patch : ga_patch;
+    float* out = blockIdx.y ? g_objp : g_obja;
+    if (!in || !out) return;
+    const long long NN = (long long)d.N * d.N, total = (long long)d.B * d.M * d.Z * NN;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int x = int(e % d.N), y = int((e / d.N) % d.N), mz = int((e / NN) % (d.M * d.Z)), b = int(e / (NN * d.M * d.Z));
+    const int64_t n0 = idx[b];
+    const int cy = crop[2 * n0], cx = crop[2 * n0 + 1];
+    float acc;
+    if (BLUR) {
+        const float* row = in + (e - x);
+        acc = 0.f;
+#pragma unroll
+        for (int dlt = -2; dlt <= 2; ++dlt) {
+            const int o = x + dlt;
+            if (o < 0 || o >= d.N) continue;
+            acc += blur_w(bl, o, x, d.N) * row[o];
+        }
+    } else acc = in[e];
+    atomicAdd(out + ((size_t)mz * d.Noy + cy + y) * d.Nox + cx + x, acc);
+}
+
+// loss_simlar (losses.py:106-141) on ROI planes (B,M,Z,N,N) (from k_roi_blurx / k_blur5: blurred or plain): area interpolation =
+// adaptive average pooling to (Zo,Yo,Xo) (window of output i over an axis of length I: [floor(i I / O), ceil((i+1) I / O)) ), times
+// occu_m, unbiased std over the object modes, mean over (B,Zo,Yo,Xo).  One thread per output cell; M <= 8.
+struct SimlarDims { int B, M, Z, N, Zo, Yo, Xo; };
+__device__ __forceinline__ void pool_window(int i, int I, int O, int& lo, int& hi) {
+    lo = (int)(((long long)i * I) / O);
+    hi = (int)((((long long)(i + 1)) * I + O - 1) / O);
+}
+__device__ __forceinline__ float simlar_cell(const SimlarDims& d, const float* __restrict__ plane, const float* __restrict__ occu, long long cell,
+                                             float (&v)[8], float& mean, int& z0, int& z1, int& y0, int& y1, int& x0, int& x1, int& b) {
+    const int xo = int(cell % d.Xo), yo = int((cell / d.Xo) % d.Yo), zo = int((cell / ((long long)d.Xo * d.Yo)) % d.Zo);
+    b = int(cell / ((long long)d.Xo * d.Yo * d.Zo));
+    pool_window(zo, d.Z, d.Zo, z0, z1); pool_window(yo, d.N, d.Yo, y0, y1); pool_window(xo, d.N, d.Xo, x0, x1);
+    const float inv = 1.0f / float((z1 - z0) * (y1 - y0) * (x1 - x0));
+    mean = 0.f;
+    for (int m = 0; m < d.M; ++m) {
+        const float* pl = plane + ((size_t)b * d.M + m) * d.Z * d.N * d.N;
+        float acc = 0.f;
+        for (int z = z0; z < z1; ++z)
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) acc += pl[((size_t)z * d.N + y) * d.N + x];
+        v[m] = acc * inv * occu[m];
+        mean += v[m];
+    }
+    mean /= float(d.M);
+    float var = 0.f;
+    for (int m = 0; m < d.M; ++m) var += (v[m] - mean) * (v[m] - mean);
+    return sqrtf(var / float(d.M - 1));
+}
+// sum_out[0] += scale * sum over cells of std  (scale = weight / number of cells)
+__global__ void k_simlar_fwd(SimlarDims d, const float* __restrict__ plane, const float* __restrict__ occu, double scale, double* sum_out) {
+    const long long cells = (long long)d.B * d.Zo * d.Yo * d.Xo;
+    float acc[1] = {0.f};
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        float v[8], mean; int z0, z1, y0, y1, x0, x1, b;
+        acc[0] += simlar_cell(d, plane, occu, c, v, mean, z0, z1, y0, y1, x0, x1, b);
+    }
+    __shared__ float red[32];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(sum_out, scale * (double)acc[0]);
+}
+// g_plane (zeroed by the caller) += upstream * d(loss)/d(plane); windows may overlap, hence atomics
+__global__ void k_simlar_bwd(SimlarDims d, const float* __restrict__ plane, const float* __restrict__ occu, float scale, const float* __restrict__ up,
+                             float* __restrict__ g_plane) {
+    const long long cells = (long long)d.B * d.Zo * d.Yo * d.Xo;
+    const float u = up[0] * scale;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        float v[8], mean; int z0, z1, y0, y1, x0, x1, b;
+        const float sd = simlar_cell(d, plane, occu, c, v, mean, z0, z1, y0, y1, x0, x1, b);
+        if (!(sd > 0.f)) continue;
+        const float inv = 1.0f / float((z1 - z0) * (y1 - y0) * (x1 - x0));
+        for (int m = 0; m < d.M; ++m) {
+            const float g = u * (v[m] - mean) / (float(d.M - 1) * sd) * occu[m] * inv;
+            float* pl = g_plane + ((size_t)b * d.M + m) * d.Z * d.N * d.N;
+            for (int z = z0; z < z1; ++z)
+                for (int y = y0; y < y1; ++y)
+                    for (int x = x0; x < x1; ++x) atomicAdd(pl + ((size_t)z * d.N + y) * d.N + x, g);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-iteration object constraints (constraints.py:83-114, 165-208), SURVEY 8f rank 3: streaming passes over the object, in place
 // ------------------------------------------------------------------------------------------------

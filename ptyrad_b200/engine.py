@@ -202,6 +202,70 @@ class SparseLossFunction(torch.autograd.Function):
         return g, None, None, None, None, None
 
 
+class RoiBlurFunction(torch.autograd.Function):
+    """(a, phi) ROI planes (B,M,Z,N,N) of the batch, 5x5-blurred inside the patch when sigma > 0: get_obj_ROI + the Gaussian pre-blur
+    of models.py:251-284 in two native launches, no gather tensor; backward = adjoint blur + scatter-add into the dense gradients."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, obja, objp, idx, crop_pos, cfg, sigma):
+        _require_cuda(obja, objp, idx, crop_pos)
+        obja, objp = obja.contiguous(), objp.contiguous()
+        B = idx.numel()
+        shape = (B, cfg.M, cfg.Z, cfg.N, cfg.N)
+        out_a = torch.empty(shape, dtype=torch.float32, device=obja.device)
+        out_p = torch.empty_like(out_a)
+        tmp = torch.empty((2,) + shape, dtype=torch.float32, device=obja.device) if sigma > 0 else None
+        _lib.check(_lib.lib().ptyb200_roi_blur(C.byref(cfg), ptr(idx), B, ptr(obja), ptr(objp), ptr(crop_pos), float(sigma), ptr(tmp),
+                                               ptr(out_a), ptr(out_p), _stream()))
+        ctx.cfg, ctx.sigma, ctx.idx, ctx.crop_pos, ctx.shape_obj = cfg, float(sigma), idx, crop_pos, obja.shape
+        return out_a, out_p
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, ga, gp):
+        cfg, B = ctx.cfg, ctx.idx.numel()
+        need_a, need_p = ctx.needs_input_grad[0] and ga is not None, ctx.needs_input_grad[1] and gp is not None
+        dev = ctx.idx.device
+        g_obja = torch.zeros(ctx.shape_obj, dtype=torch.float32, device=dev) if need_a else None
+        g_objp = torch.zeros(ctx.shape_obj, dtype=torch.float32, device=dev) if need_p else None
+        ga = ga.contiguous().float() if need_a else None
+        gp = gp.contiguous().float() if need_p else None
+        tmp = torch.empty((2, B, cfg.M, cfg.Z, cfg.N, cfg.N), dtype=torch.float32, device=dev) if ctx.sigma > 0 else None
+        if need_a or need_p:
+            _lib.check(_lib.lib().ptyb200_roi_blur_adjoint(C.byref(cfg), ptr(ctx.idx), B, ptr(ctx.crop_pos), ctx.sigma, ptr(ga), ptr(gp), ptr(tmp),
+                                                           ptr(g_obja), ptr(g_objp), _stream()))
+        return g_obja, g_objp, None, None, None, None
+
+
+class SimlarFunction(torch.autograd.Function):
+    """weight * mean over the pooled batch volume of std_m(occu_m * area_pool(plane)) (losses.py:113-138) for one set of ROI planes
+    (B,M,Z,N,N); area interpolation, std and mean in one native kernel, backward in another."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, plane, occu, cfg, out_dims, weight):
+        _require_cuda(plane, occu)
+        plane = plane.contiguous()
+        B = plane.shape[0]
+        acc = torch.zeros(1, dtype=torch.float64, device=plane.device)
+        _lib.check(_lib.lib().ptyb200_simlar_forward(C.byref(cfg), B, ptr(plane), ptr(occu), int(out_dims[0]), int(out_dims[1]), int(out_dims[2]),
+                                                     float(weight), ptr(acc), _stream()))
+        ctx.save_for_backward(plane, occu)
+        ctx.cfg, ctx.out_dims, ctx.weight = cfg, tuple(int(v) for v in out_dims), float(weight)
+        return acc[0].to(torch.float32)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        plane, occu = ctx.saved_tensors
+        gp = torch.zeros_like(plane)
+        up = g.reshape(1).to(torch.float32).contiguous()
+        _lib.check(_lib.lib().ptyb200_simlar_backward(C.byref(ctx.cfg), plane.shape[0], ptr(plane), ptr(occu), *ctx.out_dims, ctx.weight, ptr(up),
+                                                      ptr(gp), _stream()))
+        return gp, None, None, None, None
+
+
 class GaussianBlur5Function(torch.autograd.Function):
     """5x5 Gaussian blur, reflect padding, last two dims (torchvision gaussian_blur(kernel_size=5); models.py:275-284,379-380,
     losses.py:125,134); backward = the adjoint kernel."""

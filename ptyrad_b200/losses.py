@@ -5,14 +5,17 @@ poissn, pacbed, sparse, simlar])``, same key order of ``loss_params`` (it define
 reconstruction.py:687,769); inactive terms are 0-dim zeros.  The three data terms are one native reduction +
 one native gradient kernel (``engine.DataLossFunction``); ``loss_sparse`` is evaluated on the batch ROIs natively when
 ``object_patches`` is the ``LazyPatches`` handle our model hands out, and with plain tensor ops when a caller passes a
-materialised patch tensor.  ``loss_simlar`` (mixed-object regulariser) is tensor ops on materialised patches.
+materialised patch tensor.  ``loss_simlar`` (mixed-object regulariser) is native too on those handles (ROI planes
+blurred straight from the dense object, area interpolation + std + mean in one kernel).
 """
 from __future__ import annotations
 
 import torch
 
 from . import engine
-from .models import LazyPatches, gaussian_blur5
+import math
+
+from .models import LazyPatches, PatchPlanes, gaussian_blur5
 
 
 class CombinedLoss(torch.nn.Module):
@@ -64,18 +67,41 @@ class CombinedLoss(torch.nn.Module):
         return sp["weight"] * (objp_patches.abs().pow(n).mean(dim=(0, 2, 3, 4)).pow(1.0 / n) * omode_occu).sum()
 
     def get_loss_simlar(self, object_patches, omode_occu):
+        """losses.py:106-141.  With the handles our model hands out (LazyPatches / PatchPlanes) everything is native: ROI planes
+        gathered and 5x5-blurred straight from the dense object (engine.RoiBlurFunction), then area interpolation + std over the
+        object modes + mean in one kernel (engine.SimlarFunction).  A foreign, materialised patch tensor takes plain tensor ops."""
         s = self.loss_params["loss_simlar"]
         if not s["state"]:
             return torch.zeros((), dtype=torch.float32, device=omode_occu.device)
-        if isinstance(object_patches, LazyPatches):
-            object_patches = object_patches.materialize()
         sf = s.get("scale_factor")
+        blur = s.get("blur_std") or 0
+        native = isinstance(object_patches, (LazyPatches, PatchPlanes)) and omode_occu.is_cuda and 2 <= omode_occu.numel() <= 8
+        if native:
+            if isinstance(object_patches, LazyPatches):
+                m = object_patches.model
+                cfg = m._cfg(False)
+                a, p = engine.RoiBlurFunction.apply(m.opt_obja, m.opt_objp, object_patches.idx, m.crop_pos, cfg, float(blur))
+            else:                                          # pre-blurred planes (obj_preblur_std): loss_simlar's own blur on top
+                a, p = object_patches.a, object_patches.p
+                if blur:
+                    a, p = gaussian_blur5(a, blur), gaussian_blur5(p, blur)
+                B_, M_, Z_, N_ = a.shape[0], a.shape[1], a.shape[2], a.shape[-1]
+                cfg = engine.make_cfg(N_, 1, M_, Z_, N_, N_, B_, 0, 0, 0, 1.0, 1.0)
+            f = tuple(sf) if sf is not None else (1, 1, 1)
+            dims = (int(math.floor(a.shape[2] * f[0])), int(math.floor(a.shape[3] * f[1])), int(math.floor(a.shape[4] * f[2])))
+            tot = torch.zeros((), dtype=torch.float32, device=omode_occu.device)
+            for name, x in (("amplitude", a), ("phase", p)):
+                if s["obj_type"] in (name, "both"):
+                    tot = tot + engine.SimlarFunction.apply(x, omode_occu, cfg, dims, float(s["weight"]))
+            return tot
+        if isinstance(object_patches, (LazyPatches, PatchPlanes)):
+            object_patches = object_patches.materialize()
         tot = torch.zeros((), dtype=torch.float32, device=omode_occu.device)
         for name, x in (("amplitude", object_patches[..., 0]), ("phase", object_patches[..., 1])):
             if s["obj_type"] not in (name, "both"):
                 continue
-            if s.get("blur_std"):
-                x = gaussian_blur5(x, s["blur_std"])
+            if blur:
+                x = gaussian_blur5(x, blur)
             if sf is not None and any(f != 1 for f in sf):
                 x = torch.nn.functional.interpolate(x, scale_factor=tuple(sf), mode="area")
             tot = tot + (x * omode_occu[:, None, None, None]).std(1).mean()
@@ -83,7 +109,7 @@ class CombinedLoss(torch.nn.Module):
 
     def forward(self, model_DP, measured_DP, object_patches, omode_occu):
         single, poissn, pacbed = self._data_losses(model_DP, measured_DP)
-        objp = object_patches if isinstance(object_patches, LazyPatches) else object_patches[..., 1]
+        objp = object_patches if isinstance(object_patches, LazyPatches) else object_patches[..., 1]      # PatchPlanes: the phase plane
         losses = [single, poissn, pacbed, self.get_loss_sparse(objp, omode_occu), self.get_loss_simlar(object_patches, omode_occu)]
         return sum(losses), losses
 

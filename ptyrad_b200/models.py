@@ -54,6 +54,33 @@ class LazyPatches:
         return getattr(self.materialize(), name)
 
 
+class PatchPlanes:
+    """The pre-blurred ROI patches as two planes (amplitude, phase), each (B,omode,Nz,Ny,Nx): ``patches[..., 0]`` / ``patches[..., 1]``
+    (how the losses read ``_current_object_patches``, losses.py:152-153) return the planes themselves; anything else gets the stacked
+    (B,omode,Nz,Ny,Nx,2) tensor of the reference (models.py:264,284)."""
+
+    def __init__(self, a, p):
+        self.a, self.p = a, p
+        self._t = None
+
+    def materialize(self):
+        if self._t is None:
+            self._t = torch.stack([self.a, self.p], -1)
+        return self._t
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2 and key[0] is Ellipsis and key[1] in (0, 1):
+            return self.p if key[1] else self.a
+        return self.materialize()[key]
+
+    @property
+    def shape(self):
+        return torch.Size(tuple(self.a.shape) + (2,))
+
+    def __getattr__(self, name):
+        return getattr(self.materialize(), name)
+
+
 class PtychoAD(nn.Module):
     """See module docstring.  Constructor signature = reference ``models.py:70``."""
 
@@ -349,11 +376,11 @@ class PtychoAD(nn.Module):
         cfg = self._cfg(stash_fourier=bool(need_prop) and torch.is_grad_enabled(), patch_mode=preblur)
         st = dict(cfg=cfg, idx=idx, crop_pos=self.crop_pos, H=self.H, occu=self.omode_occu, change_thickness=self.change_thickness)
         if preblur:
-            # pre-blurred ROIs: gather + blur are tensor ops (as in the reference), the multislice kernels take the per-sample
-            # patch stacks as their "object" (patch mode) and hand the patch gradients back to autograd
-            patches = self.get_obj_patches(idx)
-            obja, objp = patches[..., 0].contiguous(), patches[..., 1].contiguous()
-            self._current_object_patches = patches
+            # pre-blurred ROIs (models.py:267-284): gather + 5x5 blur in two native launches straight from the dense object (no gather
+            # tensor; backward = adjoint blur + scatter-add); the multislice kernels take the per-sample planes as their "object" (patch
+            # mode).  Blurring once per (sample, object mode, slice) instead of inside the wave kernels: DESIGN 3.6.
+            obja, objp = engine.RoiBlurFunction.apply(self.opt_obja, self.opt_objp, idx, self.crop_pos, self._cfg(False), float(self.obj_preblur_std))
+            self._current_object_patches = PatchPlanes(obja, objp)
         else:
             obja, objp = self.opt_obja, self.opt_objp
             self._current_object_patches = LazyPatches(self, idx)

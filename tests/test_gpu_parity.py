@@ -890,3 +890,35 @@ def test_chunked_step_rejects_what_it_cannot_separate():
     model = PtychoAD(iv, mp, device="cuda", verbose=False)
     with pytest.raises(ValueError):
         recon_batch(model, CombinedLoss(lp, device="cuda"), FusedAdam(model.optimizable_params), np.arange(6), GradArena(model), direct=True, chunk=2)
+
+
+@pytest.mark.parametrize("sigma", [0.0, 1.0])
+def test_roi_blur_kernels_against_gather_plus_blur(sigma):
+    """ptyb200_roi_blur / _adjoint (ROI planes gathered and 5x5-blurred straight from the dense object, models.py:251-284) against the
+    reference formulation: advanced-index gather (models.py:261-264) followed by the separable reflect-padded blur, forward and
+    gradient (scatter-add of the adjoint blur)."""
+    from oracle.ptycho_torch import _gauss5
+    from ptyrad_b200 import PtychoAD, engine
+    from workloads import make_inputs
+    iv, mp, lp = make_inputs("T128m", seed=41)
+    model = PtychoAD(iv, mp, device="cuda", verbose=False)
+    idx = model._index_tensor(np.array([0, 3, 4, 9, 15]))
+    a, p = engine.RoiBlurFunction.apply(model.opt_obja, model.opt_objp, idx, model.crop_pos, model._cfg(False), sigma)
+    ga, gp = torch.randn_like(a), torch.randn_like(p)
+    (a * ga).sum().add((p * gp).sum()).backward()
+    got = (a.detach().cpu().double(), p.detach().cpu().double(), model.opt_obja.grad.cpu().double(), model.opt_objp.grad.cpu().double())
+    oa = model.opt_obja.detach().cpu().double().requires_grad_(True)
+    op = model.opt_objp.detach().cpu().double().requires_grad_(True)
+    N = a.shape[-1]
+    crop = model.crop_pos.cpu().long()
+    ar = torch.arange(N)
+    gy = crop[idx.cpu(), 0, None, None] + ar[None, :, None]
+    gx = crop[idx.cpu(), 1, None, None] + ar[None, None, :]
+    ra, rp = oa[:, :, gy, gx].permute(2, 0, 1, 3, 4), op[:, :, gy, gx].permute(2, 0, 1, 3, 4)
+    if sigma:
+        ra, rp = _gauss5(ra, sigma), _gauss5(rp, sigma)
+    (ra * ga.cpu().double()).sum().add((rp * gp.cpu().double()).sum()).backward()
+    for g, r in zip(got, (ra.detach(), rp.detach(), oa.grad, op.grad)):
+        assert rel(g.numpy(), r.numpy()) < 2e-6
+    if not sigma:
+        assert torch.equal(a.detach().cpu(), ra.detach().float())          # the plain gather is a bit-exact copy
