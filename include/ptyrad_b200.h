@@ -238,6 +238,11 @@ int ptyb200_object_constraints(const ptyb200_obj_constraints* oc, float* obja, f
 int ptyb200_backward_zero(const ptyb200_cfg* cfg, int32_t B, void* workspace, float* g_probe, float* g_shifts, uint32_t need_mask,
                           ptyb200_stream s);
 
+/* workspace_dst's gradient accumulators += workspace_src's (two parts of one batch that ran their adjoints concurrently on two
+ * streams, each into its own workspace; both sized with the same cfg and B). */
+int ptyb200_accumulators_add(const ptyb200_cfg* cfg, int32_t B, void* workspace_dst, const void* workspace_src, uint32_t need_mask,
+                             ptyb200_stream s);
+
 /* Completion of a chunked step (see PTYB200_ACC_*): object polar backward, probe-spectrum inverse FFT and the batch-level `scale`
  * (device float, e.g. from ptyb200_loss_scale; NULL = 1) applied to every requested gradient.  Same buffers / need_mask as the
  * ptyb200_backward calls whose accumulators (in `workspace`) it completes; tilt / thickness gradients are not available chunked. */

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ptyb200_blur_axis": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_int32, _P]),
     "ptyb200_object_constraints": (C.c_int, [C.POINTER(ObjConstraints), _P, _P, C.c_int64, _P, _P]),
     "ptyb200_backward_zero": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, _P, C.c_uint32, _P]),
+    "ptyb200_accumulators_add": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, C.c_uint32, _P]),
     "ptyb200_backward_finish": (C.c_int, [C.POINTER(Cfg), C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P]),
     "ptyb200_loss_finalize": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), C.c_int32, _P, _P, _P, _P]),
     "ptyb200_loss_scale": (C.c_int, [C.POINTER(Cfg), C.POINTER(LossCfg), C.c_int32, _P, _P, _P, _P]),

@@ -783,6 +783,37 @@ int ptyb200_backward_zero(const ptyb200_cfg* c, int32_t B, void* workspace, floa
     return 0;
 }
 
+int ptyb200_accumulators_add(const ptyb200_cfg* c, int32_t B, void* workspace_dst, const void* workspace_src, uint32_t need_mask,
+                             ptyb200_stream s) {
+    if (int r = check_cfg(c, B)) return r;
+    if (!workspace_dst || !workspace_src) return fail_msg("NULL argument");
+    if (c->reserved[1] & 1) return fail_msg("accumulators_add does not cover patch mode");
+    cudaStream_t st = (cudaStream_t)s;
+    Workspace wd = carve(*c, B, workspace_dst), ws = carve(*c, B, const_cast<void*>(workspace_src));
+    const size_t obj = (size_t)c->M * c->Z * c->Noy * c->Nox, pn8 = (size_t)c->P * c->N * c->N * 8;
+    auto add = [&](void* d, const void* a, size_t bytes) -> int {
+        const size_t n4 = bytes / 16;                                  // every accumulator is a multiple of 16 bytes, 256-byte aligned
+        k_add_into<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((float4*)d, (const float4*)a, n4);
+        CKL();
+        return 0;
+    };
+    if (need_mask & PTYB200_NEED_OBJ) {
+        if (use_fused(*c)) {
+            fused128::Scratch a = fused64::covers(*c) ? fused64::carve_scratch(*c, B, wd.fused) : fused128::carve_scratch(*c, B, wd.fused);
+            fused128::Scratch b = fused64::covers(*c) ? fused64::carve_scratch(*c, B, ws.fused) : fused128::carve_scratch(*c, B, ws.fused);
+            if (int r = add(a.gOpack, b.gOpack, obj * 16)) return r;
+        } else if (int r = add(wd.gO, ws.gO, (obj * 8 + 15) & ~size_t(15))) return r;
+    }
+    if ((need_mask & PTYB200_NEED_PROBE) && c->shift_probes) {
+        if (use_fused(*c)) {
+            fused128::Scratch a = fused64::covers(*c) ? fused64::carve_scratch(*c, B, wd.fused) : fused128::carve_scratch(*c, B, wd.fused);
+            fused128::Scratch b = fused64::covers(*c) ? fused64::carve_scratch(*c, B, ws.fused) : fused128::carve_scratch(*c, B, ws.fused);
+            if (int r = add(a.gPhatF, b.gPhatF, pn8)) return r;
+        } else if (int r = add(wd.gPhatT, ws.gPhatT, pn8)) return r;
+    }
+    return 0;
+}
+
 int ptyb200_backward_finish(const ptyb200_cfg* c, int32_t B, const float* obja, const float* objp, void* workspace, float* g_obja,
                             float* g_objp, float* g_probe, float* g_shifts, uint32_t need_mask, const float* scale, ptyb200_stream s) {
     if (int r = check_cfg(c, B)) return r;

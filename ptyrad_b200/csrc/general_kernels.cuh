@@ -958,6 +958,10 @@ __global__ void k_obj_finish(const float2* __restrict__ gO, const float* __restr
     if (add) { ga[i] += va; gp[i] += vp; }      // the gradient arrays already hold other terms (loss_sparse, written early on a side stream)
     else { ga[i] = va; gp[i] = vp; }
 }
+__global__ void k_add_into(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n4) { float4 a = dst[i]; const float4 b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; }
+}
 __global__ void k_scale(float* __restrict__ x, size_t n, const float* __restrict__ scale) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] *= scale[0];

@@ -13,6 +13,7 @@ are never broadcast.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -75,10 +76,10 @@ def shard_indices(indices, rank: int, world: int):
 _SIDE = {}
 
 
-def _side_stream(dev):
-    """One side stream per device for work that is independent of the multislice kernels (forked from / joined into the caller's
-    stream; a stream capture records it as a parallel branch)."""
-    key = (dev.type, dev.index)
+def _side_stream(dev, which: str = "aux"):
+    """Side streams per device (forked from / joined into the caller's stream; a stream capture records them as parallel branches):
+    "aux" for work that is independent of the multislice kernels, "half" for the second half of a split step."""
+    key = (dev.type, dev.index, which)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
     return _SIDE[key]
@@ -187,6 +188,116 @@ def _direct_grads_chunked(model, loss_fn, idx, meas: MeasurementView, arena: Gra
             _lib.check(lib.ptyb200_sparse_grad(C.byref(base), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
                                                ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), st))
     return losses
+
+
+def _direct_grads_split(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, zero_arena: bool = False):
+    """`_direct_grads` with the batch cut in two halves that run forward -> unscaled loss gradient -> adjoint on TWO streams, each into
+    its own workspace; the accumulators are added and completed once, with the batch-level factor (the machinery of the chunked
+    step).  Why: the fused kernels run one tile per SM, so a kernel over T tiles takes ceil(T / 148) waves -- C2's 1536 tiles are
+    10.38 waves, and the last, 38 %-full wave of the forward and of the adjoint costs 0.14 ms of a 2.54 ms step.  Four half-size
+    kernels on two streams fill each other's partial waves (the adjoint of the first half overlaps the forward of the second), so
+    only the very last wave of the step is partial.  Loss and gradients are those of the whole batch.  MEASURED (C2, B200): 2.819 ms
+    against 2.534 ms unsplit -- concurrent forward (stash writes) and adjoint (stash reads) kernels cost more than the tails; kept as
+    an option (`recon_batch(split=True)`), off by default."""
+    lib = _lib.lib()
+    dev = model.opt_obja.device
+    B = idx.numel()
+    obja, objp, probe = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous(), model.opt_probe.data.contiguous()
+    dz, shifts = model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
+    tilts = model.opt_obj_tilts.data.contiguous()
+    n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
+    n_probe = model.opt_probe.requires_grad
+    n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
+    need = (_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0)
+    cuts = [(0, B // 2), (B // 2, B)]
+    cap = max(hi - lo for lo, hi in cuts)
+    cfg = model._cfg(stash_fourier=False)
+    cfg.reserved[0] = cap
+    Hbase = engine.propagator(cfg, dz) if model.change_thickness else model.H
+    ws_bytes = lib.ptyb200_workspace_bytes(C.byref(cfg), cap)
+    if ws_bytes == 0:
+        _lib.check(1)
+    ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in cuts]
+    dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
+    G = torch.empty_like(dp)
+    tl = tilts if cfg.tilt_mode else None
+    sh = shifts if cfg.shift_probes else None
+    lcfg = loss_fn.lcfg()
+    losses = torch.zeros(5, dtype=torch.float32, device=dev)
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    sparse = bool(lcfg.sparse_state)
+    ones = getattr(model, "_ones3", None)
+    if ones is None or ones.device != dev:
+        ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
+
+    def out(p, wanted):
+        if not wanted:
+            return None
+        return p.grad if p.requires_grad else torch.empty_like(p.data)
+
+    g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
+    g_probe, g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
+    if sparse:
+        Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
+        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    aux, half = _side_stream(dev), _side_stream(dev, "half")
+    aux.wait_stream(cur)
+    half.wait_stream(cur)
+    with torch.cuda.stream(aux):                              # independent of the multislice kernels (see _direct_grads)
+        sst = engine._stream()
+        if zero_arena:
+            arena.zero()
+        if need:
+            for w in ws:
+                _lib.check(lib.ptyb200_backward_zero(C.byref(cfg), cap, ptr(w), ptr(g_probe), ptr(g_shifts), need, sst))
+        if sparse:
+            _lib.check(lib.ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                                  C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), sst))
+            if need and model.opt_objp.requires_grad:
+                _lib.check(lib.ptyb200_sparse_grad(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
+                                                   ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), sst))
+    cfg_f = type(cfg).from_buffer_copy(cfg)
+    cfg_f.reserved[4] = _lib.ACC_KEEP_STATS | _lib.ACC_NO_LOSS_FINAL          # `stats` was zeroed above, once for both halves
+    cfg_b = type(cfg).from_buffer_copy(cfg)
+    cfg_b.reserved[4] = _lib.ACC_KEEP_GRADS | _lib.ACC_NO_FINISH
+    for (lo, hi), stream, w in zip(cuts, (cur, half), ws):
+        n = hi - lo
+        ci, cr = idx[lo:hi], meas.idx[lo:hi]
+        with torch.cuda.stream(stream):
+            st = engine._stream()
+            _lib.check(lib.ptyb200_forward_loss(C.byref(cfg_f), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh),
+                                                ptr(Hbase), ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp[lo:hi]), ptr(w), C.byref(lcfg),
+                                                ptr(meas.all), ptr(cr), engine.mref(meas.mcfg), ptr(meas.padded), ptr(losses), ptr(stats), None, st))
+            if need:
+                _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp[lo:hi]), ptr(meas.all), ptr(cr), n, None, None, None,
+                                                 ptr(G[lo:hi]), engine.mref(meas.mcfg), ptr(meas.padded), st))
+                stream.wait_stream(aux)                       # accumulators zeroed
+                _lib.check(lib.ptyb200_backward(
+                    C.byref(cfg_b), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
+                    ptr(model.omode_occu), ptr(G[lo:hi]), ptr(w), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), None, None, need, st))
+    cur.wait_stream(half)
+    cur.wait_stream(aux)
+    st = engine._stream()
+    _lib.check(lib.ptyb200_loss_finalize(C.byref(cfg), C.byref(lcfg), B, ptr(stats), None, ptr(losses), st))
+    if need:
+        scale = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.check(lib.ptyb200_loss_scale(C.byref(cfg), C.byref(lcfg), B, ptr(stats), ptr(ones), ptr(scale), st))
+        _lib.check(lib.ptyb200_accumulators_add(C.byref(cfg), cap, ptr(ws[0]), ptr(ws[1]), need, st))
+        cfg_e = type(cfg).from_buffer_copy(cfg)
+        cfg_e.reserved[4] = _lib.ACC_ADD_OBJ                  # the arena was zeroed and holds the loss_sparse term
+        _lib.check(lib.ptyb200_backward_finish(C.byref(cfg_e), cap, ptr(obja), ptr(objp), ptr(ws[0]), ptr(g_obja), ptr(g_objp), ptr(g_probe),
+                                               ptr(g_shifts), need, ptr(scale), st))
+    return losses
+
+
+def split_step_eligible(model, loss_fn, B: int) -> bool:
+    """What `recon_batch(split=True)` covers: the fused 128^2 kernels (one tile per SM, ragged last wave) and what a chunked step
+    needs (one separable data term, no pacbed / detector blur / tilt-thickness gradients)."""
+    if not chunked_step_eligible(model, loss_fn) or B < 4:
+        return False
+    N = model.opt_probe.shape[1]
+    return N == 128 and model.kernel_path != _lib.PATH_GENERAL
 
 
 def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, zero_arena: bool = False):
@@ -299,13 +410,17 @@ def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, 
 
 def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = None, world: int = 1,
                 grad_accumulation: int = 1, do_step: bool = True, measurements=None, direct: bool | None = None,
-                first_of_group: bool = True, chunk: int = 0):
+                first_of_group: bool = True, chunk: int = 0, split: bool | None = None):
     """One batch: (zero grads), forward, loss, backward, (all-reduce), optimizer step.  Returns the 5 loss terms as a device
     tensor (no host sync).  `direct` (default: whenever eligible) takes the autograd-free route of `_direct_grads`.
 
     Gradient accumulation (reconstruction.py:750-760): pass `grad_accumulation` = group size, `first_of_group` = True only for the
     first batch of a group (gradients are zeroed there and nowhere else) and `do_step` = True only for the last one.
 
+    `split=True` runs the batch as two halves on two streams (`_direct_grads_split`; same loss and gradients).  Off by default: it
+    was built to let the partial last waves of the forward and adjoint kernels fill each other, and measured SLOWER at C2 (2.534 ->
+    2.819 ms, profiles/r02/ab_split_step.txt): the write-heavy forward and the read-heavy adjoint slow each other down by more than
+    the two 38 %-full waves cost.
     `chunk` > 0 bounds the memory of the step: the batch runs through the kernels `chunk` samples at a time (one chunk's wave stash
     alive) and still yields the loss and gradients of the whole batch (`_direct_grads_chunked`; direct route only)."""
     if world > 1 and arena is None:
@@ -321,6 +436,8 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         if chunk and idx.numel() > chunk:
             arena.zero()
             losses = _direct_grads_chunked(model, loss_fn, idx, meas, arena, int(chunk))
+        elif split:
+            losses = _direct_grads_split(model, loss_fn, idx, meas, arena, zero_arena=True)
         else:
             losses = _direct_grads(model, loss_fn, idx, meas, arena, zero_arena=True)     # zeroes the arena itself, on its side stream
         if world > 1:
@@ -371,13 +488,13 @@ class GraphedStep:
     """
 
     def __init__(self, model, loss_fn, optimizer, arena: GradArena, batch_size: int, grad_accumulation: int = 1, warmup: int = 2,
-                 world: int = 1, stream_measurements: bool = False, chunk: int = 0):
+                 world: int = 1, stream_measurements: bool = False, chunk: int = 0, split: bool = False):
         if grad_accumulation != 1:
             raise ValueError("GraphedStep captures a whole step (zero, forward, adjoint, exchange, optimizer): use the eager "
                              "recon_batch / recon_step for gradient accumulation")
         self.model, self.loss_fn, self.opt, self.arena = model, loss_fn, optimizer, arena
         self.B = int(batch_size)
-        self.world, self.warmup, self.chunk = world, warmup, int(chunk)
+        self.world, self.warmup, self.chunk, self.split = world, warmup, int(chunk), bool(split)
         dev = model.opt_obja.device
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.params = list(model.optimizable_tensors.values())
@@ -432,7 +549,7 @@ class GraphedStep:
         self._rebind()
         snap_p = [p.detach().clone() for p in self.params]
         snap_o = self._snapshot_opt()
-        run = lambda: recon_batch(model, self.loss_fn, self.opt, self.idx, self.arena, self.world, measurements=self._mv, chunk=self.chunk)
+        run = lambda: recon_batch(model, self.loss_fn, self.opt, self.idx, self.arena, self.world, measurements=self._mv, chunk=self.chunk, split=self.split)
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):

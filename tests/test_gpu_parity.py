@@ -922,3 +922,42 @@ def test_roi_blur_kernels_against_gather_plus_blur(sigma):
         assert rel(g.numpy(), r.numpy()) < 2e-6
     if not sigma:
         assert torch.equal(a.detach().cpu(), ra.detach().float())          # the plain gather is a bit-exact copy
+
+
+@pytest.mark.parametrize("case", ["T128", "T128-noshift", "T128m", "C2d", "C2d-graph"])
+def test_split_step_equals_the_whole_batch_step(case):
+    """The two-stream split of a step (two halves, each forward -> unscaled loss gradient -> adjoint on its own stream and into its own
+    workspace, accumulators added and completed once) must give the loss and gradients of the whole batch."""
+    from dataclasses import replace
+    from ptyrad_b200 import PtychoAD, CombinedLoss
+    from ptyrad_b200.optim import FusedAdam
+    from ptyrad_b200.step import GradArena, GraphedStep, recon_batch, split_step_eligible
+    from workloads import make_inputs, CONFIGS
+    name = case.split("-")[0]
+    cfg = CONFIGS[name]
+    if "noshift" in case:
+        cfg = replace(cfg, lr_shifts=0.0)
+    iv, mp, lp = make_inputs(cfg, seed=27)
+    idx = np.arange(cfg.batch, dtype=np.int64)
+    out = {}
+    for split in (False, True):
+        model = PtychoAD(iv, mp, device="cuda", verbose=False)
+        loss_fn = CombinedLoss(lp, device="cuda")
+        opt = FusedAdam(model.optimizable_params)
+        arena = GradArena(model)
+        assert split_step_eligible(model, loss_fn, cfg.batch)
+        if "graph" in case:
+            losses = GraphedStep(model, loss_fn, opt, arena, cfg.batch, split=split)(idx)     # captured as a fork / join graph
+        else:
+            losses = recon_batch(model, loss_fn, opt, idx, arena, direct=True, split=split)
+        torch.cuda.synchronize()
+        out[split] = (losses.cpu().numpy().copy(), {k: (None if t.grad is None else t.grad.detach().cpu().numpy().copy()) for k, t in model.optimizable_tensors.items()},
+                      {k: t.detach().cpu().numpy().copy() for k, t in model.optimizable_tensors.items()})
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=2e-6, atol=1e-9)
+    for k, g in out[False][1].items():
+        if g is None:
+            assert out[True][1][k] is None, k
+        else:
+            assert rel(out[True][1][k], g) < (5e-6 if k in ("obja", "objp", "probe") else 2e-4), (k, rel(out[True][1][k], g))
+    for k, v in out[False][2].items():
+        assert rel(out[True][2][k], v) < 3e-6, k
