@@ -147,7 +147,6 @@ class PtychoAD(nn.Module):
             self.loss_iters, self.iter_times, self.dz_iters, self.avg_tilt_iters = [], [], [], []
             self._current_object_patches = None
             self.kernel_path = _lib.PATH_AUTO
-            self.kernel_flags = 0          # cfg.reserved[0]: reserved for kernel experiments (no switch defined at present)
             self.kernel_chunk = 0          # general path: samples per L2-resident chunk (0 = library heuristic; cfg.reserved[2])
             self.kernel_pmodes_per_cta = 0  # general path: probe modes looped over by one CTA (0 = heuristic; cfg.reserved[3])
 
@@ -262,7 +261,6 @@ class PtychoAD(nn.Module):
             Noy = Nox = N
         cfg = engine.make_cfg(N, P, M, Z, Noy, Nox, self.crop_pos.shape[0], self.shift_probes, self._tilt_mode(), stash_fourier,
                               self._dx_host, self._lambd_host, 1e-10, self.kernel_path)
-        cfg.reserved[0] = int(self.kernel_flags)
         cfg.reserved[1] = 1 if patch_mode else 0
         cfg.reserved[2] = int(self.kernel_chunk)
         cfg.reserved[3] = int(self.kernel_pmodes_per_cta)
