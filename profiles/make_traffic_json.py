@@ -32,6 +32,7 @@ def main():
         return v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[u]
 
     kernels = {}
+    sections = {}                                       # general path: all launches of a section (one step) summed
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         short = name.split("<")[0].split("::")[-1].split("(")[0].strip()
@@ -39,6 +40,13 @@ def main():
             short = short[5:]
         kernels.setdefault(short, dict(dram_read_gb=round(gb(r, "dram__bytes_read.sum"), 6), dram_write_gb=round(gb(r, "dram__bytes_write.sum"), 6),
                                        duration_ms=round(ms(r), 6)))
+        sec = "adjoint_section" if short.startswith("k_bwd") else ("forward_section" if short.startswith(("k_fwd", "k_init_shift")) else None)
+        if sec and dominant.endswith("_section"):
+            a = sections.setdefault(sec, dict(dram_read_gb=0.0, dram_write_gb=0.0, duration_ms=0.0, launches=0))
+            a["dram_read_gb"] += gb(r, "dram__bytes_read.sum"); a["dram_write_gb"] += gb(r, "dram__bytes_write.sum")
+            a["duration_ms"] += ms(r); a["launches"] += 1
+    for k, a in sections.items():
+        kernels[k] = {kk: (round(v, 6) if isinstance(v, float) else v) for kk, v in a.items()}
     json.dump(dict(source=f"ncu --set full --clock-control none, tools/prof_step.py {cfg} {path}, one launch each ({os.path.basename(rep)})",
                    csrc_sha256=bench.csrc_hash(), batch=batch, path=path, dominant=dominant, kernels=kernels), sys.stdout, indent=1)
     print()

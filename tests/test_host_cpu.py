@@ -269,3 +269,36 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
                 assert "adjoint_np" not in txt and "ptycho_torch" not in txt, f
+
+
+def test_chunked_and_split_step_eligibility():
+    """A chunked / split step needs dL/dI = (scalar of the batch sums) x (per-pixel term): exactly one of loss_single / loss_poissn,
+    no loss_pacbed, no detector blur, no tilt / thickness gradients (ptyrad_b200/step.py)."""
+    from ptyrad_b200.losses import CombinedLoss
+    from ptyrad_b200.step import chunked_step_eligible, split_step_eligible
+    from workloads import default_loss_params
+    m, iv, mp, lp = _model(lr_shifts=1e-4)
+    assert chunked_step_eligible(m, CombinedLoss(lp, device="cpu"))
+    both = default_loss_params("single"); both["loss_poissn"]["state"] = True
+    assert not chunked_step_eligible(m, CombinedLoss(both, device="cpu"))
+    pac = default_loss_params("single"); pac["loss_pacbed"]["state"] = True
+    assert not chunked_step_eligible(m, CombinedLoss(pac, device="cpu"))
+    assert chunked_step_eligible(m, CombinedLoss(default_loss_params("poissn"), device="cpu"))
+    m.detector_blur_std = 1.0
+    assert not chunked_step_eligible(m, CombinedLoss(lp, device="cpu"))
+    m.detector_blur_std = None
+    assert not split_step_eligible(m, CombinedLoss(lp, device="cpu"), 64)      # N = 32: not the one-tile-per-SM kernels
+    m2, _, _, lp2 = _model(tilt_each=True, lr_tilts=1e-4, lr_dz=1e-4)
+    assert not chunked_step_eligible(m2, CombinedLoss(lp2, device="cpu"))      # tilt / thickness gradients
+
+
+def test_patch_planes_handle():
+    """PatchPlanes (the pre-blurred ROI planes handed out as model._current_object_patches): `[..., 0]` / `[..., 1]` are the planes
+    themselves, anything else sees the stacked (B,omode,Nz,Ny,Nx,2) tensor of the reference (models.py:264,284)."""
+    from ptyrad_b200.models import PatchPlanes
+    a, p = torch.rand(2, 1, 3, 4, 4), torch.rand(2, 1, 3, 4, 4)
+    h = PatchPlanes(a, p)
+    assert h[..., 0] is a and h[..., 1] is p
+    assert h.shape == (2, 1, 3, 4, 4, 2)
+    assert torch.equal(h[0, 0, 1], torch.stack([a, p], -1)[0, 0, 1])
+    assert torch.equal(h.permute(5, 0, 1, 2, 3, 4)[1], p)
