@@ -112,185 +112,6 @@ def chunked_step_eligible(model, loss_fn) -> bool:
     return one and not lp["loss_pacbed"]["state"] and not model.detector_blur_std and not prop
 
 
-def _direct_grads_chunked(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, chunk: int):
-    """`_direct_grads` for a batch that is processed `chunk` samples at a time so that only one chunk's wave stash is alive
-    (SURVEY 8e: memory must not grow with the per-GPU batch; the strong-scaling runs put 2 048 patterns of C4 on one GPU, whose
-    stash alone would be 206 GB).  The result is the gradient of the loss of the WHOLE batch, not a sum of per-chunk losses: every
-    chunk adds its loss sums and runs its adjoint on the unscaled loss gradient into shared accumulators; the batch-level factor is
-    applied once, when the accumulators are turned into gradients (include/ptyrad_b200.h, PTYB200_ACC_*)."""
-    if not chunked_step_eligible(model, loss_fn):
-        raise ValueError("a chunked step needs exactly one of loss_single / loss_poissn, no loss_pacbed, no detector blur and no "
-                         "tilt / thickness gradients")
-    lib = _lib.lib()
-    st = engine._stream()
-    dev = model.opt_obja.device
-    B = idx.numel()
-    obja, objp, probe = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous(), model.opt_probe.data.contiguous()
-    dz, shifts = model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
-    tilts = model.opt_obj_tilts.data.contiguous()
-    n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
-    n_probe = model.opt_probe.requires_grad
-    n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
-    base = model._cfg(stash_fourier=False)
-    base.reserved[0] = chunk                                   # every call lays the workspace out for `chunk` samples
-    Hbase = engine.propagator(base, dz) if model.change_thickness else model.H
-    ws_bytes = lib.ptyb200_workspace_bytes(C.byref(base), chunk)
-    if ws_bytes == 0:
-        _lib.check(1)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    dp = torch.empty((chunk, base.N, base.N), dtype=torch.float32, device=dev)
-    G = torch.empty_like(dp)
-    tl = tilts if base.tilt_mode else None
-    sh = shifts if base.shift_probes else None
-    lcfg = loss_fn.lcfg()
-    losses = torch.zeros(5, dtype=torch.float32, device=dev)
-    stats = torch.empty(8, dtype=torch.float64, device=dev)
-    need = (_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0)
-
-    def out(p, wanted):
-        if not wanted:
-            return None
-        return p.grad if p.requires_grad else torch.empty_like(p.data)
-
-    g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
-    g_probe, g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
-    for i, lo in enumerate(range(0, B, chunk)):
-        hi = min(B, lo + chunk)
-        n = hi - lo
-        cfg = type(base).from_buffer_copy(base)
-        cfg.reserved[4] = _lib.ACC_NO_FINISH | ((_lib.ACC_KEEP_STATS | _lib.ACC_KEEP_GRADS) if i else 0)
-        ci, cr = idx[lo:hi], meas.idx[lo:hi]
-        _lib.check(lib.ptyb200_forward_loss(C.byref(cfg), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
-                                            ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws), C.byref(lcfg), ptr(meas.all), ptr(cr),
-                                            engine.mref(meas.mcfg), ptr(meas.padded), ptr(losses), ptr(stats), None, st))
-        if need:
-            _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(cr), n, None, None, None, ptr(G),
-                                             engine.mref(meas.mcfg), ptr(meas.padded), st))
-            _lib.check(lib.ptyb200_backward(
-                C.byref(cfg), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
-                ptr(model.omode_occu), ptr(G), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), None, None, need, st))
-    _lib.check(lib.ptyb200_loss_finalize(C.byref(base), C.byref(lcfg), B, ptr(stats), None, ptr(losses), st))
-    sparse = bool(lcfg.sparse_state)
-    if sparse:
-        Ssum = torch.empty(base.M, dtype=torch.float64, device=dev)
-        cover = torch.empty(base.Noy * base.Nox, dtype=torch.int32, device=dev)
-        _lib.check(lib.ptyb200_sparse_forward(C.byref(base), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                              C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), st))
-    if need:
-        ones = getattr(model, "_ones3", None)
-        if ones is None or ones.device != dev:
-            ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
-        scale = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.check(lib.ptyb200_loss_scale(C.byref(base), C.byref(lcfg), B, ptr(stats), ptr(ones), ptr(scale), st))
-        _lib.check(lib.ptyb200_backward_finish(C.byref(base), chunk, ptr(obja), ptr(objp), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(g_probe),
-                                               ptr(g_shifts), need, ptr(scale), st))
-        if sparse and model.opt_objp.requires_grad:
-            _lib.check(lib.ptyb200_sparse_grad(C.byref(base), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                               ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), st))
-    return losses
-
-
-def _direct_grads_split(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, zero_arena: bool = False):
-    """`_direct_grads` with the batch cut in two halves that run forward -> unscaled loss gradient -> adjoint on TWO streams, each into
-    its own workspace; the accumulators are added and completed once, with the batch-level factor (the machinery of the chunked
-    step).  Why: the fused kernels run one tile per SM, so a kernel over T tiles takes ceil(T / 148) waves -- C2's 1536 tiles are
-    10.38 waves, and the last, 38 %-full wave of the forward and of the adjoint costs 0.14 ms of a 2.54 ms step.  Four half-size
-    kernels on two streams fill each other's partial waves (the adjoint of the first half overlaps the forward of the second), so
-    only the very last wave of the step is partial.  Loss and gradients are those of the whole batch.  MEASURED (C2, B200): 2.819 ms
-    against 2.534 ms unsplit -- concurrent forward (stash writes) and adjoint (stash reads) kernels cost more than the tails; kept as
-    an option (`recon_batch(split=True)`), off by default."""
-    lib = _lib.lib()
-    dev = model.opt_obja.device
-    B = idx.numel()
-    obja, objp, probe = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous(), model.opt_probe.data.contiguous()
-    dz, shifts = model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
-    tilts = model.opt_obj_tilts.data.contiguous()
-    n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
-    n_probe = model.opt_probe.requires_grad
-    n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
-    need = (_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0)
-    cuts = [(0, B // 2), (B // 2, B)]
-    cap = max(hi - lo for lo, hi in cuts)
-    cfg = model._cfg(stash_fourier=False)
-    cfg.reserved[0] = cap
-    Hbase = engine.propagator(cfg, dz) if model.change_thickness else model.H
-    ws_bytes = lib.ptyb200_workspace_bytes(C.byref(cfg), cap)
-    if ws_bytes == 0:
-        _lib.check(1)
-    ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in cuts]
-    dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
-    G = torch.empty_like(dp)
-    tl = tilts if cfg.tilt_mode else None
-    sh = shifts if cfg.shift_probes else None
-    lcfg = loss_fn.lcfg()
-    losses = torch.zeros(5, dtype=torch.float32, device=dev)
-    stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    sparse = bool(lcfg.sparse_state)
-    ones = getattr(model, "_ones3", None)
-    if ones is None or ones.device != dev:
-        ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
-
-    def out(p, wanted):
-        if not wanted:
-            return None
-        return p.grad if p.requires_grad else torch.empty_like(p.data)
-
-    g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
-    g_probe, g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
-    if sparse:
-        Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
-        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
-    cur = torch.cuda.current_stream(dev)
-    aux, half = _side_stream(dev), _side_stream(dev, "half")
-    aux.wait_stream(cur)
-    half.wait_stream(cur)
-    with torch.cuda.stream(aux):                              # independent of the multislice kernels (see _direct_grads)
-        sst = engine._stream()
-        if zero_arena:
-            arena.zero()
-        if need:
-            for w in ws:
-                _lib.check(lib.ptyb200_backward_zero(C.byref(cfg), cap, ptr(w), ptr(g_probe), ptr(g_shifts), need, sst))
-        if sparse:
-            _lib.check(lib.ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                                  C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), sst))
-            if need and model.opt_objp.requires_grad:
-                _lib.check(lib.ptyb200_sparse_grad(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                                   ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), sst))
-    cfg_f = type(cfg).from_buffer_copy(cfg)
-    cfg_f.reserved[4] = _lib.ACC_KEEP_STATS | _lib.ACC_NO_LOSS_FINAL          # `stats` was zeroed above, once for both halves
-    cfg_b = type(cfg).from_buffer_copy(cfg)
-    cfg_b.reserved[4] = _lib.ACC_KEEP_GRADS | _lib.ACC_NO_FINISH
-    for (lo, hi), stream, w in zip(cuts, (cur, half), ws):
-        n = hi - lo
-        ci, cr = idx[lo:hi], meas.idx[lo:hi]
-        with torch.cuda.stream(stream):
-            st = engine._stream()
-            _lib.check(lib.ptyb200_forward_loss(C.byref(cfg_f), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh),
-                                                ptr(Hbase), ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp[lo:hi]), ptr(w), C.byref(lcfg),
-                                                ptr(meas.all), ptr(cr), engine.mref(meas.mcfg), ptr(meas.padded), ptr(losses), ptr(stats), None, st))
-            if need:
-                _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp[lo:hi]), ptr(meas.all), ptr(cr), n, None, None, None,
-                                                 ptr(G[lo:hi]), engine.mref(meas.mcfg), ptr(meas.padded), st))
-                stream.wait_stream(aux)                       # accumulators zeroed
-                _lib.check(lib.ptyb200_backward(
-                    C.byref(cfg_b), ptr(ci), n, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
-                    ptr(model.omode_occu), ptr(G[lo:hi]), ptr(w), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), None, None, need, st))
-    cur.wait_stream(half)
-    cur.wait_stream(aux)
-    st = engine._stream()
-    _lib.check(lib.ptyb200_loss_finalize(C.byref(cfg), C.byref(lcfg), B, ptr(stats), None, ptr(losses), st))
-    if need:
-        scale = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.check(lib.ptyb200_loss_scale(C.byref(cfg), C.byref(lcfg), B, ptr(stats), ptr(ones), ptr(scale), st))
-        _lib.check(lib.ptyb200_accumulators_add(C.byref(cfg), cap, ptr(ws[0]), ptr(ws[1]), need, st))
-        cfg_e = type(cfg).from_buffer_copy(cfg)
-        cfg_e.reserved[4] = _lib.ACC_ADD_OBJ                  # the arena was zeroed and holds the loss_sparse term
-        _lib.check(lib.ptyb200_backward_finish(C.byref(cfg_e), cap, ptr(obja), ptr(objp), ptr(ws[0]), ptr(g_obja), ptr(g_objp), ptr(g_probe),
-                                               ptr(g_shifts), need, ptr(scale), st))
-    return losses
-
-
 def split_step_eligible(model, loss_fn, B: int) -> bool:
     """What `recon_batch(split=True)` covers: the fused 128^2 kernels (one tile per SM, ragged last wave) and what a chunked step
     needs (one separable data term, no pacbed / detector blur / tilt-thickness gradients)."""
@@ -300,112 +121,256 @@ def split_step_eligible(model, loss_fn, B: int) -> bool:
     return N == 128 and model.kernel_path != _lib.PATH_GENERAL
 
 
+class _StepIO:
+    """What one autograd-free step hands to the C ABI, gathered once: parameter storages, the need mask, the gradient output buffers
+    (arena views of the live parameters, scratch for frozen ones), loss configuration, and the ABI calls of a step as methods so that
+    the whole-batch, chunked and split variants below differ only in how they sequence them."""
+
+    def __init__(self, model, loss_fn, idx, meas: MeasurementView, cap: int, prop_grads: bool = True):
+        self.model, self.lib, self.idx, self.meas = model, _lib.lib(), idx, meas
+        self.dev = dev = model.opt_obja.device
+        self.B = idx.numel()
+        self.obja, self.objp = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous()
+        self.probe = model.opt_probe.data.contiguous()
+        tilts, self.dz, shifts = model.opt_obj_tilts.data.contiguous(), model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
+        Z = self.obja.shape[1]
+        n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
+        n_probe = model.opt_probe.requires_grad
+        n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
+        n_tilts = prop_grads and model.opt_obj_tilts.requires_grad and model.tilt_obj and Z > 1
+        n_dz = prop_grads and model.opt_slice_thickness.requires_grad and model.change_thickness and Z > 1
+        need_prop = prop_grads and ((model.opt_obj_tilts.requires_grad and model.tilt_obj) or
+                                    (model.opt_slice_thickness.requires_grad and model.change_thickness))
+        self.need = ((_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0) |
+                     (_lib.NEED_TILTS if n_tilts else 0) | (_lib.NEED_DZ if n_dz else 0))
+        self.cfg = cfg = model._cfg(stash_fourier=bool(need_prop))
+        self.cap = int(cap)                                     # samples per ABI call; the workspaces are laid out for it
+        if self.cap != self.B:
+            cfg.reserved[0] = self.cap
+        self.Hbase = engine.propagator(cfg, self.dz) if model.change_thickness else model.H
+        self.tl = tilts if cfg.tilt_mode else None
+        self.sh = shifts if cfg.shift_probes else None
+        self.lcfg = loss_fn.lcfg()
+        self.sparse = bool(self.lcfg.sparse_state)
+        if self.sparse and not self.need and model.opt_objp.requires_grad:
+            raise RuntimeError("unreachable: objp.requires_grad implies NEED_OBJ")
+        ones = getattr(model, "_ones3", None)                   # d(total)/d(term) = 1 for every term: total is their plain sum
+        if ones is None or ones.device != dev:
+            ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
+        self.ones = ones
+
+        def out(p, wanted):                                     # the arena view of a live parameter, scratch for a frozen one
+            if not wanted:
+                return None
+            return p.grad if p.requires_grad else torch.empty_like(p.data)
+
+        self.g_obja, self.g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
+        self.g_probe, self.g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
+        self.g_tilts, self.g_dz = out(model.opt_obj_tilts, n_tilts), out(model.opt_slice_thickness, n_dz)
+        # losses: [single, poissn, pacbed] and [sparse] land in one (5,) tensor; simlar (slot 4) is off on these paths
+        self.losses = torch.zeros(5, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if self.lcfg.pacbed_state else None
+        if self.sparse:
+            self.Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
+            self.cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
+
+    def workspace(self):
+        n = self.lib.ptyb200_workspace_bytes(C.byref(self.cfg), self.cap)
+        if n == 0:
+            _lib.check(1)
+        return torch.empty(n, dtype=torch.uint8, device=self.dev)
+
+    def flagged(self, flags: int):
+        c = type(self.cfg).from_buffer_copy(self.cfg)
+        c.reserved[4] = flags
+        return c
+
+    def _params(self):
+        m = self.model
+        return (ptr(self.obja), ptr(self.objp), ptr(m.crop_pos), ptr(self.probe), ptr(self.sh), ptr(self.Hbase), ptr(self.tl), ptr(self.dz),
+                ptr(m.omode_occu))
+
+    # -- the ABI calls of a step; lo:hi = the samples of this call, everything on the CURRENT stream
+    def forward_loss(self, flags, lo, hi, dp, ws):
+        """forward with the mode reduction fused with the data losses (the kernel that completes a pattern adds its loss sums)"""
+        me = self.meas
+        _lib.check(self.lib.ptyb200_forward_loss(C.byref(self.flagged(flags)), ptr(self.idx[lo:hi]), hi - lo, *self._params(), ptr(dp), ptr(ws),
+                                                 C.byref(self.lcfg), ptr(me.all), ptr(me.idx[lo:hi]), engine.mref(me.mcfg), ptr(me.padded),
+                                                 ptr(self.losses), ptr(self.stats), ptr(self.pac), engine._stream()))
+
+    def loss_grad(self, lo, hi, dp, G, unscaled: bool):
+        me = self.meas
+        _lib.check(self.lib.ptyb200_loss_grad(C.byref(self.cfg), C.byref(self.lcfg), ptr(dp), ptr(me.all), ptr(me.idx[lo:hi]), hi - lo,
+                                              None if unscaled else ptr(self.stats), None if unscaled else ptr(self.pac),
+                                              None if unscaled else ptr(self.ones), ptr(G), engine.mref(me.mcfg), ptr(me.padded), engine._stream()))
+
+    def backward(self, flags, lo, hi, G, ws):
+        _lib.check(self.lib.ptyb200_backward(C.byref(self.flagged(flags)), ptr(self.idx[lo:hi]), hi - lo, *self._params(), ptr(G), ptr(ws),
+                                             ptr(self.g_obja), ptr(self.g_objp), ptr(self.g_probe), ptr(self.g_shifts), ptr(self.g_tilts),
+                                             ptr(self.g_dz), self.need, engine._stream()))
+
+    def backward_zero(self, ws):
+        _lib.check(self.lib.ptyb200_backward_zero(C.byref(self.cfg), self.cap, ptr(ws), ptr(self.g_probe), ptr(self.g_shifts), self.need,
+                                                  engine._stream()))
+
+    def loss_finalize(self):
+        _lib.check(self.lib.ptyb200_loss_finalize(C.byref(self.cfg), C.byref(self.lcfg), self.B, ptr(self.stats), ptr(self.pac), ptr(self.losses),
+                                                  engine._stream()))
+
+    def finish_scaled(self, flags, ws):
+        """accumulators of `ws` -> gradients, times the batch-level factor of the (unscaled) loss gradient"""
+        scale = torch.empty(1, dtype=torch.float32, device=self.dev)
+        st = engine._stream()
+        _lib.check(self.lib.ptyb200_loss_scale(C.byref(self.cfg), C.byref(self.lcfg), self.B, ptr(self.stats), ptr(self.ones), ptr(scale), st))
+        _lib.check(self.lib.ptyb200_backward_finish(C.byref(self.flagged(flags)), self.cap, ptr(self.obja), ptr(self.objp), ptr(ws), ptr(self.g_obja),
+                                                    ptr(self.g_objp), ptr(self.g_probe), ptr(self.g_shifts), self.need, ptr(scale), st))
+
+    def sparse_forward(self):
+        m = self.model
+        _lib.check(self.lib.ptyb200_sparse_forward(C.byref(self.cfg), C.byref(self.lcfg), ptr(self.objp), ptr(m.crop_pos), ptr(self.idx), self.B,
+                                                   ptr(m.omode_occu), C.c_void_p(self.losses.data_ptr() + 12), ptr(self.Ssum), ptr(self.cover),
+                                                   engine._stream()))
+
+    def sparse_grad(self):
+        m = self.model
+        if self.need and m.opt_objp.requires_grad:
+            _lib.check(self.lib.ptyb200_sparse_grad(C.byref(self.cfg), C.byref(self.lcfg), ptr(self.objp), ptr(m.crop_pos), ptr(self.idx), self.B,
+                                                    ptr(m.omode_occu), ptr(self.Ssum), ptr(self.ones), ptr(self.cover), ptr(m.opt_objp.grad),
+                                                    engine._stream()))
+
+    def aux_work(self, workspaces, arena, zero_arena: bool):
+        """Everything that does not depend on the multislice kernels, for a side stream: zeroing of the gradient arena and of the
+        adjoint's accumulators, loss_sparse (object and batch indices only) and its gradient (ADDED into the zeroed arena; the
+        adjoint's completion then adds the object gradients on top: PTYB200_ACC_ADD_OBJ)."""
+        if zero_arena:
+            arena.zero()
+        if self.need:
+            for w in workspaces:
+                self.backward_zero(w)
+        if self.sparse:
+            self.sparse_forward()
+            self.sparse_grad()
+
+
 def _direct_grads(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, zero_arena: bool = False):
     """Forward, loss, loss gradient and adjoint through the C ABI with the gradient tensors of the arena as the kernels' output
     buffers -- what ``model(idx)`` -> ``loss_fn`` -> ``backward()`` computes (engine.MultisliceFunction / DataLossFunction /
     SparseLossFunction), minus the autograd graph, its ~30 small elementwise launches per step and the accumulate-into-.grad copies.
-    Returns the five loss terms as one device tensor."""
-    lib = _lib.lib()
-    st = engine._stream()
-    dev = model.opt_obja.device
-    B = idx.numel()
-    obja, objp, probe = model.opt_obja.data.contiguous(), model.opt_objp.data.contiguous(), model.opt_probe.data.contiguous()
-    tilts, dz, shifts = model.opt_obj_tilts.data.contiguous(), model.opt_slice_thickness.data, model.opt_probe_pos_shifts.data.contiguous()
-    Z = obja.shape[1]
-    n_obj = model.opt_obja.requires_grad or model.opt_objp.requires_grad
-    n_probe = model.opt_probe.requires_grad
-    n_shifts = model.opt_probe_pos_shifts.requires_grad and model.shift_probes
-    n_tilts = model.opt_obj_tilts.requires_grad and model.tilt_obj and Z > 1
-    n_dz = model.opt_slice_thickness.requires_grad and model.change_thickness and Z > 1
-    need_prop = (model.opt_obj_tilts.requires_grad and model.tilt_obj) or (model.opt_slice_thickness.requires_grad and model.change_thickness)
-    cfg = model._cfg(stash_fourier=bool(need_prop))
-    Hbase = engine.propagator(cfg, dz) if model.change_thickness else model.H
-    ws_bytes = lib.ptyb200_workspace_bytes(C.byref(cfg), B)
-    if ws_bytes == 0:
-        _lib.check(1)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    Returns the five loss terms as one device tensor.
+
+    A step is a chain of ~30 launches of which two matter.  Everything that does not depend on the multislice kernels
+    (`_StepIO.aux_work`, and -- once the forward is through -- the loss scalars) runs on a side stream while the forward holds the
+    caller's stream: the fused kernels use the whole register file, so these short kernels execute in its last, partial wave."""
+    io = _StepIO(model, loss_fn, idx, meas, cap=idx.numel())
+    B, cfg, dev = io.B, io.cfg, io.dev
+    ws = io.workspace()
     dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
-    tl = tilts if cfg.tilt_mode else None
-    sh = shifts if cfg.shift_probes else None
-    # losses: [single, poissn, pacbed] and [sparse] land in one (5,) tensor; simlar (slot 4) is off on this path
-    lcfg = loss_fn.lcfg()
-    losses = torch.zeros(5, dtype=torch.float32, device=dev)
-    stats = torch.empty(8, dtype=torch.float64, device=dev)
-    pac = torch.empty(2 * cfg.N * cfg.N, dtype=torch.float32, device=dev) if lcfg.pacbed_state else None
     blur = model.detector_blur_std
-    need = ((_lib.NEED_OBJ if n_obj else 0) | (_lib.NEED_PROBE if n_probe else 0) | (_lib.NEED_SHIFTS if n_shifts else 0) |
-            (_lib.NEED_TILTS if n_tilts else 0) | (_lib.NEED_DZ if n_dz else 0))
-    sparse = bool(lcfg.sparse_state)
-    if sparse and not need and model.opt_objp.requires_grad:
-        raise RuntimeError("unreachable: objp.requires_grad implies NEED_OBJ")
-    ones = getattr(model, "_ones3", None)                     # d(total)/d(term) = 1 for every term: total is their plain sum
-    if ones is None or ones.device != dev:
-        ones = model._ones3 = torch.ones(3, dtype=torch.float32, device=dev)
-
-    def out(p, wanted):                                       # the arena view of a live parameter, scratch for a frozen one
-        if not wanted:
-            return None
-        return p.grad if p.requires_grad else torch.empty_like(p.data)
-
-    g_obja, g_objp = out(model.opt_obja, n_obj), out(model.opt_objp, n_obj)
-    g_probe, g_shifts = out(model.opt_probe, n_probe), out(model.opt_probe_pos_shifts, n_shifts)
-    g_tilts, g_dz = out(model.opt_obj_tilts, n_tilts), out(model.opt_slice_thickness, n_dz)
-    if sparse:
-        Ssum = torch.empty(cfg.M, dtype=torch.float64, device=dev)
-        cover = torch.empty(cfg.Noy * cfg.Nox, dtype=torch.int32, device=dev)
-    # A step is a chain of ~30 launches of which two matter.  Everything that does not depend on the multislice kernels runs on a
-    # side stream while the forward occupies the caller's stream (the short kernels fill its last, partial wave): zeroing of the
-    # gradient arena and of the adjoint's accumulators, loss_sparse (object and batch indices only) and its gradient, and -- once
-    # the forward is through -- the loss scalars.  The adjoint then ADDS the object gradients on top (PTYB200_ACC_ADD_OBJ).
     cur = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
-        sst = engine._stream()
-        if zero_arena:
-            arena.zero()
-        if need:
-            _lib.check(lib.ptyb200_backward_zero(C.byref(cfg), B, ptr(ws), ptr(g_probe), ptr(g_shifts), need, sst))
-        if sparse:
-            _lib.check(lib.ptyb200_sparse_forward(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                                  C.c_void_p(losses.data_ptr() + 12), ptr(Ssum), ptr(cover), sst))
-            if need and model.opt_objp.requires_grad:
-                _lib.check(lib.ptyb200_sparse_grad(C.byref(cfg), C.byref(lcfg), ptr(objp), ptr(model.crop_pos), ptr(idx), B, ptr(model.omode_occu),
-                                                   ptr(Ssum), ptr(ones), ptr(cover), ptr(model.opt_objp.grad), sst))
-    # (loss_pacbed: the kernel that forms the loss scalars also completes a sum the loss gradient reads, so it stays in line)
-    defer_final = not lcfg.pacbed_state
-    cfg_f = type(cfg).from_buffer_copy(cfg)
-    cfg_f.reserved[4] = _lib.ACC_NO_LOSS_FINAL if defer_final else 0
-    fwd_args = (ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase),
-                ptr(tl), ptr(dz), ptr(model.omode_occu), ptr(dp), ptr(ws))
+        io.aux_work([ws], arena, zero_arena)
     if not blur:
-        # forward with the mode reduction fused with the data losses: the kernel that completes a pattern also adds its loss sums
-        _lib.check(lib.ptyb200_forward_loss(C.byref(cfg_f), *fwd_args, C.byref(lcfg), ptr(meas.all), ptr(meas.idx), engine.mref(meas.mcfg),
-                                            ptr(meas.padded), ptr(losses), ptr(stats), ptr(pac), st))
+        # (loss_pacbed: the kernel that forms the loss scalars also completes a sum the loss gradient reads, so it stays in line)
+        defer_final = not io.lcfg.pacbed_state
+        io.forward_loss(_lib.ACC_NO_LOSS_FINAL if defer_final else 0, 0, B, dp, ws)
         if defer_final:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                _lib.check(lib.ptyb200_loss_finalize(C.byref(cfg), C.byref(lcfg), B, ptr(stats), ptr(pac), ptr(losses), engine._stream()))
+                io.loss_finalize()
     else:
-        _lib.check(lib.ptyb200_forward(C.byref(cfg), *fwd_args, st))
+        st = engine._stream()
+        me = io.meas
+        _lib.check(io.lib.ptyb200_forward(C.byref(cfg), ptr(idx), B, *io._params(), ptr(dp), ptr(ws), st))
         dp = engine._blur5(dp, float(blur), 0)                # detector blur (models.py:379-380): native 5x5 kernel on the intensities
-        _lib.check(lib.ptyb200_loss_forward(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(losses), ptr(stats),
-                                            ptr(pac), engine.mref(meas.mcfg), ptr(meas.padded), st))
-    if need:
+        _lib.check(io.lib.ptyb200_loss_forward(C.byref(cfg), C.byref(io.lcfg), ptr(dp), ptr(me.all), ptr(me.idx), B, ptr(io.losses), ptr(io.stats),
+                                               ptr(io.pac), engine.mref(me.mcfg), ptr(me.padded), st))
+    if io.need:
         G = torch.empty_like(dp)
-        _lib.check(lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), ptr(dp), ptr(meas.all), ptr(meas.idx), B, ptr(stats), ptr(pac),
-                                         ptr(ones), ptr(G), engine.mref(meas.mcfg), ptr(meas.padded), st))
+        io.loss_grad(0, B, dp, G, unscaled=False)
         if blur:
             G = engine._blur5(G, float(blur), 1)              # adjoint of the blur
         cur.wait_stream(side)                                 # accumulators zeroed, sparse term in place
-        cfg_b = type(cfg).from_buffer_copy(cfg)
-        cfg_b.reserved[4] = _lib.ACC_KEEP_GRADS | _lib.ACC_ADD_OBJ
-        _lib.check(lib.ptyb200_backward(
-            C.byref(cfg_b), ptr(idx), B, ptr(obja), ptr(objp), ptr(model.crop_pos), ptr(probe), ptr(sh), ptr(Hbase), ptr(tl), ptr(dz),
-            ptr(model.omode_occu), ptr(G), ptr(ws), ptr(g_obja), ptr(g_objp), ptr(g_probe), ptr(g_shifts), ptr(g_tilts), ptr(g_dz), need, st))
+        io.backward(_lib.ACC_KEEP_GRADS | _lib.ACC_ADD_OBJ, 0, B, G, ws)
     else:
         cur.wait_stream(side)
-    return losses
+    return io.losses
+
+
+def _direct_grads_chunked(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, chunk: int, zero_arena: bool = False):
+    """`_direct_grads` for a batch that is processed `chunk` samples at a time so that only one chunk's wave stash is alive
+    (SURVEY 8e: memory must not grow with the per-GPU batch; the strong-scaling runs put 2 048 patterns of C4 on one GPU, whose
+    stash alone would be 206 GB).  The result is the gradient of the loss of the WHOLE batch, not a sum of per-chunk losses: every
+    chunk adds its loss sums and runs its adjoint on the unscaled loss gradient into shared accumulators; the batch-level factor is
+    applied once, when the accumulators are turned into gradients (include/ptyrad_b200.h, PTYB200_ACC_*)."""
+    if not chunked_step_eligible(model, loss_fn):
+        raise ValueError("a chunked step needs exactly one of loss_single / loss_poissn, no loss_pacbed, no detector blur and no "
+                         "tilt / thickness gradients")
+    io = _StepIO(model, loss_fn, idx, meas, cap=chunk, prop_grads=False)
+    B, cfg, dev = io.B, io.cfg, io.dev
+    ws = io.workspace()
+    dp = torch.empty((chunk, cfg.N, cfg.N), dtype=torch.float32, device=dev)
+    G = torch.empty_like(dp)
+    cur = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        io.aux_work([ws], arena, zero_arena)
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        io.forward_loss(_lib.ACC_KEEP_STATS | _lib.ACC_NO_LOSS_FINAL, lo, hi, dp, ws)      # `stats` starts zeroed (_StepIO)
+        if io.need:
+            io.loss_grad(lo, hi, dp, G, unscaled=True)
+            if lo == 0:
+                cur.wait_stream(side)                         # accumulators zeroed
+            io.backward(_lib.ACC_KEEP_GRADS | _lib.ACC_NO_FINISH, lo, hi, G, ws)
+    cur.wait_stream(side)
+    io.loss_finalize()
+    if io.need:
+        io.finish_scaled(_lib.ACC_ADD_OBJ, ws)                # the arena was zeroed and holds the loss_sparse term
+    return io.losses
+
+
+def _direct_grads_split(model, loss_fn, idx, meas: MeasurementView, arena: GradArena, zero_arena: bool = False):
+    """`_direct_grads` with the batch cut in two halves that run forward -> unscaled loss gradient -> adjoint on TWO streams, each into
+    its own workspace; the accumulators are added and completed once, with the batch-level factor (the machinery of the chunked
+    step).  Why: the fused kernels run one tile per SM, so a kernel over T tiles takes ceil(T / 148) waves -- C2's 1536 tiles are
+    10.38 waves, and the last, 38 %-full wave of the forward and of the adjoint costs 0.14 ms of a 2.54 ms step.  Four half-size
+    kernels on two streams could fill each other's partial waves.  MEASURED (C2, B200): 2.819 ms against 2.534 ms unsplit --
+    concurrent forward (stash writes) and adjoint (stash reads) kernels cost more than the tails; kept as an option
+    (`recon_batch(split=True)`), off by default.  Loss and gradients are those of the whole batch."""
+    if not chunked_step_eligible(model, loss_fn):
+        raise ValueError("a split step needs exactly one of loss_single / loss_poissn, no loss_pacbed, no detector blur and no "
+                         "tilt / thickness gradients")
+    B = idx.numel()
+    cuts = [(0, B // 2), (B // 2, B)]
+    io = _StepIO(model, loss_fn, idx, meas, cap=max(hi - lo for lo, hi in cuts), prop_grads=False)
+    cfg, dev = io.cfg, io.dev
+    ws = [io.workspace() for _ in cuts]
+    dp = torch.empty((B, cfg.N, cfg.N), dtype=torch.float32, device=dev)
+    G = torch.empty_like(dp)
+    cur = torch.cuda.current_stream(dev)
+    aux, half = _side_stream(dev), _side_stream(dev, "half")
+    aux.wait_stream(cur)
+    half.wait_stream(cur)
+    with torch.cuda.stream(aux):
+        io.aux_work(ws, arena, zero_arena)
+    for (lo, hi), stream, w in zip(cuts, (cur, half), ws):
+        with torch.cuda.stream(stream):
+            io.forward_loss(_lib.ACC_KEEP_STATS | _lib.ACC_NO_LOSS_FINAL, lo, hi, dp[lo:hi], w)
+            if io.need:
+                io.loss_grad(lo, hi, dp[lo:hi], G[lo:hi], unscaled=True)
+                stream.wait_stream(aux)                       # accumulators zeroed
+                io.backward(_lib.ACC_KEEP_GRADS | _lib.ACC_NO_FINISH, lo, hi, G[lo:hi], w)
+    cur.wait_stream(half)
+    cur.wait_stream(aux)
+    io.loss_finalize()
+    if io.need:
+        _lib.check(io.lib.ptyb200_accumulators_add(C.byref(cfg), io.cap, ptr(ws[0]), ptr(ws[1]), io.need, engine._stream()))
+        io.finish_scaled(_lib.ACC_ADD_OBJ, ws[0])
+    return io.losses
 
 
 def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = None, world: int = 1,
@@ -434,8 +399,7 @@ def recon_batch(model, loss_fn, optimizer, indices, arena: GradArena | None = No
         idx = model._index_tensor(indices)
         meas = measurements if measurements is not None else MeasurementView(model.measurements, idx, model)
         if chunk and idx.numel() > chunk:
-            arena.zero()
-            losses = _direct_grads_chunked(model, loss_fn, idx, meas, arena, int(chunk))
+            losses = _direct_grads_chunked(model, loss_fn, idx, meas, arena, int(chunk), zero_arena=True)
         elif split:
             losses = _direct_grads_split(model, loss_fn, idx, meas, arena, zero_arena=True)
         else:
