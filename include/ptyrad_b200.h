@@ -7,6 +7,13 @@
  * allocated inside the library; work is enqueued on the caller's stream and the calls do not block.
  * Return value: 0 = OK, non-zero = error, text via ptyb200_last_error().
  *
+ * State the library keeps between calls (process-wide, created on first use): the optional timing events (ptyb200_timing_*), the
+ * launch counter, and two internal non-blocking streams + events on which ptyb200_forward* / ptyb200_backward run their short,
+ * mutually independent setup and completion kernels as parallel branches.  The branches are forked from and joined back into the
+ * caller's stream inside the same call, so the caller still sees ONE stream and a stream capture sees a fork / join subgraph;
+ * PTYB200_NO_BRANCHES=1 in the environment keeps everything on the caller's stream, and a call made on another device than the one
+ * the streams were created on does the same.
+ *
  * Complex arrays are interleaved (re,im) float32 pairs ("float2").
  */
 #ifndef PTYRAD_B200_H

@@ -53,8 +53,12 @@ struct SidePool {
     cudaStream_t s[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     bool ok = false;
+    int dev = -1;                                          // the device the streams live on (one process per GPU is the intended use)
     bool init() {
-        if (ok) return true;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) return false;
+        if (ok) return cur == dev;                         // a call on another device of the same process stays serial
+        dev = cur;
         for (int i = 0; i < 2; ++i) {
             if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return false;
