@@ -302,3 +302,43 @@ def test_patch_planes_handle():
     assert h.shape == (2, 1, 3, 4, 4, 2)
     assert torch.equal(h[0, 0, 1], torch.stack([a, p], -1)[0, 0, 1])
     assert torch.equal(h.permute(5, 0, 1, 2, 3, 4)[1], p)
+
+
+def test_round2_entry_points_validate_before_touching_the_device(built):
+    """Argument checks of the entry points added in round 2 (chunked steps, grouping, ROI blur, loss_simlar): every refusal happens
+    before the first launch, so it can be exercised without a GPU."""
+    import ctypes as C
+    from ptyrad_b200 import engine
+    lib = built.lib()
+    cfg = engine.make_cfg(128, 6, 2, 8, 370, 370, 4096, 1, 0, 0, 0.1494, 0.0418)
+    lcfg = engine.make_loss_cfg({"loss_single": dict(state=True, weight=1.0, dp_pow=0.5), "loss_poissn": dict(state=True, weight=1.0, dp_pow=1.0, eps=1e-6),
+                                 "loss_pacbed": dict(state=False, weight=0.5, dp_pow=0.2), "loss_sparse": dict(state=False, weight=0.1, ln_order=1),
+                                 "loss_simlar": dict(state=False, weight=0.1, obj_type="both", scale_factor=[1, 1, 1], blur_std=1)})
+    p = lambda v: C.c_void_p(v)
+    # unscaled loss gradient / loss_scale: exactly one separable data term
+    assert lib.ptyb200_loss_grad(C.byref(cfg), C.byref(lcfg), p(256), p(512), p(768), 4, None, None, None, p(1024), None, None, None) != 0
+    assert b"exactly one" in lib.ptyb200_last_error()
+    assert lib.ptyb200_loss_scale(C.byref(cfg), C.byref(lcfg), 4, p(256), p(512), p(768), None) != 0
+    # chunked completion: no tilt / thickness gradients, no patch mode
+    assert lib.ptyb200_backward_finish(C.byref(cfg), 4, p(256), p(512), p(768), None, None, None, None, built.NEED_TILTS, None, None) != 0
+    assert b"tilt" in lib.ptyb200_last_error()
+    patch = engine.make_cfg(128, 6, 2, 8, 128, 128, 4096, 1, 0, 0, 0.1494, 0.0418)
+    patch.reserved[1] = 1
+    assert lib.ptyb200_backward_zero(C.byref(patch), 4, p(256), None, None, built.NEED_OBJ, None) != 0
+    assert lib.ptyb200_accumulators_add(C.byref(patch), 4, p(256), p(512), built.NEED_OBJ, None) != 0
+    assert b"patch mode" in lib.ptyb200_last_error()
+    # grouping: one seed per group first
+    assert lib.ptyb200_sparse_groups(p(256), 3, 5, p(512), None) != 0
+    assert lib.ptyb200_sparse_groups(None, 8, 2, p(512), None) != 0
+    # ROI blur: scratch required when blurring; simlar: 2 <= M <= 8 and pooled size within the input
+    assert lib.ptyb200_roi_blur(C.byref(cfg), p(256), 4, p(512), p(768), p(1024), 1.0, None, p(2048), p(4096), None) != 0
+    assert b"tmp" in lib.ptyb200_last_error()
+    assert lib.ptyb200_roi_blur(C.byref(cfg), p(256), 4, p(512), p(768), p(1024), -1.0, p(64), p(2048), p(4096), None) != 0
+    one = engine.make_cfg(128, 6, 1, 8, 370, 370, 4096, 1, 0, 0, 0.1494, 0.0418)
+    assert lib.ptyb200_simlar_forward(C.byref(one), 4, p(256), p(512), 8, 128, 128, 0.1, p(768), None) != 0
+    assert b"object modes" in lib.ptyb200_last_error()
+    assert lib.ptyb200_simlar_forward(C.byref(cfg), 4, p(256), p(512), 9, 128, 128, 0.1, p(768), None) != 0
+    assert b"pooled size" in lib.ptyb200_last_error()
+    # the workspace layout follows the batch capacity of a chunked step
+    cfg.reserved[0] = 256
+    assert lib.ptyb200_workspace_bytes(C.byref(cfg), 64) == lib.ptyb200_workspace_bytes(C.byref(cfg), 256)
