@@ -468,7 +468,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fw
             if (src_mode == 0) {
 #pragma unroll
                 for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[F::addr(j + N2 * k1)];
-                Dft<N1, +1>::run(v);
+                Dft<N1, +1, false>::run(v);
 #pragma unroll
                 for (int k = 0; k < N1; ++k) v[k] = cscale(v[k], 1.0f / N);
             } else {
@@ -481,7 +481,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fw
                 st_stream(st + N2 * k, v[k]);
                 v[k] = cmul(v[k], Oreg[k]);
             }
-            Dft<N1, -1>::run(v);
+            Dft<N1, -1, false>::run(v);
 #pragma unroll
             for (int k1 = 0; k1 < N1; ++k1) row[F::addr(j + N2 * k1)] = k1 ? cmul(v[k1], twN[j * k1]) : v[k1];
         }
@@ -550,13 +550,13 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB_LIGHT(F)) k_fw
             float2 v[N2];
 #pragma unroll
             for (int j = 0; j < N2; ++j) v[j] = row[F::addr(j + N2 * k1)];
-            Dft<N2, -1>::run(v);
+            Dft<N2, -1, false>::run(v);
 #pragma unroll
             for (int k2 = 0; k2 < N2; ++k2) {
                 if (ph) st_stream(ph + N1 * k2, v[k2]);
                 v[k2] = cmul(v[k2], Hreg[k2]);
             }
-            Dft<N2, +1>::run(v);
+            Dft<N2, +1, false>::run(v);
 #pragma unroll
             for (int j = 0; j < N2; ++j) row[F::addr(j + N2 * k1)] = k1 ? cmulc(v[j], twN[j * k1]) : v[j];
         }
@@ -742,7 +742,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
             float2 v[N1];
 #pragma unroll
             for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[F::addr(j + N2 * k1)];
-            Dft<N1, +1>::run(v);
+            Dft<N1, +1, false>::run(v);
 #pragma unroll
             for (int k = 0; k < N1; ++k) {
                 const float2 gphi = cscale(v[k], 1.0f / N);
@@ -750,7 +750,7 @@ template <class F> __global__ void __launch_bounds__(NT, GEN_MINB) k_bwd_da(BwdA
                 v[k] = cmulc(gphi, __ldg(Oz + roi + N2 * k));               // conj(O) * gphi
             }
             if (out_mode == 0) {
-                Dft<N1, -1>::run(v);
+                Dft<N1, -1, false>::run(v);
 #pragma unroll
                 for (int k1 = 0; k1 < N1; ++k1) row[F::addr(j + N2 * k1)] = k1 ? cmul(v[k1], twN[j * k1]) : v[k1];
             } else if (out_mode == 1) {
@@ -825,7 +825,7 @@ template <class F, bool PROP> __global__ void __launch_bounds__(NT, GEN_MINB_LIG
             }
 #pragma unroll
             for (int jj = 0; jj < N2; ++jj) v[jj] = row[F::addr(jj + N2 * k1)];
-            Dft<N2, -1>::run(v);
+            Dft<N2, -1, false>::run(v);
 #pragma unroll
             for (int k2 = 0; k2 < N2; ++k2) {
                 v[k2] = cmulc(v[k2], Hreg[k2]);                              // conj(H) * F2(gpsi)
@@ -837,7 +837,7 @@ template <class F, bool PROP> __global__ void __launch_bounds__(NT, GEN_MINB_LIG
                     s3[2] += -kk / (sqrtf(a.k0 * a.k0 - kk) + a.k0) * sv;    // Kz - k0, cancellation-free
                 }
             }
-            Dft<N2, +1>::run(v);
+            Dft<N2, +1, false>::run(v);
 #pragma unroll
             for (int jj = 0; jj < N2; ++jj) row[F::addr(jj + N2 * k1)] = k1 ? cmulc(v[jj], twN[jj * k1]) : v[jj];
         }

@@ -42,7 +42,7 @@ template <int N1_, int N2_> struct RowFFT {
         float2 v[N1];
 #pragma unroll
         for (int k = 0; k < N1; ++k) v[k] = row[addr(j + N2 * k)];
-        Dft<N1, -1>::run(v);
+        Dft<N1, -1, false>::run(v);
 #pragma unroll
         for (int k1 = 0; k1 < N1; ++k1) {
             float2 r = (k1 == 0) ? v[k1] : cmul(v[k1], tw<-1>(twN, j * k1));
@@ -53,7 +53,7 @@ template <int N1_, int N2_> struct RowFFT {
         float2 v[N2];
 #pragma unroll
         for (int j = 0; j < N2; ++j) v[j] = row[addr(j + N2 * k1)];
-        Dft<N2, -1>::run(v);
+        Dft<N2, -1, false>::run(v);
 #pragma unroll
         for (int k2 = 0; k2 < N2; ++k2) row[addr(k2 + N2 * k1)] = v[k2];
     }
@@ -61,7 +61,7 @@ template <int N1_, int N2_> struct RowFFT {
         float2 v[N2];
 #pragma unroll
         for (int k2 = 0; k2 < N2; ++k2) v[k2] = row[addr(k2 + N2 * k1)];
-        Dft<N2, +1>::run(v);
+        Dft<N2, +1, false>::run(v);
 #pragma unroll
         for (int j = 0; j < N2; ++j) {
             float2 r = (k1 == 0) ? v[j] : cmul(v[j], tw<+1>(twN, j * k1));
@@ -72,7 +72,7 @@ template <int N1_, int N2_> struct RowFFT {
         float2 v[N1];
 #pragma unroll
         for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[addr(j + N2 * k1)];
-        Dft<N1, +1>::run(v);
+        Dft<N1, +1, false>::run(v);
 #pragma unroll
         for (int k = 0; k < N1; ++k) row[addr(j + N2 * k)] = v[k];
     }
@@ -84,24 +84,24 @@ template <int N1_, int N2_> struct RowFFT {
     //   inv_stage2_regs: v[k2] = X[k1 + N1*k2] in registers        -> row (as inv_stage2 leaves it)
     //   inv_stage1_regs: row (as inv_stage2 leaves it)             -> v[k] = x[j + N2*k] in registers (unnormalised)
     PTYB_HD static void fwd_stage1_regs(float2* row, int j, float2 (&v)[N1], const float2* twN) {
-        Dft<N1, -1>::run(v);
+        Dft<N1, -1, false>::run(v);
 #pragma unroll
         for (int k1 = 0; k1 < N1; ++k1) row[addr(j + N2 * k1)] = (k1 == 0) ? v[k1] : cmul(v[k1], tw<-1>(twN, j * k1));
     }
     PTYB_HD static void fwd_stage2_regs(const float2* row, int k1, float2 (&v)[N2]) {
 #pragma unroll
         for (int j = 0; j < N2; ++j) v[j] = row[addr(j + N2 * k1)];
-        Dft<N2, -1>::run(v);
+        Dft<N2, -1, false>::run(v);
     }
     PTYB_HD static void inv_stage2_regs(float2* row, int k1, float2 (&v)[N2], const float2* twN) {
-        Dft<N2, +1>::run(v);
+        Dft<N2, +1, false>::run(v);
 #pragma unroll
         for (int j = 0; j < N2; ++j) row[addr(j + N2 * k1)] = (k1 == 0) ? v[j] : cmul(v[j], tw<+1>(twN, j * k1));
     }
     PTYB_HD static void inv_stage1_regs(const float2* row, int j, float2 (&v)[N1]) {
 #pragma unroll
         for (int k1 = 0; k1 < N1; ++k1) v[k1] = row[addr(j + N2 * k1)];
-        Dft<N1, +1>::run(v);
+        Dft<N1, +1, false>::run(v);
     }
 
 #ifdef __CUDACC__

