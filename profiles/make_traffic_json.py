@@ -17,8 +17,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     rep, cfg, batch, path, dominant = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5]
+    how = sys.argv[6] if len(sys.argv) > 6 else "ncu --set full --clock-control none"
     import bench
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
@@ -47,7 +48,7 @@ def main():
             a["duration_ms"] += ms(r); a["launches"] += 1
     for k, a in sections.items():
         kernels[k] = {kk: (round(v, 6) if isinstance(v, float) else v) for kk, v in a.items()}
-    json.dump(dict(source=f"ncu --set full --clock-control none, tools/prof_step.py {cfg} {path}, one launch each ({os.path.basename(rep)})",
+    json.dump(dict(source=f"{how}, tools/prof_step.py {cfg} {path}, one launch each ({os.path.basename(rep)})",
                    csrc_sha256=bench.csrc_hash(), batch=batch, path=path, dominant=dominant, kernels=kernels), sys.stdout, indent=1)
     print()
 
