@@ -81,7 +81,10 @@ template <int DIR> __device__ __forceinline__ float2 twd(const float2* tw, int e
 
 __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[32], float2* E, const float2* tw, const Geo& g) {
     Dft<32, -1>::run(v);
-    __syncthreads();                                   // earlier readers of E are done
+    // No CTA barrier before these stores: thread t writes exactly the slots E[r*CH + yl*N + x] that it alone has read (layout-R reads
+    // at the end of the previous inverse FFT, behind that FFT's CTA barrier) and that it alone filled with the ROI (cp.async, waited
+    // for by t); every other use of E by the kernels is fenced by its own barriers.  Measured: forward 1.170 -> 1.138 ms, adjoint
+    // 1.267 -> 1.250 ms at C2, S64 +1.3 % (profiles/r02/ab_first_barrier_and_early_stash.txt).
     {
         float2* p = E + g.yl * 128 + g.x;
 #pragma unroll
@@ -140,7 +143,7 @@ template <class Pre>
 __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[32], float2* E, const float2* tw, const Geo& g, Pre pre) {
     Dft<32, +1>::run(v);
     // no CTA barrier here: this warp only writes its OWN two chunks, whose only foreign readers are the layout-R reads at
-    // the end of an earlier inverse FFT, and a forward FFT (two CTA barriers) always runs between two inverse FFTs
+    // the end of an earlier inverse FFT, and a forward FFT (whose CTA barrier every thread passes after those reads) always runs between two inverse FFTs
     __syncwarp();
     {
         float2* p = E + (g.w2 + 16 * g.rsel) * CH + g.e16 * 33;

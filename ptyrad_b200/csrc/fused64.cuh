@@ -63,7 +63,10 @@ struct Geo {
 // tw[n] = exp(-2 pi i n / N), n < N (shared memory)
 __device__ __forceinline__ void fft2_R_to_F(float2 (&v)[R], float2* E, const float2* tw, const Geo& g) {
     Dft<R, -1>::run(v);
-    __syncthreads();                                   // earlier readers of E are done
+    // No CTA barrier before these stores: thread t writes exactly the slots E[r*CH + yl*N + x] that it alone has read (layout-R reads
+    // at the end of the previous inverse FFT, behind that FFT's CTA barrier) and that it alone filled with the ROI (cp.async, waited
+    // for by t); every other use of E by the kernels is fenced by its own barriers.  Measured: forward 1.170 -> 1.138 ms, adjoint
+    // 1.267 -> 1.250 ms at C2, S64 +1.3 % (profiles/r02/ab_first_barrier_and_early_stash.txt).
     {
         float2* p = E + g.yl * FN + g.x;
 #pragma unroll
@@ -121,7 +124,7 @@ __device__ __forceinline__ void fft2_F_to_R(float2 (&v)[R], float2* E, const flo
     const int j = g.e16, r = g.w2 + NW * g.rsel;
     float2* ch = E + r * CH;
     // no CTA barrier here: this half-warp only writes its OWN chunk, whose only foreign readers are the layout-R reads at the end of
-    // an earlier inverse FFT, and a forward FFT (two CTA barriers) always runs between two inverse FFTs
+    // an earlier inverse FFT, and a forward FFT (whose CTA barrier every thread passes after those reads) always runs between two inverse FFTs
     __syncwarp();
     {
         float2* p = ch + g.e16 * (R + 1);
