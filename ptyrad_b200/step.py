@@ -13,7 +13,6 @@ are never broadcast.
 from __future__ import annotations
 
 import ctypes as C
-import os
 
 import numpy as np
 import torch

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dataclasses import replace
 import numpy as np, torch
-from ptyrad_b200 import PtychoAD, CombinedLoss, _lib
+from ptyrad_b200 import PtychoAD, CombinedLoss
 from workloads import make_inputs, CONFIGS
 from oracle.ptycho_torch import oracle_step
 

@@ -16,7 +16,7 @@ orthogonalised probe modes, half-bin-shifted propagator grid.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, asdict
+from dataclasses import dataclass, asdict
 from typing import Optional
 
 import numpy as np
