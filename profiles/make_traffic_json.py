@@ -9,10 +9,20 @@ kernels, batch size or path.  Reads the report with `ncu -i <rep> --page raw --c
 import csv
 import json
 import os
+import re
 import subprocess
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def short_name(name):
+    """'void ptyb::fused128::k_forward<(bool)0, (bool)0>(ptyb::fused128::Args)' -> 'k_forward'; 'ptyb::k_adam(ptyb::AdamArgs)' -> 'k_adam'"""
+    prev = None
+    while prev != name:                                  # template arguments, innermost first
+        prev, name = name, re.sub(r"<[^<>]*>", "", name)
+    name = name.split("(")[0].strip()
+    return name.split("::")[-1].split(" ")[-1]
 
 
 def main():
@@ -36,9 +46,7 @@ def main():
     sections = {}                                       # general path: all launches of a section (one step) summed
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
-        short = name.split("<")[0].split("::")[-1].split("(")[0].strip()
-        if short.startswith("void "):
-            short = short[5:]
+        short = short_name(name)
         kernels.setdefault(short, dict(dram_read_gb=round(gb(r, "dram__bytes_read.sum"), 6), dram_write_gb=round(gb(r, "dram__bytes_write.sum"), 6),
                                        duration_ms=round(ms(r), 6)))
         sec = "adjoint_section" if short.startswith("k_bwd") else ("forward_section" if short.startswith(("k_fwd", "k_init_shift")) else None)

@@ -342,3 +342,44 @@ def test_round2_entry_points_validate_before_touching_the_device(built):
     # the workspace layout follows the batch capacity of a chunked step
     cfg.reserved[0] = 256
     assert lib.ptyb200_workspace_bytes(C.byref(cfg), 64) == lib.ptyb200_workspace_bytes(C.byref(cfg), 256)
+
+
+def test_traffic_stamps_are_well_formed_and_the_stamp_maker_reads_a_launch_csv(tmp_path):
+    """bench.py quotes `roofline.traffic` from profiles/<round>/ncu_traffic_<cfg>.json only for the build of the kernels the capture
+    was taken from (content hash of csrc + the header) and for the workload's batch.  The committed stamps must name their dominant
+    kernel, carry the workload's batch, and profiles/make_traffic_json.py must turn an `ncu --page raw --csv` launch list into one
+    (per-kernel first launch; general-path launches summed per section)."""
+    import glob
+    import json
+    import subprocess
+    import bench
+    from workloads import CONFIGS
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stamps = sorted(glob.glob(os.path.join(root, "profiles", bench.PROFILE_ROUND, "ncu_traffic_*.json")))
+    assert stamps, "no traffic stamps committed for this round"
+    for p in stamps:
+        d = json.load(open(p))
+        cfg = os.path.basename(p)[len("ncu_traffic_"):-len(".json")]
+        assert d["batch"] == CONFIGS[cfg].batch and d["path"] == "auto", p
+        k = d["kernels"][d["dominant"]]
+        assert k["dram_read_gb"] + k["dram_write_gb"] > 0 and k["duration_ms"] > 0, p
+        assert re.fullmatch(r"[0-9a-f]{16}", d["csrc_sha256"]), p
+    assert re.fullmatch(r"[0-9a-f]{16}", bench.csrc_hash())
+    # the stamp maker on a hand-made launch list: two general-path launches per section + one unrelated kernel
+    csv_path = tmp_path / "launches.csv"
+    rows = [('"ID"', '"Kernel Name"', '"dram__bytes_read.sum"', '"dram__bytes_write.sum"', '"gpu__time_duration.sum"'),
+            ('""', '""', '"Gbyte"', '"Mbyte"', '"us"'),
+            ('"0"', '"void ptyb::k_fwd_da<(int)256>(ptyb::Args)"', '"1.5"', '"500"', '"250"'),
+            ('"1"', '"void ptyb::k_fwd_bc<(int)256>(ptyb::Args)"', '"0.5"', '"250"', '"150"'),
+            ('"2"', '"void ptyb::k_bwd_da<(int)256>(ptyb::Args)"', '"2"', '"1000"', '"400"'),
+            ('"3"', '"void ptyb::k_bwd_bc<(int)256>(ptyb::Args)"', '"1"', '"0"', '"100"'),
+            ('"4"', '"ptyb::k_adam(ptyb::AdamArgs)"', '"0.01"', '"10"', '"5"')]
+    csv_path.write_text("\n".join(",".join(r) for r in rows) + "\n")
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "make_traffic_json.py"), str(csv_path), "C4", "256", "auto",
+                          "adjoint_section", "hand-made"], capture_output=True, text=True, check=True).stdout
+    d = json.loads(out)
+    assert d["csrc_sha256"] == bench.csrc_hash() and d["dominant"] == "adjoint_section" and d["source"].startswith("hand-made")
+    a, f = d["kernels"]["adjoint_section"], d["kernels"]["forward_section"]
+    assert a["launches"] == 2 and abs(a["dram_read_gb"] - 3.0) < 1e-9 and abs(a["dram_write_gb"] - 1.0) < 1e-9 and abs(a["duration_ms"] - 0.5) < 1e-9
+    assert f["launches"] == 2 and abs(f["dram_read_gb"] - 2.0) < 1e-9 and abs(f["dram_write_gb"] - 0.75) < 1e-9 and abs(f["duration_ms"] - 0.4) < 1e-9
+    assert abs(d["kernels"]["k_adam"]["dram_write_gb"] - 0.01) < 1e-9
