@@ -230,6 +230,18 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # the library normally arrives built (driver's build()); on a box without it local rank 0 compiles, the others wait for the file
+    from ptyrad_b200 import _lib as _libmod
+    if not os.path.exists(_libmod.LIB_PATH):
+        if local_rank == 0:
+            from ptyrad_b200.build import build_library
+            build_library()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(_libmod.LIB_PATH):
+                if time.time() - t_wait > 900:
+                    raise SystemExit(f"{_libmod.LIB_PATH} did not appear within 15 min")
+                time.sleep(1.0)
     import torch
     import torch.distributed as dist
     from ptyrad_b200 import PtychoAD, CombinedLoss, MeasurementView, _lib

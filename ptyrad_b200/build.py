@@ -24,11 +24,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = f"{OUT}.{os.getpid()}.tmp"                       # built aside and renamed: a concurrent loader never sees a partial file
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libptyrad_b200.so")
+    os.replace(tmp, OUT)
     if verbose:
         sys.stderr.write(r.stderr)
     return OUT
