@@ -45,6 +45,11 @@ def main():
         batch = np.sort(rng.choice(cfg.scan ** 2, nglobal, replace=False)).astype(np.int64)
         mine = shard_indices(batch, rank, world)
         ref = ddp_emulated_grads(iv, mp, lp, batch, world, torch.float64)
+        # Shift / tilt sums of a handful of positions nearly cancel; where float32 itself cannot resolve them to TOL (T256, 3 positions per
+        # rank: the float32 run of the same expressions is 5.2e-4 away from float64) the bound is twice the float32 restatement's error.
+        r32 = ddp_emulated_grads(iv, mp, lp, batch, world, torch.float32)
+        tol = {k: (max(TOL[k], 2.0 * rel(np.asarray(r32[k], np.float64), g)) if k in ("probe_pos_shifts", "obj_tilts") else TOL[k])
+               for k, g in ref.items()}
         for mode in ("eager", "graph"):
             model = PtychoAD(iv, mp, device=dev, verbose=False)
             loss_fn = CombinedLoss(lp, device=dev)
@@ -57,9 +62,9 @@ def main():
             torch.cuda.synchronize()
             for k, g in ref.items():
                 e = rel(model.optimizable_tensors[k].grad.cpu().numpy(), g)
-                ok = e < TOL[k]
+                ok = e < tol[k]
                 if rank == 0:
-                    print(f"{cfg_name:5s} {mode:5s} world={world} grad {k:18s} {e:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+                    print(f"{cfg_name:5s} {mode:5s} world={world} grad {k:18s} {e:.2e} (bound {tol[k]:.1e}) {'ok' if ok else 'FAIL'}", flush=True)
                 if not ok:
                     fails.append((cfg_name, mode, k, e))
         # several real Adam steps through the graph: all ranks must end with bit-identical parameters
